@@ -1,0 +1,419 @@
+"""`FeedForwardTransformer` -- drop-in for the class of the same name in the reference's
+fastspeech.py (:28-387), with the mel-synthesis forward path running on libfs2b200.so.
+
+Surface kept from the reference:
+  __init__(idim, odim, hp)          hp = the reference's HParam Dotdict (or any mapping)
+  forward(xs, ilens, ys, olens, ds, es, ps) -> (loss, report_keys)     fastspeech.py:245-337
+  inference(x) -> [L, odim]                                            fastspeech.py:339-357
+  _forward(xs, ilens, olens=None, ds=None, es=None, ps=None, is_inference=False) -> 5-tuple
+  nn.Module behaviour: parameters()/state_dict()/load_state_dict() with the reference's 225
+  keys, .to(), .eval()/.train().
+
+The sub-modules below are *parameter holders* laid out so that `state_dict()` has the
+reference's keys in the reference's order; they carry no PyTorch compute graph.  All
+arithmetic happens in hand-written sm_100a kernels behind the C ABI (include/fs2_b200.h).
+There is no CPU path and no PyTorch fallback: CPU tensors, a missing library or train mode
+raise.  Train-mode forward/backward (dropout, BatchNorm batch statistics, autograd) is the
+next scope item and raises NotImplementedError today.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib
+from . import length_regulator as _lr
+from .weights import ModelDims, positional_table, variance_bins
+
+DEFAULT_PRECISION = os.environ.get("FS2_PRECISION", "fp32")
+
+
+def _get(node: Any, key: str, default: Any = None) -> Any:
+    if isinstance(node, dict):
+        return node.get(key, default)
+    return getattr(node, key, default)
+
+
+def dims_from_hp(idim: int, odim: int, hp: Any) -> ModelDims:
+    """Read the shape-defining subset of `hp` (fastspeech.py:53-160) and reject what the kernels
+    do not implement, loudly."""
+    m, d = _get(hp, "model"), _get(hp, "data")
+    if m is None or d is None:
+        raise ValueError("hp must provide .model and .data (utils/hparams.py HParam)")
+
+    def need(cond: bool, what: str):
+        if not cond:
+            raise NotImplementedError(f"fastspeech2_b200 supports the configs/default.yaml architecture only: {what}")
+
+    need(_get(m, "positionwise_layer_type", "conv1d") == "conv1d", "positionwise_layer_type must be 'conv1d'")
+    need(not _get(m, "encoder_normalize_before", False) and not _get(m, "decoder_normalize_before", False), "post-LN blocks only")
+    need(not _get(m, "encoder_concat_after", False) and not _get(m, "decoder_concat_after", False), "concat_after=False only")
+    need(bool(_get(m, "use_scaled_pos_enc", True)), "use_scaled_pos_enc=True only")
+    need(bool(_get(m, "use_batch_norm", True)), "use_batch_norm=True only")
+    need(int(_get(m, "reduction_factor", 1)) == 1, "reduction_factor=1 only")
+    need(int(_get(m, "postnet_layers", 5)) >= 1, "postnet_layers >= 1")
+    return ModelDims(
+        idim=int(idim), odim=int(odim), adim=int(_get(m, "adim")),
+        aheads=int(_get(m, "aheads")), elayers=int(_get(m, "elayers")), eunits=int(_get(m, "eunits")),
+        ddim=int(_get(m, "ddim")), dlayers=int(_get(m, "dlayers")), dunits=int(_get(m, "dunits")),
+        ffn_kernel=int(_get(m, "positionwise_conv_kernel_size")),
+        # DurationPredictor honours hp; Energy/PitchPredictor hard-code VariancePredictor(idim)
+        # defaults 2 x 256 x k3 (variance_predictor.py:125,198).  One shape for all three is
+        # what default.yaml yields; anything else is rejected.
+        pred_layers=int(_get(m, "duration_predictor_layers")), pred_chans=int(_get(m, "duration_predictor_chans")),
+        pred_kernel=int(_get(m, "duration_predictor_kernel_size")),
+        postnet_layers=int(_get(m, "postnet_layers")), postnet_chans=int(_get(m, "postnet_chans")),
+        postnet_filts=int(_get(m, "postnet_filts")),
+        e_min=float(_get(d, "e_min")), e_max=float(_get(d, "e_max")), p_min=float(_get(d, "p_min")), p_max=float(_get(d, "p_max")),
+    )
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter holders (checkpoint layout only)
+# ------------------------------------------------------------------------------------------------
+class _Holder(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("parameter holder: the forward path runs in libfs2b200.so, not in torch modules")
+
+
+class _ScaledPosEnc(_Holder):
+    def __init__(self, d_model: int, max_len: int):
+        super().__init__()
+        self.alpha = nn.Parameter(torch.tensor(1.0))
+        self.register_buffer("pe", positional_table(max_len, d_model))
+
+
+class _SelfAttn(_Holder):
+    def __init__(self, C_: int):
+        super().__init__()
+        self.linear_q, self.linear_k = nn.Linear(C_, C_), nn.Linear(C_, C_)
+        self.linear_v, self.linear_out = nn.Linear(C_, C_), nn.Linear(C_, C_)
+
+
+class _ConvFFN(_Holder):
+    def __init__(self, C_: int, H: int, k: int):
+        super().__init__()
+        self.w_1 = nn.Conv1d(C_, H, k, padding=(k - 1) // 2)
+        self.w_2 = nn.Conv1d(H, C_, 1)
+
+
+class _FFTBlock(_Holder):
+    def __init__(self, C_: int, H: int, k: int):
+        super().__init__()
+        self.self_attn = _SelfAttn(C_)
+        self.feed_forward = _ConvFFN(C_, H, k)
+        self.norm1, self.norm2 = nn.LayerNorm(C_), nn.LayerNorm(C_)
+        self.concat_linear = nn.Linear(2 * C_, C_)  # present in the checkpoint, unused (concat_after=False)
+
+
+class _FFTStack(_Holder):
+    def __init__(self, embed: nn.Sequential, C_: int, H: int, k: int, n: int):
+        super().__init__()
+        self.after_norm = nn.LayerNorm(C_)  # present in the checkpoint, unused (normalize_before=False)
+        self.embed = embed
+        self.encoders_ = nn.ModuleList([_FFTBlock(C_, H, k) for _ in range(n)])
+
+
+class _ChannelNorm(_Holder):
+    def __init__(self, n: int):
+        super().__init__()
+        self.layer_norm = nn.LayerNorm(n, eps=1e-12)
+
+
+class _ConvPredictor(_Holder):
+    def __init__(self, cin: int, layers: int, chans: int, k: int):
+        super().__init__()
+        self.conv = nn.ModuleList([
+            nn.Sequential(nn.Conv1d(cin if i == 0 else chans, chans, k, padding=(k - 1) // 2), nn.ReLU(), _ChannelNorm(chans),
+                          nn.Dropout(0.5)) for i in range(layers)])
+        self.linear = nn.Linear(chans, 1)
+
+
+class _BinnedPredictor(_Holder):
+    """Energy / Pitch predictor: bins buffer + conv predictor (variance_predictor.py:98-232)."""
+
+    def __init__(self, bins_name: str, bins: torch.Tensor, dims: ModelDims):
+        super().__init__()
+        self.register_buffer(bins_name, bins)
+        self.predictor = _ConvPredictor(dims.adim, dims.pred_layers, dims.pred_chans, dims.pred_kernel)
+        self._bins_name = bins_name
+        self._n_bins = dims.n_bins
+
+    def to_one_hot(self, x: torch.Tensor) -> torch.Tensor:
+        """bucketize + one_hot(256).float() (variance_predictor.py:154-159 / :227-232) on the GPU kernels."""
+        lib = _lib.load()
+        bins = getattr(self, self._bins_name)
+        xs = x.contiguous().float()
+        ids = torch.empty(xs.shape, dtype=torch.int64, device=xs.device)
+        st = _lib.stream_ptr(xs.device)
+        _lib.check(lib.fs2_bucketize(_lib.ptr(xs), _lib.ptr(bins), bins.numel(), xs.numel(), _lib.ptr(ids), st), "fs2_bucketize")
+        out = torch.empty(tuple(xs.shape) + (self._n_bins,), dtype=torch.float32, device=xs.device)
+        _lib.check(lib.fs2_one_hot(_lib.ptr(ids), ids.numel(), self._n_bins, _lib.ptr(out), st), "fs2_one_hot")
+        return out
+
+
+class _Postnet(_Holder):
+    def __init__(self, dims: ModelDims):
+        super().__init__()
+        layers = []
+        for i in range(dims.postnet_layers):
+            cin = dims.odim if i == 0 else dims.postnet_chans
+            cout = dims.odim if i == dims.postnet_layers - 1 else dims.postnet_chans
+            mods: List[nn.Module] = [nn.Conv1d(cin, cout, dims.postnet_filts, padding=(dims.postnet_filts - 1) // 2, bias=False),
+                                     nn.BatchNorm1d(cout)]
+            if i < dims.postnet_layers - 1:
+                mods.append(nn.Tanh())
+            mods.append(nn.Dropout(0.5))
+            layers.append(nn.Sequential(*mods))
+        self.postnet = nn.ModuleList(layers)
+
+
+def _init_like_reference(model: nn.Module, init_type: str) -> None:
+    """core/modules.py:51-81 `initialize`."""
+    if init_type == "pytorch":
+        return
+    fns = {"xavier_uniform": nn.init.xavier_uniform_, "xavier_normal": nn.init.xavier_normal_,
+           "kaiming_uniform": lambda p: nn.init.kaiming_uniform_(p, nonlinearity="relu"),
+           "kaiming_normal": lambda p: nn.init.kaiming_normal_(p, nonlinearity="relu")}
+    if init_type not in fns:
+        raise ValueError("Unknown initialization: " + init_type)
+    for p in model.parameters():
+        if p.dim() > 1:
+            fns[init_type](p.data)
+    for p in model.parameters():
+        if p.dim() == 1:
+            p.data.zero_()
+    for m in model.modules():
+        if isinstance(m, (nn.Embedding, nn.LayerNorm)):
+            m.reset_parameters()
+
+
+# ------------------------------------------------------------------------------------------------
+class FeedForwardTransformer(nn.Module):
+    """Feed-forward Transformer TTS (FastSpeech2) on B200.  See module docstring."""
+
+    def __init__(self, idim: int, odim: int, hp: Dict, precision: Optional[str] = None):
+        super().__init__()
+        dims = dims_from_hp(idim, odim, hp)
+        self.dims = dims
+        self.idim, self.odim = idim, odim
+        m = _get(hp, "model")
+        self.use_scaled_pos_enc = bool(_get(m, "use_scaled_pos_enc", True))
+        self.use_masking = bool(_get(m, "use_masking", True))
+        self.use_weighted_masking = bool(_get(m, "use_weighted_masking", False))
+        if not self.use_masking or self.use_weighted_masking:
+            raise NotImplementedError("loss kernels implement use_masking=True, use_weighted_masking=False (configs/default.yaml:57-58)")
+        self.precision = precision or DEFAULT_PRECISION
+        if self.precision not in _lib.MATH_MODES:
+            raise ValueError(f"precision must be one of {sorted(_lib.MATH_MODES)}")
+
+        A, D = dims.adim, dims.ddim
+        self.encoder = _FFTStack(nn.Sequential(nn.Embedding(idim, A, padding_idx=0), _ScaledPosEnc(A, dims.pe_len)),
+                                 A, dims.eunits, dims.ffn_kernel, dims.elayers)
+        self.duration_predictor = _ConvPredictor(A, dims.pred_layers, dims.pred_chans, dims.pred_kernel)
+        e_bins, p_bins = variance_bins(dims)
+        self.energy_predictor = _BinnedPredictor("energy_bins", e_bins, dims)
+        self.energy_embed = nn.Linear(dims.n_bins, A)
+        self.pitch_predictor = _BinnedPredictor("pitch_bins", p_bins, dims)
+        self.pitch_embed = nn.Linear(dims.n_bins, A)
+        self.length_regulator = _lr.LengthRegulator()
+        self.decoder = _FFTStack(nn.Sequential(nn.Linear(A, D), nn.LayerNorm(D), nn.Dropout(0.2), nn.ReLU(), _ScaledPosEnc(D, dims.pe_len)),
+                                 D, dims.dunits, dims.ffn_kernel, dims.dlayers)
+        self.postnet = _Postnet(dims)
+        self.feat_out = nn.Linear(D, odim)
+
+        _init_like_reference(self, str(_get(m, "transformer_init", "pytorch")))
+        self.encoder.embed[-1].alpha.data = torch.tensor(float(_get(m, "initial_encoder_alpha", 1.0)))
+        self.decoder.embed[-1].alpha.data = torch.tensor(float(_get(m, "initial_decoder_alpha", 1.0)))
+
+        self._handle: Optional[C.c_void_p] = None
+        self._handle_device: Optional[torch.device] = None
+        self._fingerprint: Optional[Tuple] = None
+        self._workspace: Optional[torch.Tensor] = None
+        self._keepalive: List[Any] = []
+
+    # -- library plumbing --------------------------------------------------------------------
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                _lib.load().fs2_destroy(self._handle)
+        except Exception:
+            pass
+
+    def _device(self) -> torch.device:
+        return self.feat_out.weight.device
+
+    def _current_fingerprint(self) -> Tuple:
+        return tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
+
+    def _ready(self, like: torch.Tensor) -> C.c_void_p:
+        """Handle with weights packed for the current parameters (repacks after load_state_dict,
+        .to(), optimizer steps ...)."""
+        if self.training:
+            raise NotImplementedError(
+                "fastspeech2_b200 implements the eval-mode forward path; call model.eval(). Train-mode forward/backward "
+                "(dropout, BatchNorm batch statistics, autograd) is not implemented and there is no silent fallback.")
+        dev = self._device()
+        if dev.type != "cuda":
+            raise _lib.Fs2Error("model parameters are on %s: the B200 path has no CPU fallback, call model.to('cuda')" % dev)
+        if like.device != dev:
+            raise _lib.Fs2Error(f"input on {like.device} but model on {dev}")
+        lib = _lib.load()
+        if self._handle is None or self._handle_device != dev:
+            if self._handle is not None:
+                lib.fs2_destroy(self._handle)
+            d = self.dims
+            cfg = _lib.Config(d.idim, d.odim, d.adim, d.aheads, d.elayers, d.eunits, d.ddim, d.dlayers, d.dunits, d.ffn_kernel,
+                              d.pred_layers, d.pred_chans, d.pred_kernel, d.postnet_layers, d.postnet_chans, d.postnet_filts,
+                              d.n_bins, d.pe_len, _lib.MATH_MODES[self.precision])
+            h = C.c_void_p()
+            _lib.check(lib.fs2_create(C.byref(h), C.byref(cfg), dev.index if dev.index is not None else torch.cuda.current_device()), "fs2_create")
+            self._handle, self._handle_device, self._fingerprint = h, dev, None
+        fp = self._current_fingerprint()
+        if fp != self._fingerprint:
+            sd = self.state_dict(keep_vars=True)
+            descs = (_lib.WeightDesc * len(sd))()
+            keep = []
+            for i, (k, t) in enumerate(sd.items()):
+                t = t.detach()
+                if t.dtype not in (torch.float32, torch.int64):
+                    raise _lib.Fs2Error(f"parameter {k} is {t.dtype}: the path is fp32-only like the reference (variance_predictor.py:159)")
+                t = t.contiguous()
+                keep.append(t)
+                name = k.encode()
+                keep.append(name)
+                shape = (C.c_int64 * 4)(*([int(s) for s in t.shape] + [0] * (4 - t.dim())))
+                descs[i] = _lib.WeightDesc(name, t.data_ptr(), t.dim(), shape, 0 if t.dtype == torch.float32 else 1)
+            _lib.check(lib.fs2_load_weights(self._handle, descs, len(sd), _lib.stream_ptr(dev)), "fs2_load_weights")
+            self._fingerprint = fp
+        _lib.check(lib.fs2_set_math_mode(self._handle, _lib.MATH_MODES[self.precision]), "fs2_set_math_mode")
+        return self._handle
+
+    def _ws(self, B: int, T: int, L: int) -> torch.Tensor:
+        lib = _lib.load()
+        need = C.c_size_t()
+        _lib.check(lib.fs2_workspace_bytes(self._handle, B, T, L, C.byref(need)), "fs2_workspace_bytes")
+        dev = self._device()
+        if self._workspace is None or self._workspace.device != dev or self._workspace.numel() < need.value:
+            self._workspace = None
+            self._workspace = torch.empty(int(need.value), dtype=torch.uint8, device=dev)
+        return self._workspace
+
+    # -- the path ----------------------------------------------------------------------------
+    def _forward(self, xs: torch.Tensor, ilens: torch.Tensor, olens: torch.Tensor = None, ds: torch.Tensor = None,
+                 es: torch.Tensor = None, ps: torch.Tensor = None, is_inference: bool = False,
+                 _one_hot: bool = True) -> Sequence[torch.Tensor]:
+        h = self._ready(xs)
+        lib = _lib.load()
+        dev, d = xs.device, self.dims
+        st = _lib.stream_ptr(dev)
+        if xs.dim() != 2:
+            raise ValueError("xs must be [B, Tmax]")
+        B, T = xs.shape
+        xs = xs.to(torch.int64).contiguous()
+        ilens = ilens.to(device=dev, dtype=torch.int64).contiguous()
+        f32 = dict(dtype=torch.float32, device=dev)
+
+        if is_inference:
+            L_known = None
+        else:
+            if olens is None or ds is None or es is None or ps is None:
+                raise ValueError("teacher-forced _forward needs olens, ds, es and ps (fastspeech.py:197-216)")
+            L_known = int(es.shape[1])
+            if ps.shape != es.shape or es.shape[0] != B:
+                raise ValueError(f"es {tuple(es.shape)} / ps {tuple(ps.shape)} must both be [B, Lmax]")
+
+        # stage 1: encoder + duration predictor
+        ws = self._ws(B, T, L_known or 0)
+        hs = torch.empty((B, T, d.adim), **f32)
+        d_log = None if is_inference else torch.empty((B, T), **f32)
+        d_int = torch.empty((B, T), dtype=torch.int64, device=dev) if is_inference else None
+        _lib.check(lib.fs2_encode(h, _lib.ptr(xs), _lib.ptr(ilens), B, T, _lib.ptr(hs), _lib.ptr(d_log), _lib.ptr(d_int),
+                                  _lib.ptr(ws), ws.numel(), st), "fs2_encode")
+
+        # stage 2: length regulator
+        cum, olens_lr, stats, _ = _lr.plan(hs, d_int if is_inference else ds, ilens, 1.0)
+        if is_inference:
+            lmax, n_neg = stats.tolist()  # the single host sync of inference: sizes the mel buffers
+            L = int(lmax)
+            if L <= 0:
+                raise RuntimeError("inference produced zero frames")
+            olens_dec = None  # decoder unmasked, fastspeech.py:221-224
+        else:
+            L = L_known
+            olens_dec = olens.to(device=dev, dtype=torch.int64).contiguous()
+        hm = _lr.gather(hs, cum, ilens, L)
+
+        # stage 3: variance adaptor + decoder + postnet
+        ws = self._ws(B, T, L)
+        before = torch.empty((B, L, d.odim), **f32)
+        after = torch.empty((B, L, d.odim), **f32)
+        e_out, p_out = torch.empty((B, L), **f32), torch.empty((B, L), **f32)
+        want_ids = is_inference and _one_hot
+        e_ids = torch.empty((B, L), dtype=torch.int64, device=dev) if want_ids else None
+        p_ids = torch.empty((B, L), dtype=torch.int64, device=dev) if want_ids else None
+        es_c = None if is_inference else es.to(**f32).contiguous()
+        ps_c = None if is_inference else ps.to(**f32).contiguous()
+        _lib.check(lib.fs2_decode(h, _lib.ptr(hm), _lib.ptr(olens_dec), _lib.ptr(es_c), _lib.ptr(ps_c), B, L, _lib.ptr(before),
+                                  _lib.ptr(after), _lib.ptr(e_out), _lib.ptr(p_out), _lib.ptr(e_ids), _lib.ptr(p_ids),
+                                  _lib.ptr(ws), ws.numel(), st), "fs2_decode")
+
+        if is_inference:
+            if not _one_hot:
+                return before, after, d_int, None, None
+            oh_e = torch.empty((B, L, d.n_bins), **f32)
+            oh_p = torch.empty((B, L, d.n_bins), **f32)
+            _lib.check(lib.fs2_one_hot(_lib.ptr(e_ids), B * L, d.n_bins, _lib.ptr(oh_e), st), "fs2_one_hot")
+            _lib.check(lib.fs2_one_hot(_lib.ptr(p_ids), B * L, d.n_bins, _lib.ptr(oh_p), st), "fs2_one_hot")
+            return before, after, d_int, oh_e, oh_p
+
+        # teacher-forced: validate what the reference would have tripped over with shape errors
+        # (mask widths are max(lengths): utils/util.py:262-272), one host read at the end.
+        chk = torch.stack([stats[0], stats[1], ilens.max(), olens_dec.max()]).tolist()
+        if chk[1]:
+            raise RuntimeError(f"LengthRegulator: {chk[1]} negative duration(s)")
+        if chk[2] != T:
+            raise RuntimeError(f"xs has Tmax={T} but max(ilens)={chk[2]} (the reference's masks are max(ilens) wide)")
+        if chk[0] != L or chk[3] != L:
+            raise RuntimeError(f"length mismatch: es/ps have Lmax={L}, max(sum(ds))={chk[0]}, max(olens)={chk[3]}")
+        return before, after, d_log, e_out, p_out
+
+    def forward(self, xs: torch.Tensor, ilens: torch.Tensor, ys: torch.Tensor, olens: torch.Tensor, ds: torch.Tensor,
+                es: torch.Tensor, ps: torch.Tensor) -> Tuple[torch.Tensor, List[Dict[str, float]]]:
+        """Eval-mode loss computation (fastspeech.py:245-337). Returns (loss, report_keys)."""
+        self._ready(xs)
+        lib = _lib.load()
+        dev = xs.device
+        ilens = ilens.to(device=dev, dtype=torch.int64)
+        olens = olens.to(device=dev, dtype=torch.int64)
+        tmax, lmax = torch.stack([ilens.max(), olens.max()]).tolist()
+        xs = xs[:, :tmax]  # fastspeech.py:266-267
+        ds_t = ds[:, :tmax].contiguous() if ds.shape[1] != tmax else ds
+        es_t, ps_t = es[:, :lmax], ps[:, :lmax]
+        before, after, d_outs, e_outs, p_outs = self._forward(xs, ilens, olens, ds_t, es_t, ps_t, is_inference=False)
+        if ds_t is not ds and ds_t.shape == ds[:, :tmax].shape:
+            ds[:, :tmax].copy_(ds_t)
+        B, T = xs.shape
+        L = before.shape[1]
+        ys_c = ys.to(dtype=torch.float32, device=dev).contiguous()
+        es_c, ps_c = es_t.to(torch.float32).contiguous(), ps_t.to(torch.float32).contiguous()
+        ds_c = ds_t.contiguous()
+        out7 = torch.empty((7,), dtype=torch.float32, device=dev)
+        scratch = torch.empty((16,), dtype=torch.float64, device=dev)
+        _lib.check(lib.fs2_masked_losses(_lib.ptr(before), _lib.ptr(after), _lib.ptr(ys_c), int(ys_c.shape[1]), _lib.ptr(d_outs),
+                                         _lib.ptr(ds_c), _lib.dur_dtype(ds_c), _lib.ptr(e_outs), _lib.ptr(p_outs), _lib.ptr(es_c),
+                                         _lib.ptr(ps_c), _lib.ptr(ilens.contiguous()), _lib.ptr(olens.contiguous()), B, T, L,
+                                         self.odim, _lib.ptr(out7), _lib.ptr(scratch), _lib.stream_ptr(dev)), "fs2_masked_losses")
+        vals = out7.tolist()
+        names = ["l1_loss", "before_loss", "after_loss", "duration_loss", "energy_loss", "pitch_loss", "loss"]
+        return out7[6], [{k: v} for k, v in zip(names, vals)]
+
+    def inference(self, x: torch.Tensor) -> torch.Tensor:
+        """x [T] int64 -> mel [L, odim] (fastspeech.py:339-357)."""
+        ilens = torch.tensor([x.shape[0]], dtype=torch.long, device=x.device)
+        _, outs, _, _, _ = self._forward(x.unsqueeze(0), ilens, is_inference=True, _one_hot=False)
+        return outs[0]

@@ -1,0 +1,33 @@
+"""Minimal attribute-access config so the package is usable without the reference's
+utils/hparams.py.  The reference's own `HParam` object is accepted unchanged by
+`FeedForwardTransformer` (it is a dict subclass with attribute access too)."""
+from __future__ import annotations
+
+import os
+
+import yaml
+
+DEFAULT_YAML = os.path.join(os.path.dirname(os.path.abspath(__file__)), "configs", "default.yaml")
+
+
+class AttrDict(dict):
+    """dict whose keys are also attributes; nested mappings are converted recursively."""
+
+    def __init__(self, mapping=None):
+        super().__init__()
+        for k, v in (mapping or {}).items():
+            self[k] = AttrDict(v) if isinstance(v, dict) else v
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def load_hp(path: str = DEFAULT_YAML) -> AttrDict:
+    with open(path) as f:
+        return AttrDict(yaml.safe_load(f))

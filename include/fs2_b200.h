@@ -1,0 +1,165 @@
+/*
+ * fs2_b200.h -- C ABI of libfs2b200.so, the sm_100a FastSpeech2 mel-synthesis forward path.
+ *
+ * The reference (rishikksh20/FastSpeech2) has no FFI layer: its operator API for this
+ * path is the Python class `FeedForwardTransformer` in fastspeech.py, whose stages call
+ * torch.nn modules.  Each entry point below replaces one stage of
+ * `FeedForwardTransformer._forward` (fastspeech.py:169-243) / `forward` (:245-337); the
+ * reference lines a function replaces are cited at its declaration.  The Python class in
+ * fastspeech2_b200/fastspeech.py binds these with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types in signatures.
+ *   - every function returns 0 on success or a negative FS2_ERR_* code;
+ *     fs2_last_error() returns a thread-local message for the last failure.
+ *   - all tensor pointers are DEVICE pointers (fp32 row-major [batch, time, channel],
+ *     lengths / ids / durations int64) unless a parameter says "host".
+ *   - the caller owns every input, output and workspace buffer; the library owns only the
+ *     opaque handle (packed weights, TMA descriptors, launch plans).
+ *   - all work is enqueued on the `stream` argument (a cudaStream_t passed as void*);
+ *     no function synchronises the device.  fs2_length_plan writes its two result words to
+ *     device memory; the caller reads them back (that is the path's single host sync).
+ *   - a handle is bound to one device and is not thread-safe.
+ */
+#ifndef FS2_B200_H_
+#define FS2_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FS2_OK 0
+#define FS2_ERR_INVALID (-1)        /* bad argument / unsupported shape            */
+#define FS2_ERR_CUDA (-2)           /* a CUDA runtime / driver call failed         */
+#define FS2_ERR_MISSING_WEIGHT (-3) /* fs2_load_weights: a required key is absent  */
+#define FS2_ERR_WORKSPACE (-4)      /* workspace too small                         */
+#define FS2_ERR_NOT_LOADED (-5)     /* stage called before fs2_load_weights        */
+
+/* duration dtypes accepted by the length regulator (tests/test_fastspeech2.py:17 feeds floats) */
+#define FS2_DUR_I64 0
+#define FS2_DUR_F32 1
+#define FS2_DUR_I32 2
+
+/* arithmetic of the dense contractions of the decoder side (decoder embed, decoder FFT
+ * blocks, mel linear, Postnet).  The encoder, the three predictors and every integer /
+ * normalisation / gather kernel always run in fp32. */
+#define FS2_MATH_FP32 0 /* fp32 FMA on CUDA cores everywhere                                 */
+#define FS2_MATH_TF32 1 /* tcgen05 kind::tf32 tensor-core tiles fed by TMA, fp32 accumulate  */
+
+typedef struct fs2_handle fs2_handle;
+
+/* Shapes of the network: the subset of `hp` read by FeedForwardTransformer.__init__
+ * (fastspeech.py:37-160; values in configs/default.yaml:38-106). */
+typedef struct fs2_config {
+  int32_t idim, odim;               /* 68 symbols, 80 mel bins                            */
+  int32_t adim, aheads, elayers, eunits;   /* encoder: 256, 2, 4, 1024                    */
+  int32_t ddim, dlayers, dunits;           /* decoder: 384, 4, 1024 (heads shared)        */
+  int32_t ffn_kernel;               /* positionwise_conv_kernel_size: 9                   */
+  int32_t pred_layers, pred_chans, pred_kernel; /* 2, 256, 3                              */
+  int32_t postnet_layers, postnet_chans, postnet_filts; /* 5, 256, 5                      */
+  int32_t n_bins;                   /* 256 pitch / energy buckets                         */
+  int32_t pe_len;                   /* rows of the positional table in the checkpoint     */
+  int32_t math_mode;                /* FS2_MATH_*                                         */
+} fs2_config;
+
+/* One checkpoint tensor, addressed by its reference state_dict key. */
+typedef struct fs2_weight_desc {
+  const char* name;     /* e.g. "decoder.encoders_.0.feed_forward.w_1.weight"  */
+  const void* data;     /* device pointer, contiguous                           */
+  int32_t ndim;
+  int64_t shape[4];
+  int32_t dtype;        /* 0 = float32, 1 = int64                               */
+} fs2_weight_desc;
+
+const char* fs2_last_error(void);
+/* "fs2-b200 <ver> sm_100a" ; lets the binding check it loaded the right library */
+const char* fs2_version(void);
+/* number of kernels this library has enqueued in this process (bench.py reports the per-step delta) */
+unsigned long long fs2_kernel_launches(void);
+
+/* ---- handle --------------------------------------------------------------------------- */
+/* replaces FeedForwardTransformer.__init__ shape plumbing (fastspeech.py:37-160) */
+int fs2_create(fs2_handle** out, const fs2_config* cfg, int device);
+void fs2_destroy(fs2_handle* h);
+int fs2_set_math_mode(fs2_handle* h, int math_mode);
+
+/* Repack the checkpoint into kernel layout: Conv1d [N,K,taps] -> [taps][N][K]; q/k/v Linear
+ * concatenated; BatchNorm1d (eval) folded into the Postnet convolutions
+ * (core/modules.py:283-348); pitch/energy embedding Linear transposed to a [bin][channel]
+ * table.  Replaces load_state_dict -> module attribute reads of the reference. */
+int fs2_load_weights(fs2_handle* h, const fs2_weight_desc* w, int n, void* stream);
+
+/* Bytes of scratch the two big stages need (max of both) for a batch of B utterances,
+ * Tmax phonemes and Lmax frames. */
+int fs2_workspace_bytes(fs2_handle* h, int B, int Tmax, int Lmax, size_t* out);
+
+/* ---- stage 1: phoneme encoder + duration predictor ------------------------------------- */
+/* fastspeech.py:180-193,210: _source_mask, encoder (core/encoder.py:185-204 ->
+ * attention.py:30-74, modules.py:237-248), duration_predictor (duration_predictor.py:64-86).
+ *   xs [B,Tmax] i64 (0 = pad), ilens [B] i64
+ *   hs [B,Tmax,adim] f32 out
+ *   d_log [B,Tmax] f32 out (log-domain prediction, 0 at pads)           -- may be NULL
+ *   d_int [B,Tmax] i64 out (clamp(round(exp(x)-1),0), 0 at pads)        -- may be NULL */
+int fs2_encode(fs2_handle* h, const int64_t* xs, const int64_t* ilens, int B, int Tmax, float* hs, float* d_log,
+               int64_t* d_int, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- stage 2: LengthRegulator (needs no handle) ---------------------------------------- */
+/* core/duration_modeling/length_regulator.py:38-95 + utils/util.py:91-104.
+ * Plan: per utterance, optionally scale by alpha (round half to even, :58-59), truncate to
+ * ilens (:60-61), apply the all-zero -> all-one rule (:86-88; written back into `ds` when
+ * mutate_ds != 0, which mirrors the reference's in-place fill_ for alpha == 1), inclusive
+ * prefix sum.
+ *   ds [B,Tmax] of ds_dtype; cum [B,Tmax] i32 out; olens [B] i64 out
+ *   stats [2] i64 out (device): stats[0] = max_b olens[b], stats[1] = #negative durations */
+int fs2_length_plan(void* ds, int ds_dtype, const int64_t* ilens, float alpha, int B, int Tmax, int mutate_ds,
+                    int32_t* cum, int64_t* olens, int64_t* stats, void* stream);
+/* Gather: out[b,j,:] = hs[b, min{i: cum[b,i] > j}, :] for j < olens[b], 0 for the rest of
+ * [0,Lcap).  Bit-exact copy.  hs [B,Tmax,C], out [B,Lcap,C]; C % 4 == 0. */
+int fs2_length_gather(const float* hs, const int32_t* cum, const int64_t* ilens, int B, int Tmax, int C, float* out,
+                      int Lcap, void* stream);
+
+/* ---- stage 3: variance adaptor + mel decoder + Postnet --------------------------------- */
+/* fastspeech.py:195-238.
+ *   hm [B,L,adim] f32: length-regulated encoder states (read only)
+ *   olens [B] i64 or NULL.  NULL reproduces is_inference=True: decoder unmasked
+ *         (fastspeech.py:221-224) and e_out / p_out unmasked.
+ *   es, ps [B,L] f32 or NULL.  NULL => bucketize the predictors' own outputs (:195-196),
+ *         else bucketize the given values (:200-206).
+ *   before, after [B,L,odim] f32 out; e_out, p_out [B,L] f32 out (predictor values)
+ *   e_ids, p_ids [B,L] i64 out (bucket indices actually embedded) -- may be NULL */
+int fs2_decode(fs2_handle* h, const float* hm, const int64_t* olens, const float* es, const float* ps, int B, int L,
+               float* before, float* after, float* e_out, float* p_out, int64_t* e_ids, int64_t* p_ids, void* ws,
+               size_t ws_bytes, void* stream);
+
+/* ---- stage 4: masked losses (fastspeech.py:277-333) ------------------------------------- */
+/* out7 (device, f32): l1, before, after, duration, energy, pitch, total -- the order of
+ * report_keys (fastspeech.py:325-333).  use_masking=True, use_weighted_masking=False.
+ * scratch: >= 64 bytes of device memory (zeroed by the call). */
+int fs2_masked_losses(const float* before, const float* after, const float* ys, int ld_ys_time, const float* d_out,
+                      const void* ds, int ds_dtype, const float* e_out, const float* p_out, const float* es,
+                      const float* ps, const int64_t* ilens, const int64_t* olens, int B, int Tmax, int L, int odim,
+                      float* out7, void* scratch, void* stream);
+
+/* ---- single operators (used by the per-kernel parity tests; same kernels as the stages) - */
+/* variance_predictor.py:154-159,227-232 + fastspeech.py:218-219 */
+int fs2_bucketize(const float* vals, const float* bins, int n_edges, int64_t n, int64_t* ids, void* stream);
+/* F.one_hot(ids, n_bins).float(): the 4th/5th return value of _forward(is_inference=True) */
+int fs2_one_hot(const int64_t* ids, int64_t n, int n_bins, float* out, void* stream);
+/* out[b,t,:] = act(sum_j x[b,t+j-pad,:] . W[j] + bias) (+ resid); W [taps][N][K].
+ * math_mode selects the kernel family (FS2_MATH_*). act: 0 none, 1 relu, 2 tanh */
+int fs2_op_tap_gemm(int math_mode, const float* x, int B, int L, int K, const float* w, const float* bias, int N, int taps,
+                    int act, const float* resid, float* out, void* stream);
+/* qkv [B,L,3C] (q | k | v, heads contiguous inside each) -> ctx [B,L,C]; lens NULL => no mask */
+int fs2_op_attention(int math_mode, const float* qkv, const int64_t* lens, int B, int L, int C, int heads, float* ctx,
+                     void* stream);
+/* y = LayerNorm_C(x (+resid)) * g + b over the last dim (C in {256,384}) */
+int fs2_op_layernorm(const float* x, const float* resid, const float* g, const float* b, float eps, int64_t rows, int C,
+                     float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FS2_B200_H_ */

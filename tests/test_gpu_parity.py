@@ -1,0 +1,265 @@
+"""Parity of the CUDA path (through the C ABI) against the golden vectors of the reference
+and against the CPU oracle on seeded inputs.  Needs a B200: run with `-m gpu`.
+
+Tolerances (stated, per SURVEY.md section 7 "fp32 tolerance vs tensor cores"):
+  FS2_MATH_FP32 : max-abs <= 1e-4 on mels (output rms ~0.6; the oracle's own fp32 noise floor
+                  vs fp64 is 2.4e-6, long K=3456 fp32 reductions in a different order add ~1e-5)
+  FS2_MATH_TF32 : max-abs <= 1e-2, mean-abs <= 1e-3 on mels (tf32 operands: 10-bit mantissa)
+  integer outputs (durations, bucket ids, LengthRegulator rows): bit-exact in both modes.
+"""
+import numpy as np
+import pytest
+import torch
+
+from fastspeech2_b200 import FeedForwardTransformer, LengthRegulator, _lib
+from fastspeech2_b200.hparams import load_hp
+from fastspeech2_b200.synthetic import make_batch
+from oracle import fs2_oracle as O
+
+pytestmark = pytest.mark.gpu
+T_ = torch.from_numpy
+TOL = {"fp32": dict(max=1e-4, mean=1e-5), "tf32": dict(max=1e-2, mean=1e-3)}
+PRECISIONS = ["fp32", "tf32"]
+
+
+def close(got, want, tol, what=""):
+    got = got.detach().float().cpu().numpy().astype(np.float64)
+    want = np.asarray(want.detach().cpu().numpy() if torch.is_tensor(want) else want, dtype=np.float64)
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    err = np.abs(got - want)
+    assert err.max() <= tol["max"] and err.mean() <= tol["mean"], f"{what}: max {err.max():.3e} mean {err.mean():.3e}"
+
+
+@pytest.fixture(scope="module")
+def models(weights):
+    out = {}
+    for prec in PRECISIONS:
+        m = FeedForwardTransformer(68, 80, load_hp(), precision=prec)
+        m.load_state_dict(weights, strict=True)
+        out[prec] = m.cuda().eval()
+    return out
+
+
+def cuda(d, *keys):
+    return [T_(d[k]).cuda() if isinstance(d[k], np.ndarray) else d[k].cuda() for k in keys]
+
+
+# ---- golden vectors of the unmodified reference -------------------------------------------------
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_golden_teacher_forced(models, golden, prec):
+    g = golden("tf_ragged")
+    xs, il, ol, ds, es, ps = cuda(g, "xs", "ilens", "olens", "ds", "es", "ps")
+    with torch.no_grad():
+        b, a, d, e, p = models[prec]._forward(xs, il, ol, ds, es, ps, is_inference=False)
+    close(d, g["d_outs"], TOL["fp32"], "d_outs")       # encoder + predictors are fp32 in both modes
+    close(e, g["e_outs"], dict(max=2e-4, mean=2e-5), "e_outs")
+    close(p, g["p_outs"], dict(max=2e-4, mean=2e-5), "p_outs")
+    close(b, g["before"], TOL[prec], "before")
+    close(a, g["after"], TOL[prec], "after")
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_golden_inference_ragged(models, golden, prec):
+    g = golden("inf_ragged")
+    xs, il = cuda(g, "xs", "ilens")
+    with torch.no_grad():
+        b, a, d, eh, ph = models[prec]._forward(xs, il, is_inference=True)
+    assert d.dtype == torch.int64 and torch.equal(d.cpu(), T_(g["d_outs"]))          # bit-exact durations
+    assert eh.shape == (3, g["before"].shape[1], 256) and eh.dtype == torch.float32
+    assert torch.equal(eh.argmax(-1).cpu(), T_(g["e_ids"])) and torch.equal(ph.argmax(-1).cpu(), T_(g["p_ids"]))
+    assert float(eh.sum()) == eh.shape[0] * eh.shape[1]
+    close(b, g["before"], TOL[prec], "before")
+    close(a, g["after"], TOL[prec], "after")
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_golden_inference_single(models, golden, prec):
+    g = golden("inf_single")
+    with torch.no_grad():
+        mel = models[prec].inference(T_(g["x"]).cuda())
+    close(mel, g["mel"], TOL[prec], "mel")
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_golden_forward_loss(models, golden, prec):
+    g, gl = golden("tf_ragged"), golden("tf_ragged_loss")
+    xs, il, ys, ol, ds, es, ps = cuda(g, "xs", "ilens", "ys", "olens", "ds", "es", "ps")
+    with torch.no_grad():
+        loss, report = models[prec](xs, il, ys, ol, ds, es, ps)
+    import json, os
+    from conftest import GOLDEN
+    assert [list(r.keys())[0] for r in report] == json.load(open(os.path.join(GOLDEN, "report_keys.json")))
+    rel = 1e-4 if prec == "fp32" else 2e-3
+    got = np.array([list(r.values())[0] for r in report])
+    assert np.all(np.abs(got - gl["report"]) <= rel * np.maximum(1.0, np.abs(gl["report"]))), (got, gl["report"])
+    assert abs(float(loss) - float(gl["loss"])) <= rel * max(1.0, abs(float(gl["loss"])))
+    assert loss.dim() == 0 and loss.is_cuda
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_reference_unit_test_twin(models, golden, prec):
+    """tests/test_fastspeech2.py:7-20 with the same shapes/dtypes (float durations!) on CUDA, eval, no_grad."""
+    gl = golden("unit_shapes")
+    x = torch.ones(2, 100, dtype=torch.int64).cuda(); il = torch.tensor([100, 100]).cuda()
+    y = torch.ones(2, 100, 80).cuda(); dur = torch.ones(2, 100).cuda(); e = torch.ones(2, 100).cuda(); p = torch.ones(2, 100).cuda()
+    with torch.no_grad():
+        loss, report = models[prec](x, il, y, il.clone(), dur, e, p)
+    rel = 1e-4 if prec == "fp32" else 2e-3
+    got = np.array([list(r.values())[0] for r in report])
+    assert np.all(np.abs(got - gl["report"]) <= rel * np.maximum(1.0, np.abs(gl["report"]))), (got, gl["report"])
+
+
+def test_golden_length_regulator_bit_exact(golden):
+    g = golden("length_regulator")
+    lr = LengthRegulator()
+    hs, il = T_(g["hs"]).cuda(), T_(g["ilens"]).cuda()
+    d = T_(g["d_int"]).cuda()
+    assert torch.equal(lr(hs, d, il).cpu(), T_(g["out_int"]))
+    assert torch.equal(d.cpu(), T_(g["d_int_after"]))             # in-place all-zero -> ones
+    d = T_(g["d_int"]).cuda()
+    assert torch.equal(lr(hs, d, il, alpha=2.5).cpu(), T_(g["out_alpha"]))
+    assert torch.equal(d.cpu(), T_(g["d_alpha_after"]))           # alpha != 1: caller's ds untouched
+    d = T_(g["d_float"]).cuda()
+    assert torch.equal(lr(hs, d, il).cpu(), T_(g["out_float"]))
+    assert torch.equal(d.cpu(), T_(g["d_float_after"]))
+    with pytest.raises(RuntimeError, match="negative"):
+        lr(hs, torch.full((4, 9), -1, dtype=torch.int64).cuda(), il)
+
+
+def test_golden_bucketize(models, golden):
+    g = golden("bucketize")
+    m = models["fp32"]
+    assert torch.equal(m.energy_predictor.to_one_hot(T_(g["vals_e"]).cuda()).argmax(-1).cpu(), T_(g["ids_e"]))
+    assert torch.equal(m.pitch_predictor.to_one_hot(T_(g["vals_p"]).cuda()).argmax(-1).cpu(), T_(g["ids_p"]))
+
+
+# ---- CPU oracle on seeded inputs ------------------------------------------------------------------
+def test_length_regulator_c5_stress_bit_exact():
+    """BASELINE config 5: B=256, T=100, ds~U{1..15}, alpha=4 (round half even) -> Lmax ~3.7k; ragged twin with
+    zeros and an all-zero row.  Full size, bit-exact against the oracle, plus the mutated ds."""
+    g = torch.Generator().manual_seed(5)
+    hs = torch.randn(256, 100, 256, generator=g)
+    lr = LengthRegulator()
+    for ragged in (False, True):
+        ds = torch.randint(1, 16, (256, 100), generator=g)
+        il = torch.full((256,), 100, dtype=torch.int64)
+        if ragged:
+            il = torch.randint(30, 101, (256,), generator=g); il[0] = 100
+            ds[torch.rand(256, 100, generator=g) < 0.1] = 0
+            ds[7, :] = 0
+        want_ds = ds.clone()
+        want = O.length_regulator(hs, want_ds, il, alpha=4.0)
+        got_ds = ds.clone().cuda()
+        got = lr(hs.cuda(), got_ds, il.cuda(), alpha=4.0)
+        assert got.shape == want.shape and torch.equal(got.cpu(), want)
+        assert torch.equal(got_ds.cpu(), want_ds)
+        want_ds = ds.clone(); want = O.length_regulator(hs, want_ds, il)       # alpha == 1 path mutates
+        got_ds = ds.clone().cuda(); got = lr(hs.cuda(), got_ds, il.cuda())
+        assert torch.equal(got.cpu(), want) and torch.equal(got_ds.cpu(), want_ds)
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_oracle_teacher_forced_ragged_batch(models, weights, prec):
+    """B=8 ragged LJSpeech-like batch (padding leaks into valid frames in the reference; the rectangle
+    must be reproduced): every output against the oracle on the identical padded batch."""
+    ilens = [60, 57, 49, 41, 33, 25, 12, 5]
+    olens = [480, 470, 401, 300, 259, 211, 90, 37]
+    bt = make_batch(8, 60, 480, seed=21, ilens=ilens, olens=olens)
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        want = O.forward_path(weights, bt["xs"], bt["ilens"], bt["olens"], bt["ds"].clone(), bt["es"], bt["ps"], False)
+        got = models[prec]._forward(bt["xs"].cuda(), bt["ilens"].cuda(), bt["olens"].cuda(), bt["ds"].cuda(), bt["es"].cuda(),
+                                    bt["ps"].cuda(), is_inference=False)
+    close(got[2], want[2], TOL["fp32"], "d_outs")
+    close(got[3], want[3], dict(max=2e-4, mean=2e-5), "e_outs"); close(got[4], want[4], dict(max=2e-4, mean=2e-5), "p_outs")
+    close(got[0], want[0], TOL[prec], "before"); close(got[1], want[1], TOL[prec], "after")
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_oracle_long_form(models, weights, prec):
+    """config-4 shape at reduced batch: L = 2000 frames (attention tiles, positional table, Postnet)."""
+    bt = make_batch(2, 250, 2000, seed=22, ilens=[250, 190], olens=[2000, 1603])
+    with torch.no_grad():
+        want = O.forward_path(weights, bt["xs"], bt["ilens"], bt["olens"], bt["ds"].clone(), bt["es"], bt["ps"], False)
+        got = models[prec]._forward(*[bt[k].cuda() for k in ("xs", "ilens", "olens", "ds", "es", "ps")], is_inference=False)
+    close(got[0], want[0], TOL[prec], "before"); close(got[1], want[1], TOL[prec], "after")
+
+
+def test_repack_after_weight_update(models, weights):
+    m = models["fp32"]
+    bt = make_batch(2, 20, 150, seed=23)
+    args = [bt[k].cuda() for k in ("xs", "ilens", "olens", "ds", "es", "ps")]
+    with torch.no_grad():
+        a0 = m._forward(*args)[1].clone()
+        m.feat_out.bias.add_(1.0)                      # in-place update bumps the version counter
+        a1 = m._forward(*args)[1].clone()
+        m.feat_out.bias.sub_(1.0)
+        a2 = m._forward(*args)[1]
+    assert float((a1 - a0).abs().min()) > 0.5 and torch.allclose(a2, a0, atol=1e-6)
+
+
+# ---- single kernels against plain PyTorch fp32 ----------------------------------------------------
+def _tap_gemm(mode, x, w, bias, act, resid):
+    lib = _lib.load()
+    B, L, K = x.shape
+    taps, N, _ = w.shape
+    out = torch.empty(B, L, N, device="cuda")
+    _lib.check(lib.fs2_op_tap_gemm(mode, _lib.ptr(x), B, L, K, _lib.ptr(w), _lib.ptr(bias), N, taps, act, _lib.ptr(resid),
+                                   _lib.ptr(out), _lib.stream_ptr(x.device)), "fs2_op_tap_gemm")
+    return out
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+@pytest.mark.parametrize("shape", [(3, 70, 256, 1024, 9, 1), (2, 333, 384, 384, 1, 0), (5, 41, 80, 256, 5, 2),
+                                   (2, 130, 256, 80, 5, 0), (1, 7, 1024, 384, 1, 0), (4, 100, 256, 256, 3, 1)])
+def test_tap_gemm_vs_torch(prec, shape):
+    B, L, K, N, taps, act = shape
+    g = torch.Generator().manual_seed(hash(shape) & 0xffff)
+    x = torch.randn(B, L, K, generator=g); w = torch.randn(N, K, taps, generator=g) / (K * taps) ** 0.5
+    bias = torch.randn(N, generator=g); resid = torch.randn(B, L, N, generator=g)
+    y = torch.nn.functional.conv1d(x.transpose(1, 2).double(), w.double(), bias.double(), padding=(taps - 1) // 2).transpose(1, 2)
+    y = torch.relu(y) if act == 1 else torch.tanh(y) if act == 2 else y
+    y = (y + resid.double()).float()
+    wp = w.permute(2, 0, 1).contiguous().cuda()
+    got = _tap_gemm(_lib.MATH_MODES[prec], x.cuda(), wp, bias.cuda(), act, resid.cuda())
+    tol = dict(max=2e-5, mean=2e-6) if prec == "fp32" else dict(max=1e-2, mean=1e-3)
+    close(got, y, tol, str(shape))
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+@pytest.mark.parametrize("C,L,masked", [(256, 100, True), (384, 333, True), (384, 800, False), (256, 37, False)])
+def test_attention_vs_torch(prec, C, L, masked):
+    B, H = 3, 2
+    g = torch.Generator().manual_seed(C + L)
+    qkv = torch.randn(B, L, 3 * C, generator=g)
+    lens = torch.tensor([L, max(1, L // 2), max(1, L // 7)])
+    q, k, v = [t.view(B, L, H, C // H).transpose(1, 2).double() for t in qkv.split(C, dim=-1)]
+    s = q @ k.transpose(-1, -2) / (C // H) ** 0.5
+    if masked:
+        valid = torch.arange(L)[None] < lens[:, None]
+        m = (valid[:, None, :] & valid[:, :, None])[:, None]
+        p = torch.softmax(s.masked_fill(~m, -float("inf")), -1).masked_fill(~m, 0.0)
+    else:
+        p = torch.softmax(s, -1)
+    want = (p @ v).transpose(1, 2).reshape(B, L, C).float()
+    lib = _lib.load()
+    ctx = torch.empty(B, L, C, device="cuda")
+    qkv_c, lens_c = qkv.cuda(), lens.cuda()
+    _lib.check(lib.fs2_op_attention(_lib.MATH_MODES[prec], _lib.ptr(qkv_c), _lib.ptr(lens_c) if masked else None, B, L, C, H,
+                                    _lib.ptr(ctx), _lib.stream_ptr(ctx.device)), "fs2_op_attention")
+    tol = dict(max=2e-5, mean=2e-6) if prec == "fp32" else dict(max=1e-2, mean=1e-3)
+    close(ctx, want, tol, f"attention C={C} L={L} masked={masked}")
+
+
+@pytest.mark.parametrize("C", [256, 384])
+def test_layernorm_vs_torch(C):
+    g = torch.Generator().manual_seed(C)
+    x, r = torch.randn(1000, C, generator=g) * 3, torch.randn(1000, C, generator=g)
+    w, b = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    want = torch.nn.functional.layer_norm(x + r, (C,), w, b, 1e-5)
+    out = torch.empty(1000, C, device="cuda")
+    lib = _lib.load()
+    xc, rc, wc, bc = x.cuda(), r.cuda(), w.cuda(), b.cuda()
+    _lib.check(lib.fs2_op_layernorm(_lib.ptr(xc), _lib.ptr(rc), _lib.ptr(wc), _lib.ptr(bc), 1e-5, 1000, C, _lib.ptr(out),
+                                    _lib.stream_ptr(out.device)), "fs2_op_layernorm")
+    close(out, want, dict(max=1e-5, mean=1e-6), "layernorm")

@@ -1,0 +1,83 @@
+"""Host-side logic that needs no GPU: checkpoint layout, hp validation, loud failures,
+and that the C-ABI library loads and exports every symbol include/fs2_b200.h declares."""
+import ctypes
+import json
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import GOLDEN, REPO
+from fastspeech2_b200 import FeedForwardTransformer, _lib
+from fastspeech2_b200.hparams import load_hp
+
+
+@pytest.fixture(scope="module")
+def model():
+    torch.manual_seed(0)
+    return FeedForwardTransformer(68, 80, load_hp())
+
+
+def test_state_dict_layout_matches_reference(model):
+    ref = json.load(open(os.path.join(GOLDEN, "state_dict_keys.json")))
+    sd = model.state_dict()
+    assert list(sd.keys()) == [k for k, _, _ in ref]
+    for k, shape, dtype in ref:
+        assert list(sd[k].shape) == shape and str(sd[k].dtype) == dtype, k
+
+
+def test_load_state_dict_strict(model, weights):
+    missing = model.load_state_dict(weights, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    assert torch.equal(model.state_dict()["decoder.embed.4.pe"], weights["decoder.embed.4.pe"])
+
+
+def test_fresh_init_matches_reference_conventions(model):
+    m = FeedForwardTransformer(68, 80, load_hp())
+    assert float(m.encoder.embed[-1].alpha) == 1.0 and float(m.decoder.embed[-1].alpha) == 1.0
+    assert torch.count_nonzero(m.encoder.embed[0].weight[0]) == 0          # padding_idx = 0
+    assert sum(p.numel() for p in m.parameters()) == 34015605
+
+
+def test_cpu_inputs_fail_loudly(model):
+    model.eval()
+    x = torch.ones(2, 5, dtype=torch.int64)
+    with pytest.raises(_lib.Fs2Error, match="no CPU fallback"):
+        model._forward(x, torch.tensor([5, 5]), is_inference=True)
+
+
+def test_train_mode_fails_loudly(model):
+    model.train()
+    with pytest.raises(NotImplementedError, match="eval"):
+        model._forward(torch.ones(1, 5, dtype=torch.int64), torch.tensor([5]), is_inference=True)
+    model.eval()
+
+
+def test_unsupported_hp_is_rejected():
+    hp = load_hp()
+    hp.model.positionwise_layer_type = "linear"
+    with pytest.raises(NotImplementedError):
+        FeedForwardTransformer(68, 80, hp)
+    hp = load_hp()
+    hp.model.encoder_normalize_before = True
+    with pytest.raises(NotImplementedError):
+        FeedForwardTransformer(68, 80, hp)
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(REPO, "include", "fs2_b200.h")).read()
+    declared = set(re.findall(r"\b(fs2_[a-z0-9_]+)\s*\(", header))
+    declared -= {"fs2_handle", "fs2_config", "fs2_weight_desc"}
+    assert declared == set(_lib.ALL_SYMBOLS), declared ^ set(_lib.ALL_SYMBOLS)
+    lib = ctypes.CDLL(_lib.LIB_PATH)   # loads without a GPU (cudart is linked statically)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.fs2_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.fs2_version()
+
+
+def test_library_rejects_bad_arguments_without_a_gpu():
+    lib = _lib.load()
+    assert lib.fs2_length_gather(None, None, None, 1, 1, 256, None, 8, None) == -1
+    assert b"null" in lib.fs2_last_error()
