@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""Benchmark of the FastSpeech2 mel-synthesis forward path on B200 (one process per GPU).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                  # our arm, N=1
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W      # N ranks, NCCL
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1  # reference arm (CPU)
+
+Metric (BASELINE.json): valid mel-frames/s of batched synthesis.  A "step" is one eval-mode
+`FeedForwardTransformer._forward` over one synthetic LJSpeech-shaped batch: phoneme encoder,
+duration predictor, LengthRegulator, pitch/energy predictors + embeddings, mel decoder, mel
+linear, Postnet (teacher-forced durations so the frame count is fixed),
+plus -- for N > 1 -- the single NCCL all-gather of the final mels.  Workload c2: B=64,
+T=100 phonemes, L=800 frames per utterance per GPU (weak scaling: every rank owns its shard).
+
+`value`  : whole-job frames/s with inputs resident in HBM, CUDA-event timed, max over ranks.
+`e2e`    : same through the public API with HOST (pinned) inputs: H2D of xs/ilens/olens/ds/es/ps
+           and D2H of the mel batch inside the timed region, every step.
+`roofline`: dominant kernel class (decoder conv-FFN w_1: k=9 conv 384->1024 as a tap-GEMM),
+           algorithmic FLOPs per launch / its CUDA-event duration measured by the library's
+           per-kernel-class event profiler on extra steps of this same workload.
+`cpu_baseline`: the CPU oracle port (same ATen calls as the reference, oracle/fs2_oracle.py) on a
+           bounded sample of the same workload, all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (B per GPU, T, L)
+    "c2": (64, 100, 800),     # BASELINE.json configs[1]: batch=64 LJSpeech-length on 1xB200 (headline)
+    "c4": (32, 250, 2000),    # configs[3]: long-form
+}
+HOP, SR = 256, 22050
+
+
+def mflop_per_frame(T: int, L: int) -> float:
+    """Algorithmic MFLOP (2*MAC) per valid mel frame, SURVEY.md section 8d table."""
+    fpp = L / T
+    enc = 4 * (4 * 256 ** 2 + 2 * T * 256 + 256 * 1024 * 9 + 1024 * 256) + 2 * 256 ** 2 * 3 + 256
+    var = 2 * (2 * 256 ** 2 * 3 + 256)
+    dec = 256 * 384 + 4 * (4 * 384 ** 2 + 2 * L * 384 + 384 * 1024 * 9 + 1024 * 384) + 384 * 80
+    post = 80 * 256 * 5 + 3 * 256 ** 2 * 5 + 256 * 80 * 5
+    return 2.0 * (enc / fpp + var + dec + post) / 1e6
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops"], d["bf16_tflops_sustained"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+def oracle_frames_per_s(B: int, T: int, L: int, steps: int, warmup: int):
+    """CPU oracle port on B utterances of the workload, all host threads."""
+    from fastspeech2_b200 import synthetic_state_dict
+    from fastspeech2_b200.synthetic import make_batch
+    from oracle import fs2_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synthetic_state_dict(0)
+    bt = make_batch(B, T, L, seed=1234)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.forward_path(sd, bt["xs"], bt["ilens"], bt["olens"], bt["ds"].clone(), bt["es"], bt["ps"], False)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return B * L / dt, dt, cores
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path = the oracle port (the
+    reference is pure Python over ATen; oracle/fs2_oracle.py issues the same ATen calls and is
+    pinned bit-exact to it by tests/golden).  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    B, T, L = WORKLOADS[args.workload]
+    Bs = min(B, args.cpu_sample_batch)
+    fps, dt, cores = oracle_frames_per_s(Bs, T, L, args.steps, args.warmup)
+    sample = f"{Bs} of the {B} utterances of workload {args.workload} (T={T}, L={L}) per step"
+    line = {
+        "impl": "reference", "metric": "mel-frames/sec (batched inference)", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "B_per_gpu": B, "T": T, "L": L, "mode": "teacher-forced _forward, eval, no_grad"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "rtf": (1.0 / fps) / (HOP / SR),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    from fastspeech2_b200 import FeedForwardTransformer, _lib, synthetic_state_dict
+    from fastspeech2_b200.hparams import load_hp
+    from fastspeech2_b200.synthetic import make_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    B, T, L = WORKLOADS[args.workload]
+    model = FeedForwardTransformer(68, 80, load_hp(), precision=args.precision)
+    model.load_state_dict(synthetic_state_dict(0), strict=True)
+    model = model.to(dev).eval()
+    bt = make_batch(B, T, L, seed=1234 + rank)          # rank r owns utterances [r*B, (r+1)*B)
+    keys = ("xs", "ilens", "olens", "ds", "es", "ps")
+    host = {k: bt[k].pin_memory() for k in keys}
+    devin = {k: bt[k].to(dev) for k in keys}
+    frames_rank = int(bt["olens"].sum())
+    gathered = torch.empty((world * B, L, 80), dtype=torch.float32, device=dev) if world > 1 else None
+    mel_host = torch.empty((B, L, 80), dtype=torch.float32).pin_memory()
+
+    def step(inp):
+        with torch.no_grad():
+            out = model._forward(inp["xs"], inp["ilens"], inp["olens"], inp["ds"], inp["es"], inp["ps"], is_inference=False)
+        if world > 1:   # the single exchange step: gather the final mel batch over NVLink
+            dist.all_gather_into_tensor(gathered, out[1])
+        return out[1]
+
+    def step_e2e():
+        inp = {k: host[k].to(dev, non_blocking=True) for k in keys}
+        mel = step(inp)
+        mel_host.copy_(mel, non_blocking=True)
+        return mel
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms / steps
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    n0 = lib.fs2_kernel_launches()
+    for _ in range(max(args.warmup, 3)):
+        step(devin)
+    torch.cuda.synchronize()
+    n1 = lib.fs2_kernel_launches()
+    launches_per_step = (n1 - n0) // max(args.warmup, 3)
+    if sampler:
+        sampler.start()
+    ms_step = timed(lambda: step(devin), args.steps, 0)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e = timed(step_e2e, args.steps, 2)
+
+    # per-kernel-class CUDA-event profile on extra steps of the same workload
+    prof = None
+    if rank == 0 and hasattr(lib, "fs2_profile_enable"):
+        import ctypes as C
+        h = model._handle
+        lib.fs2_profile_enable(h, 1)
+        for _ in range(3):
+            step(devin)
+        torch.cuda.synchronize()
+        n = lib.fs2_profile_classes()
+        ms = (C.c_double * n)(); cnt = (C.c_int64 * n)(); fl = (C.c_double * n)(); by = (C.c_double * n)()
+        lib.fs2_profile_read(h, ms, cnt, fl, by)
+        lib.fs2_profile_enable(h, 0)
+        prof = {lib.fs2_profile_label(i).decode(): {"ms": ms[i], "launches": cnt[i], "flop": fl[i], "bytes": by[i]}
+                for i in range(n) if cnt[i]}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm, tf_burst, tf_sus, peak_src = peaks()
+    frames = frames_rank * world
+    value = frames / (ms_step * 1e-3)
+    e2e = frames / (ms_e2e * 1e-3)
+    h2d = sum(host[k].numel() * host[k].element_size() for k in keys)
+    d2h = mel_host.numel() * 4
+    mf = mflop_per_frame(T, L)
+    tensor_peak = (tf_sus / 2.0) if args.precision == "tf32" else 2 * 148 * 128 * 1.965e9 / 1e12
+    roof = None
+    if prof:
+        tot = sum(v["ms"] for v in prof.values())
+        top = max(prof, key=lambda k: prof[k]["ms"])
+        pk = prof[top]
+        achieved = pk["flop"] / (pk["ms"] * 1e-3) / 1e12 if pk["ms"] > 0 else 0.0
+        roof = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
+                "frac": achieved / tensor_peak, "traffic": None,
+                "avg_launch_ms": pk["ms"] / pk["launches"], "share_of_step": pk["ms"] / tot,
+                "peak_source": peak_src + ("; tf32 dense = 1/2 of the measured sustained bf16 rate" if args.precision == "tf32"
+                                           else "; fp32 FMA pipe = 148 SM x 128 lanes x 2 x 1.965 GHz (nominal)"),
+                "classes": {k: {"ms_per_step": v["ms"] / 3, "launches_per_step": v["launches"] // 3,
+                                "tflops": (v["flop"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 else None,
+                                "gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else None} for k, v in prof.items()}}
+    cpu_fps, cpu_dt, cores = oracle_frames_per_s(min(B, args.cpu_sample_batch), T, L, 1, 1) if args.gpus == 1 else (None, None, None)
+    line = {
+        "metric": "mel-frames/sec (batched inference)", "value": value, "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": args.workload, "B_per_gpu": B, "global_batch": B * world, "T": T, "L": L,
+                   "mode": "teacher-forced _forward, eval, no_grad", "parallelism": f"dp{world}",
+                   "collective": "one NCCL all_gather of the [B,L,80] mel shard" if world > 1 else "none",
+                   "l2": "per-step working set ~0.9 GB of activations >> 126 MB L2; no flush needed",
+                   "tolerance": "fp32 mode: max-abs 1e-4 vs CPU oracle; tf32 mode: max-abs 1e-2, mean-abs 1e-3 (tests/test_gpu_parity.py)"},
+        "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "gpu_launches_per_step": int(launches_per_step),
+        "clocks": clocks,
+        "rtf": (1.0 / value) / (HOP / SR),
+        "model_tflops": value * mf / 1e6,
+        "mflop_per_frame": mf,
+    }
+    if roof:
+        line["roofline"] = roof
+    if cpu_fps:
+        line["cpu_baseline"] = {"value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                                "sample": f"{min(B, args.cpu_sample_batch)} of the {B} utterances of workload {args.workload}, 1 warm-up + 1 timed forward"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default=os.environ.get("FS2_PRECISION", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--cpu-sample-batch", type=int, default=8)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

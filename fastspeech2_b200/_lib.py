@@ -41,6 +41,9 @@ _P, _I, _F, _L, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t
 SIGNATURES = {
     "fs2_create": [C.POINTER(_P), C.POINTER(Config), _I],
     "fs2_set_math_mode": [_P, _I],
+    "fs2_profile_enable": [_P, _I],
+    "fs2_profile_classes": [],
+    "fs2_profile_read": [_P, C.POINTER(C.c_double), C.POINTER(_L), C.POINTER(C.c_double), C.POINTER(C.c_double)],
     "fs2_load_weights": [_P, C.POINTER(WeightDesc), _I, _P],
     "fs2_workspace_bytes": [_P, _I, _I, _I, C.POINTER(_SZ)],
     "fs2_encode": [_P, _P, _P, _I, _I, _P, _P, _P, _P, _SZ, _P],
@@ -54,7 +57,7 @@ SIGNATURES = {
     "fs2_op_attention": [_I, _P, _P, _I, _I, _I, _I, _P, _P],
     "fs2_op_layernorm": [_P, _P, _P, _P, _F, _L, _I, _P, _P],
 }
-OTHER_SYMBOLS = ("fs2_last_error", "fs2_version", "fs2_destroy", "fs2_kernel_launches")
+OTHER_SYMBOLS = ("fs2_last_error", "fs2_version", "fs2_destroy", "fs2_kernel_launches", "fs2_profile_label")
 ALL_SYMBOLS = tuple(SIGNATURES) + OTHER_SYMBOLS
 
 _lib: Optional[C.CDLL] = None
@@ -80,6 +83,8 @@ def load() -> C.CDLL:
     lib.fs2_version.argtypes = []
     lib.fs2_kernel_launches.restype = C.c_ulonglong
     lib.fs2_kernel_launches.argtypes = []
+    lib.fs2_profile_label.restype = C.c_char_p
+    lib.fs2_profile_label.argtypes = [_I]
     lib.fs2_destroy.restype = None
     lib.fs2_destroy.argtypes = [_P]
     _lib = lib

@@ -30,9 +30,40 @@ struct Norm { const float* g = nullptr; const float* b = nullptr; float eps = 1e
 struct Block { Dense qkv, out, w1, w2; Norm ln1, ln2; };
 struct Predictor { Dense conv[4]; Norm ln[4]; const float* head_w = nullptr; const float* head_b = nullptr; int layers = 0; };
 
+
+// ---- per-kernel-class CUDA-event profiler (bench.py roofline; off by default) -------------
+enum ProfClass {
+  P_EMBED, P_ENC_GEMM, P_ENC_ATTN, P_PRED_GEMM, P_ROWNORM, P_VAR_EMBED, P_DEC_IN, P_DEC_QKV, P_DEC_ATTN, P_DEC_OUT,
+  P_DEC_W1, P_DEC_W2, P_FEAT_OUT, P_POSTNET, P_COUNT
+};
+static const char* kProfLabels[P_COUNT] = {
+  "embed_posenc", "enc.tap_gemm", "enc.attention", "predictor.tap_gemm", "row_norm", "variance_embed_add", "dec.embed_linear",
+  "dec.qkv_proj", "dec.attention", "dec.out_proj", "dec.ffn_w1_conv9", "dec.ffn_w2", "feat_out", "postnet.conv5"};
+struct ProfRec { int cls; cudaEvent_t a, b; double flop, bytes; };
+struct Profiler {
+  bool on = false;
+  std::vector<ProfRec> recs;
+};
+static thread_local Profiler* t_prof = nullptr;
+struct ProfScope {
+  ProfRec r; bool live; cudaStream_t st;
+  ProfScope(int cls, double flop, double bytes, cudaStream_t s) : live(t_prof && t_prof->on), st(s) {
+    if (!live) return;
+    r.cls = cls; r.flop = flop; r.bytes = bytes;
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+  }
+  ~ProfScope() {
+    if (!live) return;
+    cudaEventRecord(r.b, st);
+    t_prof->recs.push_back(r);
+  }
+};
+
 }  // namespace fs2
 
 struct fs2_handle {
+  fs2::Profiler prof;
   fs2_config cfg;
   int device = 0;
   bool loaded = false;
@@ -68,8 +99,21 @@ struct Bump {  // bump allocator over a caller-provided (or null = counting) buf
 
 using Map = std::unordered_map<std::string, const fs2_weight_desc*>;
 
-int dense(const TapGemm& g, int math_mode, cudaStream_t st) {
+int dense(const TapGemm& g, int math_mode, cudaStream_t st, int cls) {
+  const double M = (double)g.B * g.L;
+  ProfScope prof_scope(cls, 2.0 * M * g.N * g.K * g.taps,
+               4.0 * (M * g.K + (double)g.taps * g.N * g.K + M * g.N * (g.resid ? 2 : 1)), st);
   return math_mode == FS2_MATH_TF32 ? tap_gemm_tf32(g, st) : tap_gemm_fp32(g, st);
+}
+int norm_rows(const RowNorm& r, cudaStream_t st) {
+  ProfScope prof_scope(P_ROWNORM, 8.0 * r.rows * r.C, 4.0 * r.rows * r.C * (1 + (r.resid ? 1 : 0) + (r.out ? 1 : 0)), st);
+  return row_norm(r, st);
+}
+int attention(int math_mode, const float* qkv, const int64_t* lens, int B, int L, int C, int heads, float* ctx, cudaStream_t st,
+              int cls) {
+  ProfScope prof_scope(cls, 4.0 * B * (double)L * L * C, 4.0 * 4.0 * B * (double)L * C, st);
+  return math_mode == FS2_MATH_TF32 ? attention_tf32(qkv, lens, B, L, C, heads, ctx, st)
+                                    : attention_fp32(qkv, lens, B, L, C, heads, ctx, st);
 }
 
 TapGemm make_gemm(const Dense& d, const float* x, int ldx, int B, int L, int act, const float* resid, int ldr, float* out,
@@ -89,22 +133,22 @@ RowNorm make_norm(const Norm& n, const float* x, int ldx, int64_t rows, int C, f
 
 // x <- FFT blocks(x); scratch buffers sized for [rows, .]
 int run_blocks(const std::vector<Block>& blocks, float* x, float* y, float* qkv, float* ctx, float* hid,
-               const int64_t* lens, int B, int L, int C, int heads, int math_mode, cudaStream_t st) {
+               const int64_t* lens, int B, int L, int C, int heads, int math_mode, bool is_dec, cudaStream_t st) {
   const int64_t rows = (int64_t)B * L;
+  const int c_qkv = is_dec ? P_DEC_QKV : P_ENC_GEMM, c_att = is_dec ? P_DEC_ATTN : P_ENC_ATTN;
+  const int c_out = is_dec ? P_DEC_OUT : P_ENC_GEMM, c_w1 = is_dec ? P_DEC_W1 : P_ENC_GEMM, c_w2 = is_dec ? P_DEC_W2 : P_ENC_GEMM;
   for (const Block& k : blocks) {
     int rc;
     // q | k | v projection (attention.py:48-50), one GEMM with N = 3C
-    if ((rc = dense(make_gemm(k.qkv, x, C, B, L, ACT_NONE, nullptr, 0, qkv, 3 * C), math_mode, st))) return rc;
-    rc = math_mode == FS2_MATH_TF32 ? attention_tf32(qkv, lens, B, L, C, heads, ctx, st)
-                                    : attention_fp32(qkv, lens, B, L, C, heads, ctx, st);
-    if (rc) return rc;
+    if ((rc = dense(make_gemm(k.qkv, x, C, B, L, ACT_NONE, nullptr, 0, qkv, 3 * C), math_mode, st, c_qkv))) return rc;
+    if ((rc = attention(math_mode, qkv, lens, B, L, C, heads, ctx, st, c_att))) return rc;
     // y = x + linear_out(ctx) (attention.py:74, encoder.py:60); x = LN(y) (:61-62)
-    if ((rc = dense(make_gemm(k.out, ctx, C, B, L, ACT_NONE, x, C, y, C), math_mode, st))) return rc;
-    if ((rc = row_norm(make_norm(k.ln1, y, C, rows, C, x, C), st))) return rc;
+    if ((rc = dense(make_gemm(k.out, ctx, C, B, L, ACT_NONE, x, C, y, C), math_mode, st, c_out))) return rc;
+    if ((rc = norm_rows(make_norm(k.ln1, y, C, rows, C, x, C), st))) return rc;
     // conv-FFN: hid = relu(conv_k(x)); y = x + conv_1(hid); x = LN(y)  (modules.py:247-248, encoder.py:64-69)
-    if ((rc = dense(make_gemm(k.w1, x, C, B, L, ACT_RELU, nullptr, 0, hid, k.w1.N), math_mode, st))) return rc;
-    if ((rc = dense(make_gemm(k.w2, hid, k.w1.N, B, L, ACT_NONE, x, C, y, C), math_mode, st))) return rc;
-    if ((rc = row_norm(make_norm(k.ln2, y, C, rows, C, x, C), st))) return rc;
+    if ((rc = dense(make_gemm(k.w1, x, C, B, L, ACT_RELU, nullptr, 0, hid, k.w1.N), math_mode, st, c_w1))) return rc;
+    if ((rc = dense(make_gemm(k.w2, hid, k.w1.N, B, L, ACT_NONE, x, C, y, C), math_mode, st, c_w2))) return rc;
+    if ((rc = norm_rows(make_norm(k.ln2, y, C, rows, C, x, C), st))) return rc;
   }
   return FS2_OK;
 }
@@ -116,13 +160,13 @@ int run_predictor(const Predictor& p, const float* x, int C, int B, int L, float
   const float* cur = x; int curC = C;
   for (int i = 0; i < p.layers; ++i) {
     int rc;
-    if ((rc = tap_gemm_fp32(make_gemm(p.conv[i], cur, curC, B, L, ACT_RELU, nullptr, 0, t1, p.conv[i].N), st))) return rc;
+    if ((rc = dense(make_gemm(p.conv[i], cur, curC, B, L, ACT_RELU, nullptr, 0, t1, p.conv[i].N), FS2_MATH_FP32, st, P_PRED_GEMM))) return rc;
     RowNorm r = make_norm(p.ln[i], t1, p.conv[i].N, rows, p.conv[i].N, t2, p.conv[i].N);
     if (i == p.layers - 1) {  // last layer: only the scalar head leaves the kernel
       r.out = nullptr; r.head_w = p.head_w; r.head_b = p.head_b; r.head_out = head_out; r.dur_out = dur_out;
       r.lens = lens; r.L = L;
     }
-    if ((rc = row_norm(r, st))) return rc;
+    if ((rc = norm_rows(r, st))) return rc;
     cur = t2; curC = p.conv[i].N;
   }
   return FS2_OK;
@@ -318,6 +362,27 @@ void fs2_destroy(fs2_handle* h) {
   delete h;
 }
 
+int fs2_profile_enable(fs2_handle* h, int on) {
+  FS2_REQUIRE(h, "fs2_profile_enable: null handle");
+  h->prof.on = on != 0;
+  return FS2_OK;
+}
+int fs2_profile_classes(void) { return P_COUNT; }
+const char* fs2_profile_label(int i) { return i >= 0 && i < P_COUNT ? kProfLabels[i] : ""; }
+int fs2_profile_read(fs2_handle* h, double* ms, int64_t* launches, double* flop, double* bytes) {
+  FS2_REQUIRE(h && ms && launches && flop && bytes, "fs2_profile_read: null argument");
+  for (int i = 0; i < P_COUNT; ++i) { ms[i] = 0; launches[i] = 0; flop[i] = 0; bytes[i] = 0; }
+  for (ProfRec& r : h->prof.recs) {
+    FS2_CUDA_CHECK(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    FS2_CUDA_CHECK(cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.cls] += t; launches[r.cls] += 1; flop[r.cls] += r.flop; bytes[r.cls] += r.bytes;
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  h->prof.recs.clear();
+  return FS2_OK;
+}
+
 int fs2_set_math_mode(fs2_handle* h, int math_mode) {
   FS2_REQUIRE(h, "fs2_set_math_mode: null handle");
   FS2_REQUIRE(math_mode == FS2_MATH_FP32 || math_mode == FS2_MATH_TF32, "fs2_set_math_mode: bad mode %d", math_mode);
@@ -370,13 +435,15 @@ int fs2_encode(fs2_handle* h, const int64_t* xs, const int64_t* ilens, int B, in
   FS2_REQUIRE(Tmax <= h->cfg.pe_len, "fs2_encode: Tmax=%d exceeds the positional table (%d rows)", Tmax, h->cfg.pe_len);
   cudaStream_t st = (cudaStream_t)stream;
   const fs2_config& c = h->cfg;
+  t_prof = &h->prof;
   Bump b(ws, ws_bytes);
   EncodePlan p = plan_encode(c, b, (int64_t)B * Tmax);
   if (!b.ok()) { set_error("fs2_encode: workspace too small (%zu < %zu)", ws_bytes, b.off); return FS2_ERR_WORKSPACE; }
   int rc;
   // the encoder always runs in exact fp32: its output feeds round() in the duration predictor
-  if ((rc = embed_posenc(xs, h->emb, c.idim, h->enc_pe, h->enc_alpha, B, Tmax, c.adim, p.x, st))) return rc;
-  if ((rc = run_blocks(h->enc, p.x, p.y, p.qkv, p.ctx, p.hid, ilens, B, Tmax, c.adim, c.aheads, FS2_MATH_FP32, st))) return rc;
+  { ProfScope prof_scope(P_EMBED, 0, 8.0 * B * Tmax * c.adim, st);
+    if ((rc = embed_posenc(xs, h->emb, c.idim, h->enc_pe, h->enc_alpha, B, Tmax, c.adim, p.x, st))) return rc; }
+  if ((rc = run_blocks(h->enc, p.x, p.y, p.qkv, p.ctx, p.hid, ilens, B, Tmax, c.adim, c.aheads, FS2_MATH_FP32, false, st))) return rc;
   FS2_CUDA_CHECK(cudaMemcpyAsync(hs, p.x, (size_t)B * Tmax * c.adim * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (d_log || d_int)
     if ((rc = run_predictor(h->dur, p.x, c.adim, B, Tmax, p.t1, p.t2, ilens, d_log, d_int, st))) return rc;
@@ -405,6 +472,7 @@ int fs2_decode(fs2_handle* h, const float* hm, const int64_t* olens, const float
   cudaStream_t st = (cudaStream_t)stream;
   const fs2_config& c = h->cfg;
   const int64_t rows = (int64_t)B * L;
+  t_prof = &h->prof;
   Bump b(ws, ws_bytes);
   DecodePlan p = plan_decode(c, b, rows);
   if (!b.ok()) { set_error("fs2_decode: workspace too small (%zu < %zu)", ws_bytes, b.off); return FS2_ERR_WORKSPACE; }
@@ -414,18 +482,19 @@ int fs2_decode(fs2_handle* h, const float* hm, const int64_t* olens, const float
   if ((rc = run_predictor(h->energy, hm, c.adim, B, L, p.t1, p.t2, olens, e_out, nullptr, st))) return rc;
   if ((rc = run_predictor(h->pitch, hm, c.adim, B, L, p.t1, p.t2, olens, p_out, nullptr, st))) return rc;
   // hs + pitch_embed(one_hot) + energy_embed(one_hot) (fastspeech.py:218-219)
+  { ProfScope prof_scope(P_VAR_EMBED, 0, 4.0 * rows * c.adim * 4, st);
   if ((rc = variance_embed_add(hm, es ? es : e_out, ps ? ps : p_out, h->e_bins, h->p_bins, c.n_bins - 1, h->e_tab,
-                               h->e_tab_bias, h->p_tab, h->p_tab_bias, rows, c.adim, p.hm2, e_ids, p_ids, st))) return rc;
+                               h->e_tab_bias, h->p_tab, h->p_tab_bias, rows, c.adim, p.hm2, e_ids, p_ids, st))) return rc; }
   // decoder input layer: Linear -> LayerNorm -> ReLU -> x + alpha*pe (core/encoder.py:118-125)
-  if ((rc = dense(make_gemm(h->dec_in, p.hm2, c.adim, B, L, ACT_NONE, nullptr, 0, p.y, c.ddim), mode, st))) return rc;
+  if ((rc = dense(make_gemm(h->dec_in, p.hm2, c.adim, B, L, ACT_NONE, nullptr, 0, p.y, c.ddim), mode, st, P_DEC_IN))) return rc;
   {
     RowNorm r = make_norm(h->dec_in_ln, p.y, c.ddim, rows, c.ddim, p.x, c.ddim);
     r.relu_after = 1; r.pe = h->dec_pe; r.alpha = h->dec_alpha; r.L = L;
-    if ((rc = row_norm(r, st))) return rc;
+    if ((rc = norm_rows(r, st))) return rc;
   }
-  if ((rc = run_blocks(h->dec, p.x, p.y, p.qkv, p.ctx, p.hid, olens, B, L, c.ddim, c.aheads, mode, st))) return rc;
+  if ((rc = run_blocks(h->dec, p.x, p.y, p.qkv, p.ctx, p.hid, olens, B, L, c.ddim, c.aheads, mode, true, st))) return rc;
   // mel linear (fastspeech.py:228-230)
-  if ((rc = dense(make_gemm(h->feat_out, p.x, c.ddim, B, L, ACT_NONE, nullptr, 0, before, c.odim), mode, st))) return rc;
+  if ((rc = dense(make_gemm(h->feat_out, p.x, c.ddim, B, L, ACT_NONE, nullptr, 0, before, c.odim), mode, st, P_FEAT_OUT))) return rc;
   // Postnet + residual (fastspeech.py:236-238, modules.py:350-359)
   const float* cur = before; int curC = c.odim;
   float* pp[2] = {p.q1, p.q2};
@@ -434,7 +503,7 @@ int fs2_decode(fs2_handle* h, const float* hm, const int64_t* olens, const float
     float* dst = last ? after : pp[i & 1];
     TapGemm g = make_gemm(h->postnet[i], cur, curC, B, L, last ? ACT_NONE : ACT_TANH, last ? before : nullptr, c.odim, dst,
                           h->postnet[i].N);
-    if ((rc = dense(g, mode, st))) return rc;
+    if ((rc = dense(g, mode, st, P_POSTNET))) return rc;
     cur = dst; curC = h->postnet[i].N;
   }
   return FS2_OK;
@@ -462,13 +531,12 @@ int fs2_op_tap_gemm(int math_mode, const float* x, int B, int L, int K, const fl
                     int act, const float* resid, float* out, void* stream) {
   FS2_REQUIRE(x && w && out, "fs2_op_tap_gemm: null argument");
   Dense d; d.w = w; d.bias = bias; d.N = N; d.K = K; d.taps = taps;
-  return dense(make_gemm(d, x, K, B, L, act, resid, N, out, N), math_mode, (cudaStream_t)stream);
+  return dense(make_gemm(d, x, K, B, L, act, resid, N, out, N), math_mode, (cudaStream_t)stream, P_DEC_W1);
 }
 int fs2_op_attention(int math_mode, const float* qkv, const int64_t* lens, int B, int L, int C, int heads, float* ctx,
                      void* stream) {
   FS2_REQUIRE(qkv && ctx, "fs2_op_attention: null argument");
-  return math_mode == FS2_MATH_TF32 ? attention_tf32(qkv, lens, B, L, C, heads, ctx, (cudaStream_t)stream)
-                                    : attention_fp32(qkv, lens, B, L, C, heads, ctx, (cudaStream_t)stream);
+  return attention(math_mode, qkv, lens, B, L, C, heads, ctx, (cudaStream_t)stream, P_DEC_ATTN);
 }
 int fs2_op_layernorm(const float* x, const float* resid, const float* g, const float* b, float eps, int64_t rows, int C,
                      float* out, void* stream) {

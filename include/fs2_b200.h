@@ -96,6 +96,16 @@ int fs2_load_weights(fs2_handle* h, const fs2_weight_desc* w, int n, void* strea
  * Tmax phonemes and Lmax frames. */
 int fs2_workspace_bytes(fs2_handle* h, int B, int Tmax, int Lmax, size_t* out);
 
+/* ---- per-kernel-class CUDA-event profiler (used by bench.py for the roofline; off by default) -
+ * While enabled, every kernel the stage functions enqueue is bracketed by two events on the
+ * launch stream.  fs2_profile_read synchronises those events, sums elapsed ms / launches /
+ * algorithmic FLOPs / algorithmic bytes per class into arrays of fs2_profile_classes()
+ * entries, and clears the records. */
+int fs2_profile_enable(fs2_handle* h, int on);
+int fs2_profile_classes(void);
+const char* fs2_profile_label(int cls);
+int fs2_profile_read(fs2_handle* h, double* ms, int64_t* launches, double* flop, double* bytes);
+
 /* ---- stage 1: phoneme encoder + duration predictor ------------------------------------- */
 /* fastspeech.py:180-193,210: _source_mask, encoder (core/encoder.py:185-204 ->
  * attention.py:30-74, modules.py:237-248), duration_predictor (duration_predictor.py:64-86).
