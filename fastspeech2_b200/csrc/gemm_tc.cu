@@ -1,0 +1,310 @@
+// Tensor-core "tap GEMM" for sm_100a: tcgen05.mma kind::tf32 with TMEM accumulators, operands
+// staged in shared memory by TMA (cp.async.bulk.tensor, 128-byte swizzle), mbarrier pipeline.
+//
+//   out[b,t,n] = act( sum_{j<taps} sum_{k<K} x[b, t+j-pad, k] * w[j][n][k] + bias[n] ) (+ resid[b,t,n])
+//
+// Same contract as gemm_fp32.cu (the exact-fp32 family); this one serves the decoder side in
+// FS2_MATH_TF32: decoder input Linear, q|k|v and output projections, conv-FFN (k=9 and k=1),
+// mel Linear and the Postnet convolutions -- ~88 % of the path's FLOPs.
+//
+// Why no im2col: activations are [B, time, channel] fp32 with channels innermost, which *is* the
+// K-major A operand of a GEMM.  Tap j of a 1-D convolution is the same matrix shifted by
+// (j - pad) rows, so the producer just issues the TMA box at row coordinate t0 + j - pad of a
+// 3-D tensor map {channel, time, utterance}; rows outside [0, L) of the utterance are
+// zero-filled by the TMA unit (that is exactly Conv1d's "same" padding), and fp32 data in shared
+// memory is consumed directly by kind::tf32 (the tensor core reads the top 19 bits), so there
+// is no conversion pass either.  K loop = taps x (K / 32) pipeline steps of 4 MMAs (K = 8 each).
+//
+// CTA = one 128 x BN output tile (BN in {256,192,128,96,80,64}), 6 warps:
+//   warp 0   : TMA producer (one elected lane)                    smem ring of STAGES slots
+//   warp 1   : TMEM allocator + MMA issuer (one elected lane)     full/empty mbarriers per slot
+//   warps 2-5: epilogue, thread == output row (TMEM lane): tcgen05.ld 32 columns at a time,
+//              bias / ReLU / tanh / residual in registers, 16-byte global stores.
+// Convolutions tile each utterance separately (ceil(L/128) tiles) so the shifted boxes never
+// cross an utterance boundary; plain GEMMs (taps == 1) tile the flat [B*L, K] matrix.
+// Every mbarrier wait is bounded: a pipeline bug traps instead of hanging the GPU.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace fs2 {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 32;                 // fp32 elements per pipeline step = one 128-byte swizzle row
+constexpr int UMMA_K = 8;              // tf32
+constexpr int A_BYTES = BM * BK * 4;   // 16 KB
+constexpr int NUM_THREADS = 192;
+constexpr int SMEM_BUDGET = 200 * 1024;
+
+struct TcParams {
+  int L, M_rows, tiles_per_utt;  // tiles_per_utt == 0: flat tiling over M_rows = B*L
+  int K, taps, pad, N;
+  const float* bias; const float* resid; int ldr;
+  float* out; int ldo; int act;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // try_wait suspends for a HW-defined time slice; 1<<22 slices is seconds -- far beyond any legal wait
+  for (uint32_t spin = 0; spin < (1u << 22); ++spin)
+    if (mbar_try_wait(bar, parity)) return;
+  printf("fs2 tap_gemm_tf32: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+  __trap();
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (ignored for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B between
+// 8-row groups | version=1 [46,48) | base_offset [49,52) = 0 (tiles are 1024-B aligned) | layout [61,64) = 2.
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
+  static constexpr int TMEM_COLS = BN > 128 ? 256 : (BN > 64 ? 128 : 64);
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2,
+  // A/B K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29)
+  static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128");
+  static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment");
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, TcParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + (size_t)C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + C::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  int b, t0;
+  if (p.tiles_per_utt > 0) { b = blockIdx.y / p.tiles_per_utt; t0 = (blockIdx.y - b * p.tiles_per_utt) * BM; }
+  else { b = 0; t0 = blockIdx.y * BM; }
+  const int kchunks = (p.K + BK - 1) / BK;
+  const int steps = p.taps * kchunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // whole warp: allocate the accumulator columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---- TMA producer ----
+      for (int s = 0; s < steps; ++s) {
+        const int slot = s % C::STAGES, round = s / C::STAGES;
+        mbar_wait(&empty_bar[slot], (round & 1) ^ 1);
+        const int j = s / kchunks, k0 = (s - j * kchunks) * BK;
+        uint8_t* a_dst = tiles + (size_t)slot * C::STAGE_BYTES;
+        mbar_expect_tx(&full_bar[slot], C::STAGE_BYTES);
+        tma_load_3d(a_dst, &tmap_a, &full_bar[slot], k0, t0 + j - p.pad, b);
+        tma_load_3d(a_dst + A_BYTES, &tmap_b, &full_bar[slot], k0, n0, j);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---- MMA issuer ----
+      for (int s = 0; s < steps; ++s) {
+        const int slot = s % C::STAGES, round = s / C::STAGES;
+        mbar_wait(&full_bar[slot], round & 1);
+        tcgen05_fence_after();
+        const uint32_t a_addr = smem_u32(tiles + (size_t)slot * C::STAGE_BYTES);
+        const uint64_t adesc = make_sw128_kmajor_desc(a_addr), bdesc = make_sw128_kmajor_desc(a_addr + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k)  // +32 bytes along K inside the swizzle row = +2 in descriptor units
+          umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, C::IDESC, (s | k) != 0);
+        tcgen05_commit(&empty_bar[slot]);    // slot reusable once these MMAs have read it
+      }
+      tcgen05_commit(tmem_full_bar);         // accumulator complete
+    }
+  } else {
+    // ---- epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31; thread == output row ----
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    const int row = (warp & 3) * 32 + lane;
+    const int t = t0 + row;
+    const bool row_ok = t < p.L;               // flat mode: L == M_rows
+    const long m = (long)b * p.L + t;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    float v[32];
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      __syncwarp();
+      tmem_ld32(lane_addr + c0, v);            // warp-collective: executed by all lanes regardless of row_ok
+      if (row_ok) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int n = n0 + c0 + q * 4;
+          if (c0 + q * 4 < BN) {
+            float4 o = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            if (p.bias) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+              o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+            }
+            if (p.act == ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            else if (p.act == ACT_TANH) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
+            if (p.resid) {
+              const float4 rv = __ldg(reinterpret_cast<const float4*>(p.resid + m * p.ldr + n));
+              o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+            }
+            *reinterpret_cast<float4*>(p.out + m * p.ldo + n) = o;
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// fp32 tensor {d0 (contiguous), d1, d2}, strides in bytes for d1, d2; box {32, box1, 1}, 128-byte swizzle, zero OOB fill
+int make_map(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2, uint32_t box1) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled unavailable (driver too old?)"); return FS2_ERR_CUDA; }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {s1, s2};
+  cuuint32_t box[3] = {(cuuint32_t)BK, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (dims %llu,%llu,%llu strides %llu,%llu box1 %u)", (int)r,
+                                     (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)s1, (unsigned long long)s2, box1); return FS2_ERR_CUDA; }
+  return FS2_OK;
+}
+
+template <int BN>
+int launch(const TapGemm& g, cudaStream_t st) {
+  using C = Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    FS2_CUDA_CHECK(cudaFuncSetAttribute(tap_gemm_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    configured = true;
+  }
+  TcParams p;
+  p.K = g.K; p.taps = g.taps; p.pad = (g.taps - 1) / 2; p.N = g.N;
+  p.bias = g.bias; p.resid = g.resid; p.ldr = g.ldr; p.out = g.out; p.ldo = g.ldo; p.act = g.act;
+  CUtensorMap ma, mb;
+  int rc, m_tiles;
+  const uint64_t row_bytes = (uint64_t)g.ldx * 4;
+  if (g.taps == 1) {  // flat [B*L, K]
+    const uint64_t M = (uint64_t)g.B * g.L;
+    p.L = (int)M; p.M_rows = (int)M; p.tiles_per_utt = 0;
+    m_tiles = (int)((M + BM - 1) / BM);
+    if ((rc = make_map(&ma, g.x, g.K, M, 1, row_bytes, row_bytes * M, BM))) return rc;
+  } else {            // per-utterance tiles: shifted boxes zero-fill outside [0, L)
+    p.L = g.L; p.M_rows = g.B * g.L; p.tiles_per_utt = (g.L + BM - 1) / BM;
+    m_tiles = p.tiles_per_utt * g.B;
+    if ((rc = make_map(&ma, g.x, g.K, g.L, g.B, row_bytes, row_bytes * g.L, BM))) return rc;
+  }
+  if ((rc = make_map(&mb, g.w, g.K, g.N, g.taps, (uint64_t)g.K * 4, (uint64_t)g.K * 4 * g.N, BN))) return rc;
+  dim3 grid(g.N / BN, m_tiles);
+  tap_gemm_tf32_kernel<BN><<<grid, NUM_THREADS, C::SMEM, st>>>(ma, mb, p);
+  FS2_LAUNCH_CHECK();
+  return FS2_OK;
+}
+
+}  // namespace
+
+int tap_gemm_tf32(const TapGemm& g, cudaStream_t st) {
+  FS2_REQUIRE(g.K % 4 == 0 && g.N % 16 == 0, "tap_gemm_tf32: K (%d) must be a multiple of 4 and N (%d) of 16", g.K, g.N);
+  FS2_REQUIRE(g.ldx % 4 == 0 && g.ldo % 4 == 0 && (!g.resid || g.ldr % 4 == 0), "tap_gemm_tf32: row strides must be 16-byte multiples");
+  FS2_REQUIRE((reinterpret_cast<uintptr_t>(g.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.w) & 15) == 0, "tap_gemm_tf32: operands must be 16-byte aligned");
+  FS2_REQUIRE((g.taps & 1) == 1, "tap_gemm_tf32: taps must be odd");
+  if ((long)g.B * g.L == 0) return FS2_OK;
+  if (g.N % 256 == 0) return launch<256>(g, st);
+  if (g.N % 192 == 0) return launch<192>(g, st);
+  if (g.N % 128 == 0) return launch<128>(g, st);
+  if (g.N % 96 == 0) return launch<96>(g, st);
+  if (g.N % 80 == 0) return launch<80>(g, st);
+  if (g.N % 64 == 0) return launch<64>(g, st);
+  set_error("tap_gemm_tf32: N=%d has no supported tile width", g.N);
+  return FS2_ERR_INVALID;
+}
+
+}  // namespace fs2
