@@ -109,12 +109,13 @@ int norm_rows(const RowNorm& r, cudaStream_t st) {
   ProfScope prof_scope(P_ROWNORM, 8.0 * r.rows * r.C, 4.0 * r.rows * r.C * (1 + (r.resid ? 1 : 0) + (r.out ? 1 : 0)), st);
   return row_norm(r, st);
 }
-int attention(int math_mode, const float* qkv, const int64_t* lens, int B, int L, int C, int heads, float* ctx, cudaStream_t st,
-              int cls) {
+int attention(int math_mode, const float* qkv, const float* vt, int lpad, const int64_t* lens, int B, int L, int C, int heads,
+              float* ctx, cudaStream_t st, int cls) {
   ProfScope prof_scope(cls, 4.0 * B * (double)L * L * C, 4.0 * 4.0 * B * (double)L * C, st);
-  return math_mode == FS2_MATH_TF32 ? attention_tf32(qkv, lens, B, L, C, heads, ctx, st)
+  return math_mode == FS2_MATH_TF32 ? attention_tf32(qkv, vt, lpad, lens, B, L, C, heads, ctx, st)
                                     : attention_fp32(qkv, lens, B, L, C, heads, ctx, st);
 }
+inline int round4(int x) { return (x + 3) & ~3; }
 
 TapGemm make_gemm(const Dense& d, const float* x, int ldx, int B, int L, int act, const float* resid, int ldr, float* out,
                   int ldo) {
@@ -132,7 +133,7 @@ RowNorm make_norm(const Norm& n, const float* x, int ldx, int64_t rows, int C, f
 }
 
 // x <- FFT blocks(x); scratch buffers sized for [rows, .]
-int run_blocks(const std::vector<Block>& blocks, float* x, float* y, float* qkv, float* ctx, float* hid,
+int run_blocks(const std::vector<Block>& blocks, float* x, float* y, float* qkv, float* vt, float* ctx, float* hid,
                const int64_t* lens, int B, int L, int C, int heads, int math_mode, bool is_dec, cudaStream_t st) {
   const int64_t rows = (int64_t)B * L;
   const int c_qkv = is_dec ? P_DEC_QKV : P_ENC_GEMM, c_att = is_dec ? P_DEC_ATTN : P_ENC_ATTN;
@@ -140,8 +141,12 @@ int run_blocks(const std::vector<Block>& blocks, float* x, float* y, float* qkv,
   for (const Block& k : blocks) {
     int rc;
     // q | k | v projection (attention.py:48-50), one GEMM with N = 3C
-    if ((rc = dense(make_gemm(k.qkv, x, C, B, L, ACT_NONE, nullptr, 0, qkv, 3 * C), math_mode, st, c_qkv))) return rc;
-    if ((rc = attention(math_mode, qkv, lens, B, L, C, heads, ctx, st, c_att))) return rc;
+    TapGemm gq = make_gemm(k.qkv, x, C, B, L, ACT_NONE, nullptr, 0, qkv, 3 * C);
+    if (math_mode == FS2_MATH_TF32) {  // V third stored transposed for the tensor-core attention (gemm_tc.cu epilogue)
+      gq.vt_out = vt; gq.vt_col0 = 2 * C; gq.vt_dk = C / heads; gq.vt_heads = heads; gq.vt_lpad = round4(L);
+    }
+    if ((rc = dense(gq, math_mode, st, c_qkv))) return rc;
+    if ((rc = attention(math_mode, qkv, vt, round4(L), lens, B, L, C, heads, ctx, st, c_att))) return rc;
     // y = x + linear_out(ctx) (attention.py:74, encoder.py:60); x = LN(y) (:61-62)
     if ((rc = dense(make_gemm(k.out, ctx, C, B, L, ACT_NONE, x, C, y, C), math_mode, st, c_out))) return rc;
     if ((rc = norm_rows(make_norm(k.ln1, y, C, rows, C, x, C), st))) return rc;
@@ -314,11 +319,12 @@ EncodePlan plan_encode(const fs2_config& c, Bump& b, int64_t rows) {
   p.t1 = b.floats(rows * c.pred_chans); p.t2 = b.floats(rows * c.pred_chans);
   return p;
 }
-struct DecodePlan { float *hm2, *x, *y, *qkv, *ctx, *hid, *t1, *t2, *q1, *q2; };
-DecodePlan plan_decode(const fs2_config& c, Bump& b, int64_t rows) {
+struct DecodePlan { float *hm2, *x, *y, *qkv, *vt, *ctx, *hid, *t1, *t2, *q1, *q2; };
+DecodePlan plan_decode(const fs2_config& c, Bump& b, int64_t rows, int B, int L) {
   DecodePlan p;
   p.hm2 = b.floats(rows * c.adim);
   p.x = b.floats(rows * c.ddim); p.y = b.floats(rows * c.ddim); p.qkv = b.floats(rows * 3 * c.ddim);
+  p.vt = b.floats((int64_t)B * c.ddim * round4(L));
   p.ctx = b.floats(rows * c.ddim); p.hid = b.floats(rows * c.dunits);
   p.t1 = b.floats(rows * c.pred_chans); p.t2 = b.floats(rows * c.pred_chans);
   p.q1 = b.floats(rows * c.postnet_chans); p.q2 = b.floats(rows * c.postnet_chans);
@@ -423,7 +429,7 @@ int fs2_workspace_bytes(fs2_handle* h, int B, int Tmax, int Lmax, size_t* out) {
   FS2_REQUIRE(h && out && B >= 0 && Tmax >= 0 && Lmax >= 0, "fs2_workspace_bytes: bad argument");
   Bump e(nullptr, 0), d(nullptr, 0);
   plan_encode(h->cfg, e, (int64_t)B * Tmax);
-  plan_decode(h->cfg, d, (int64_t)B * Lmax);
+  plan_decode(h->cfg, d, (int64_t)B * Lmax, B, Lmax);
   *out = (e.off > d.off ? e.off : d.off) + 1024;
   return FS2_OK;
 }
@@ -443,7 +449,7 @@ int fs2_encode(fs2_handle* h, const int64_t* xs, const int64_t* ilens, int B, in
   // the encoder always runs in exact fp32: its output feeds round() in the duration predictor
   { ProfScope prof_scope(P_EMBED, 0, 8.0 * B * Tmax * c.adim, st);
     if ((rc = embed_posenc(xs, h->emb, c.idim, h->enc_pe, h->enc_alpha, B, Tmax, c.adim, p.x, st))) return rc; }
-  if ((rc = run_blocks(h->enc, p.x, p.y, p.qkv, p.ctx, p.hid, ilens, B, Tmax, c.adim, c.aheads, FS2_MATH_FP32, false, st))) return rc;
+  if ((rc = run_blocks(h->enc, p.x, p.y, p.qkv, nullptr, p.ctx, p.hid, ilens, B, Tmax, c.adim, c.aheads, FS2_MATH_FP32, false, st))) return rc;
   FS2_CUDA_CHECK(cudaMemcpyAsync(hs, p.x, (size_t)B * Tmax * c.adim * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (d_log || d_int)
     if ((rc = run_predictor(h->dur, p.x, c.adim, B, Tmax, p.t1, p.t2, ilens, d_log, d_int, st))) return rc;
@@ -474,7 +480,7 @@ int fs2_decode(fs2_handle* h, const float* hm, const int64_t* olens, const float
   const int64_t rows = (int64_t)B * L;
   t_prof = &h->prof;
   Bump b(ws, ws_bytes);
-  DecodePlan p = plan_decode(c, b, rows);
+  DecodePlan p = plan_decode(c, b, rows, B, L);
   if (!b.ok()) { set_error("fs2_decode: workspace too small (%zu < %zu)", ws_bytes, b.off); return FS2_ERR_WORKSPACE; }
   const int mode = c.math_mode;
   int rc;
@@ -492,7 +498,7 @@ int fs2_decode(fs2_handle* h, const float* hm, const int64_t* olens, const float
     r.relu_after = 1; r.pe = h->dec_pe; r.alpha = h->dec_alpha; r.L = L;
     if ((rc = norm_rows(r, st))) return rc;
   }
-  if ((rc = run_blocks(h->dec, p.x, p.y, p.qkv, p.ctx, p.hid, olens, B, L, c.ddim, c.aheads, mode, true, st))) return rc;
+  if ((rc = run_blocks(h->dec, p.x, p.y, p.qkv, p.vt, p.ctx, p.hid, olens, B, L, c.ddim, c.aheads, mode, true, st))) return rc;
   // mel linear (fastspeech.py:228-230)
   if ((rc = dense(make_gemm(h->feat_out, p.x, c.ddim, B, L, ACT_NONE, nullptr, 0, before, c.odim), mode, st, P_FEAT_OUT))) return rc;
   // Postnet + residual (fastspeech.py:236-238, modules.py:350-359)
@@ -536,7 +542,16 @@ int fs2_op_tap_gemm(int math_mode, const float* x, int B, int L, int K, const fl
 int fs2_op_attention(int math_mode, const float* qkv, const int64_t* lens, int B, int L, int C, int heads, float* ctx,
                      void* stream) {
   FS2_REQUIRE(qkv && ctx, "fs2_op_attention: null argument");
-  return attention(math_mode, qkv, lens, B, L, C, heads, ctx, (cudaStream_t)stream, P_DEC_ATTN);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (math_mode != FS2_MATH_TF32) return attention(math_mode, qkv, nullptr, 0, lens, B, L, C, heads, ctx, st, P_DEC_ATTN);
+  // single-operator entry (tests): build the transposed V the projection epilogue normally provides
+  float* vt = nullptr;
+  const int lpad = round4(L);
+  FS2_CUDA_CHECK(cudaMallocAsync(&vt, (size_t)B * C * lpad * sizeof(float), st));
+  int rc = transpose_v(qkv, B, L, C, heads, vt, lpad, st);
+  if (!rc) rc = attention(math_mode, qkv, vt, lpad, lens, B, L, C, heads, ctx, st, P_DEC_ATTN);
+  cudaFreeAsync(vt, st);
+  return rc;
 }
 int fs2_op_layernorm(const float* x, const float* resid, const float* g, const float* b, float eps, int64_t rows, int C,
                      float* out, void* stream) {

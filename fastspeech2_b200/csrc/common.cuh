@@ -50,6 +50,8 @@ struct TapGemm {
   int act;
   const float* resid; int ldr;  // nullptr => none
   float* out; int ldo;
+  // tf32 family only: store output columns >= vt_col0 transposed into vt_out (see gemm_tc.cu)
+  float* vt_out = nullptr; int vt_col0 = 0, vt_dk = 0, vt_heads = 0, vt_lpad = 0;
 };
 int tap_gemm_fp32(const TapGemm& g, cudaStream_t st);
 int tap_gemm_tf32(const TapGemm& g, cudaStream_t st);   // tcgen05 + TMA (gemm_tc.cu)
@@ -80,7 +82,12 @@ int variance_embed_add(const float* hm, const float* e_val, const float* p_val, 
                        int64_t rows, int C, float* out, int64_t* e_ids, int64_t* p_ids, cudaStream_t st);
 
 int attention_fp32(const float* qkv, const int64_t* lens, int B, int L, int C, int heads, float* ctx, cudaStream_t st);
-int attention_tf32(const float* qkv, const int64_t* lens, int B, int L, int C, int heads, float* ctx, cudaStream_t st);
+// tensor-core attention: q, k from qkv [B,L,3C]; v from the transposed buffer vt [B*heads, dk, lpad]
+int attention_tf32(const float* qkv, const float* vt, int lpad, const int64_t* lens, int B, int L, int C, int heads,
+                   float* ctx, cudaStream_t st);
+
+// vt[(b*heads + h)*dk + d][t] = qkv[b, t, 2C + h*dk + d]   (test helper for the single-operator entry)
+int transpose_v(const float* qkv, int B, int L, int C, int heads, float* vt, int lpad, cudaStream_t st);
 
 int length_plan(void* ds, int ds_dtype, const int64_t* ilens, float alpha, int B, int T, int mutate, int32_t* cum,
                 int64_t* olens, int64_t* stats, cudaStream_t st);
