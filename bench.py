@@ -74,9 +74,17 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def wait_first(self, timeout=5.0):
+        t0 = time.time()
+        while self.proc and not self.lines and time.time() - t0 < timeout:
+            time.sleep(0.05)
+
+    def mark(self):
+        return time.time()
+
+    def stop(self, t_begin=0.0, t_end=1e300):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -85,7 +93,9 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if ts < t_begin or ts > t_end + 0.15:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -215,17 +225,21 @@ def run_b200(args):
         return ms / steps
 
     sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        sampler.wait_first()
     n0 = lib.fs2_kernel_launches()
     for _ in range(max(args.warmup, 3)):
         step(devin)
     torch.cuda.synchronize()
     n1 = lib.fs2_kernel_launches()
     launches_per_step = (n1 - n0) // max(args.warmup, 3)
-    if sampler:
-        sampler.start()
+    t_begin = time.time()
     ms_step = timed(lambda: step(devin), args.steps, 0)
-    clocks = sampler.stop() if sampler else None
     ms_e2e = timed(step_e2e, args.steps, 2)
+    clocks = sampler.stop(t_begin, time.time()) if sampler else None
+    if clocks is not None:
+        clocks["window"] = "samples every 100 ms during the device-timed loop and the e2e loop"
 
     # per-kernel-class CUDA-event profile on extra steps of the same workload
     prof = None
@@ -305,7 +319,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default=os.environ.get("FS2_PRECISION", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--precision", default=os.environ.get("FS2_PRECISION", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--cpu-sample-batch", type=int, default=8)
     args = ap.parse_args()
     if args.impl == "reference":

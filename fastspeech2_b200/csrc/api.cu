@@ -23,6 +23,8 @@ void set_error(const char* fmt, ...) {
 
 struct Dense {           // one Linear / Conv1d in kernel layout
   const float* w = nullptr;     // [taps][N][K]
+  const float* w_hi = nullptr;  // 3xTF32 split of w (encoder / predictors only)
+  const float* w_lo = nullptr;
   const float* bias = nullptr;  // [N] or nullptr
   int N = 0, K = 0, taps = 1;
 };
@@ -103,7 +105,7 @@ int dense(const TapGemm& g, int math_mode, cudaStream_t st, int cls) {
   const double M = (double)g.B * g.L;
   ProfScope prof_scope(cls, 2.0 * M * g.N * g.K * g.taps,
                4.0 * (M * g.K + (double)g.taps * g.N * g.K + M * g.N * (g.resid ? 2 : 1)), st);
-  return math_mode == FS2_MATH_TF32 ? tap_gemm_tf32(g, st) : tap_gemm_fp32(g, st);
+  return math_mode == MATH_3XTF32 ? tap_gemm_3xtf32(g, st) : math_mode == FS2_MATH_TF32 ? tap_gemm_tf32(g, st) : tap_gemm_fp32(g, st);
 }
 int norm_rows(const RowNorm& r, cudaStream_t st) {
   ProfScope prof_scope(P_ROWNORM, 8.0 * r.rows * r.C, 4.0 * r.rows * r.C * (1 + (r.resid ? 1 : 0) + (r.out ? 1 : 0)), st);
@@ -112,6 +114,7 @@ int norm_rows(const RowNorm& r, cudaStream_t st) {
 int attention(int math_mode, const float* qkv, const float* vt, int lpad, const int64_t* lens, int B, int L, int C, int heads,
               float* ctx, cudaStream_t st, int cls) {
   ProfScope prof_scope(cls, 4.0 * B * (double)L * L * C, 4.0 * 4.0 * B * (double)L * C, st);
+  // the encoder (MATH_3XTF32) keeps the exact-fp32 attention core: 0.2 ms at c2, and its scores feed the durations
   return math_mode == FS2_MATH_TF32 ? attention_tf32(qkv, vt, lpad, lens, B, L, C, heads, ctx, st)
                                     : attention_fp32(qkv, lens, B, L, C, heads, ctx, st);
 }
@@ -120,7 +123,7 @@ inline int round4(int x) { return (x + 3) & ~3; }
 TapGemm make_gemm(const Dense& d, const float* x, int ldx, int B, int L, int act, const float* resid, int ldr, float* out,
                   int ldo) {
   TapGemm g;
-  g.x = x; g.ldx = ldx; g.B = B; g.L = L; g.K = d.K; g.w = d.w; g.bias = d.bias; g.N = d.N; g.taps = d.taps;
+  g.x = x; g.ldx = ldx; g.B = B; g.L = L; g.K = d.K; g.w = d.w; g.w_hi = d.w_hi; g.w_lo = d.w_lo; g.bias = d.bias; g.N = d.N; g.taps = d.taps;
   g.act = act; g.resid = resid; g.ldr = ldr; g.out = out; g.ldo = ldo;
   return g;
 }
@@ -160,12 +163,12 @@ int run_blocks(const std::vector<Block>& blocks, float* x, float* y, float* qkv,
 
 // conv stack + scalar head (duration_predictor.py:64-86 / variance_predictor.py:39-60); always fp32
 int run_predictor(const Predictor& p, const float* x, int C, int B, int L, float* t1, float* t2, const int64_t* lens,
-                  float* head_out, int64_t* dur_out, cudaStream_t st) {
+                  float* head_out, int64_t* dur_out, int math_mode, cudaStream_t st) {
   const int64_t rows = (int64_t)B * L;
   const float* cur = x; int curC = C;
   for (int i = 0; i < p.layers; ++i) {
     int rc;
-    if ((rc = dense(make_gemm(p.conv[i], cur, curC, B, L, ACT_RELU, nullptr, 0, t1, p.conv[i].N), FS2_MATH_FP32, st, P_PRED_GEMM))) return rc;
+    if ((rc = dense(make_gemm(p.conv[i], cur, curC, B, L, ACT_RELU, nullptr, 0, t1, p.conv[i].N), math_mode, st, P_PRED_GEMM))) return rc;
     RowNorm r = make_norm(p.ln[i], t1, p.conv[i].N, rows, p.conv[i].N, t2, p.conv[i].N);
     if (i == p.layers - 1) {  // last layer: only the scalar head leaves the kernel
       r.out = nullptr; r.head_w = p.head_w; r.head_b = p.head_b; r.head_out = head_out; r.dur_out = dur_out;
@@ -212,6 +215,15 @@ struct Packer {
     if (!bkey.empty()) { int rc = copy(bkey, N, &out->bias); if (rc) return rc; }
     return FS2_OK;
   }
+  // hi / lo copies for the 3xTF32 kernel (gemm_tc.cu)
+  int split(Dense* d) {
+    const size_t n = (size_t)d->N * d->K * d->taps;
+    float* hi = bump.floats(n);
+    float* lo = bump.floats(n);
+    if (!counting) { int rc = split_tf32(d->w, hi, lo, (long)n, st); if (rc) return rc; }
+    d->w_hi = hi; d->w_lo = lo;
+    return FS2_OK;
+  }
   int norm(const std::string& prefix, int C, float eps, Norm* out) {
     int rc;
     if ((rc = copy(prefix + "weight", C, &out->g))) return rc;
@@ -219,7 +231,7 @@ struct Packer {
     out->eps = eps;
     return FS2_OK;
   }
-  int blocks(const std::string& prefix, int n, int C, int H, int kffn, std::vector<Block>* out) {
+  int blocks(const std::string& prefix, int n, int C, int H, int kffn, bool precise, std::vector<Block>* out) {
     out->assign(n, Block());
     for (int i = 0; i < n; ++i) {
       std::string p = prefix + ".encoders_." + std::to_string(i) + ".";
@@ -241,6 +253,7 @@ struct Packer {
       if ((rc = dense(p + "self_attn.linear_out.weight", p + "self_attn.linear_out.bias", C, C, 1, &b.out))) return rc;
       if ((rc = dense(p + "feed_forward.w_1.weight", p + "feed_forward.w_1.bias", H, C, kffn, &b.w1))) return rc;
       if ((rc = dense(p + "feed_forward.w_2.weight", p + "feed_forward.w_2.bias", C, H, 1, &b.w2))) return rc;
+      if (precise) for (Dense* d : {&b.qkv, &b.out, &b.w1, &b.w2}) if ((rc = split(d))) return rc;
       if ((rc = norm(p + "norm1.", C, 1e-5f, &b.ln1))) return rc;   // encoder.py:37-38
       if ((rc = norm(p + "norm2.", C, 1e-5f, &b.ln2))) return rc;
     }
@@ -253,6 +266,7 @@ struct Packer {
       std::string p = prefix + "conv." + std::to_string(i) + ".";
       int rc;
       if ((rc = dense(p + "0.weight", p + "0.bias", c.pred_chans, i == 0 ? c.adim : c.pred_chans, c.pred_kernel, &out->conv[i]))) return rc;
+      if ((rc = split(&out->conv[i]))) return rc;
       if ((rc = norm(p + "2.layer_norm.", c.pred_chans, 1e-12f, &out->ln[i]))) return rc;  // modules.py:115
     }
     int rc;
@@ -267,7 +281,7 @@ struct Packer {
     if ((rc = copy("encoder.embed.0.weight", (int64_t)c.idim * c.adim, &h->emb))) return rc;
     if ((rc = copy("encoder.embed.1.alpha", 1, &h->enc_alpha))) return rc;
     if ((rc = copy("encoder.embed.1.pe", (int64_t)c.pe_len * c.adim, &h->enc_pe))) return rc;
-    if ((rc = blocks("encoder", c.elayers, c.adim, c.eunits, c.ffn_kernel, &h->enc))) return rc;
+    if ((rc = blocks("encoder", c.elayers, c.adim, c.eunits, c.ffn_kernel, true, &h->enc))) return rc;
     if ((rc = predictor("duration_predictor.", &h->dur))) return rc;
     if ((rc = predictor("energy_predictor.predictor.", &h->energy))) return rc;
     if ((rc = predictor("pitch_predictor.predictor.", &h->pitch))) return rc;
@@ -292,7 +306,7 @@ struct Packer {
     if ((rc = norm("decoder.embed.1.", c.ddim, 1e-5f, &h->dec_in_ln))) return rc;
     if ((rc = copy("decoder.embed.4.alpha", 1, &h->dec_alpha))) return rc;
     if ((rc = copy("decoder.embed.4.pe", (int64_t)c.pe_len * c.ddim, &h->dec_pe))) return rc;
-    if ((rc = blocks("decoder", c.dlayers, c.ddim, c.dunits, c.ffn_kernel, &h->dec))) return rc;
+    if ((rc = blocks("decoder", c.dlayers, c.ddim, c.dunits, c.ffn_kernel, false, &h->dec))) return rc;
     if ((rc = dense("feat_out.weight", "feat_out.bias", c.odim, c.ddim, 1, &h->feat_out))) return rc;
     // Postnet: Conv1d(no bias) + BatchNorm1d(eval) folded into weight scale + bias (modules.py:283-348)
     h->postnet.assign(c.postnet_layers, Dense());
@@ -446,13 +460,15 @@ int fs2_encode(fs2_handle* h, const int64_t* xs, const int64_t* ilens, int B, in
   EncodePlan p = plan_encode(c, b, (int64_t)B * Tmax);
   if (!b.ok()) { set_error("fs2_encode: workspace too small (%zu < %zu)", ws_bytes, b.off); return FS2_ERR_WORKSPACE; }
   int rc;
-  // the encoder always runs in exact fp32: its output feeds round() in the duration predictor
+  // the encoder's output feeds round() in the duration predictor: exact fp32 FMA in FS2_MATH_FP32,
+  // error-compensated 3xTF32 on the tensor cores in FS2_MATH_TF32 (never plain tf32)
+  const int precise = c.math_mode == FS2_MATH_TF32 ? MATH_3XTF32 : FS2_MATH_FP32;
   { ProfScope prof_scope(P_EMBED, 0, 8.0 * B * Tmax * c.adim, st);
     if ((rc = embed_posenc(xs, h->emb, c.idim, h->enc_pe, h->enc_alpha, B, Tmax, c.adim, p.x, st))) return rc; }
-  if ((rc = run_blocks(h->enc, p.x, p.y, p.qkv, nullptr, p.ctx, p.hid, ilens, B, Tmax, c.adim, c.aheads, FS2_MATH_FP32, false, st))) return rc;
+  if ((rc = run_blocks(h->enc, p.x, p.y, p.qkv, nullptr, p.ctx, p.hid, ilens, B, Tmax, c.adim, c.aheads, precise, false, st))) return rc;
   FS2_CUDA_CHECK(cudaMemcpyAsync(hs, p.x, (size_t)B * Tmax * c.adim * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (d_log || d_int)
-    if ((rc = run_predictor(h->dur, p.x, c.adim, B, Tmax, p.t1, p.t2, ilens, d_log, d_int, st))) return rc;
+    if ((rc = run_predictor(h->dur, p.x, c.adim, B, Tmax, p.t1, p.t2, ilens, d_log, d_int, precise, st))) return rc;
   return FS2_OK;
 }
 
@@ -483,10 +499,11 @@ int fs2_decode(fs2_handle* h, const float* hm, const int64_t* olens, const float
   DecodePlan p = plan_decode(c, b, rows, B, L);
   if (!b.ok()) { set_error("fs2_decode: workspace too small (%zu < %zu)", ws_bytes, b.off); return FS2_ERR_WORKSPACE; }
   const int mode = c.math_mode;
+  const int precise = mode == FS2_MATH_TF32 ? MATH_3XTF32 : FS2_MATH_FP32;
   int rc;
   // energy / pitch predictors on the length-regulated states (fastspeech.py:195-196,214-216); fp32
-  if ((rc = run_predictor(h->energy, hm, c.adim, B, L, p.t1, p.t2, olens, e_out, nullptr, st))) return rc;
-  if ((rc = run_predictor(h->pitch, hm, c.adim, B, L, p.t1, p.t2, olens, p_out, nullptr, st))) return rc;
+  if ((rc = run_predictor(h->energy, hm, c.adim, B, L, p.t1, p.t2, olens, e_out, nullptr, precise, st))) return rc;
+  if ((rc = run_predictor(h->pitch, hm, c.adim, B, L, p.t1, p.t2, olens, p_out, nullptr, precise, st))) return rc;
   // hs + pitch_embed(one_hot) + energy_embed(one_hot) (fastspeech.py:218-219)
   { ProfScope prof_scope(P_VAR_EMBED, 0, 4.0 * rows * c.adim * 4, st);
   if ((rc = variance_embed_add(hm, es ? es : e_out, ps ? ps : p_out, h->e_bins, h->p_bins, c.n_bins - 1, h->e_tab,
@@ -537,7 +554,17 @@ int fs2_op_tap_gemm(int math_mode, const float* x, int B, int L, int K, const fl
                     int act, const float* resid, float* out, void* stream) {
   FS2_REQUIRE(x && w && out, "fs2_op_tap_gemm: null argument");
   Dense d; d.w = w; d.bias = bias; d.N = N; d.K = K; d.taps = taps;
-  return dense(make_gemm(d, x, K, B, L, act, resid, N, out, N), math_mode, (cudaStream_t)stream, P_DEC_W1);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (math_mode != MATH_3XTF32) return dense(make_gemm(d, x, K, B, L, act, resid, N, out, N), math_mode, st, P_DEC_W1);
+  // single-operator entry for the 3xTF32 family (tests): split the weights on the fly
+  const size_t n = (size_t)N * K * taps;
+  float* tmp = nullptr;
+  FS2_CUDA_CHECK(cudaMallocAsync(&tmp, 2 * n * sizeof(float), st));
+  int rc = split_tf32(w, tmp, tmp + n, (long)n, st);
+  d.w_hi = tmp; d.w_lo = tmp + n;
+  if (!rc) rc = dense(make_gemm(d, x, K, B, L, act, resid, N, out, N), math_mode, st, P_DEC_W1);
+  cudaFreeAsync(tmp, st);
+  return rc;
 }
 int fs2_op_attention(int math_mode, const float* qkv, const int64_t* lens, int B, int L, int C, int heads, float* ctx,
                      void* stream) {

@@ -3,23 +3,32 @@
 //
 //   out[b,t,n] = act( sum_{j<taps} sum_{k<K} x[b, t+j-pad, k] * w[j][n][k] + bias[n] ) (+ resid[b,t,n])
 //
-// Same contract as gemm_fp32.cu (the exact-fp32 family); this one serves the decoder side in
-// FS2_MATH_TF32: decoder input Linear, q|k|v and output projections, conv-FFN (k=9 and k=1),
-// mel Linear and the Postnet convolutions -- ~88 % of the path's FLOPs.
+// Same contract as gemm_fp32.cu (the CUDA-core family).  In FS2_MATH_TF32 this kernel serves
+//   * the decoder side in plain tf32 (one MMA per product): decoder input Linear, q|k|v and output
+//     projections, conv-FFN (k=9 and k=1), mel Linear, Postnet convolutions;
+//   * the encoder and the three predictors in *3xTF32* (PRECISE = true): every operand is split
+//     into hi = rn_tf32(x) and lo = rn_tf32(x - hi) and the product is accumulated as
+//     hi*hi + lo*hi + hi*lo in the fp32 TMEM accumulator (the dropped lo*lo term is ~2^-22
+//     relative), which gives fp32-class results on the tensor pipe.  Their outputs feed round() /
+//     bucketize(), where plain tf32 noise (~1e-3) would flip integers.
 //
 // Why no im2col: activations are [B, time, channel] fp32 with channels innermost, which *is* the
 // K-major A operand of a GEMM.  Tap j of a 1-D convolution is the same matrix shifted by
 // (j - pad) rows, so the producer just issues the TMA box at row coordinate t0 + j - pad of a
 // 3-D tensor map {channel, time, utterance}; rows outside [0, L) of the utterance are
 // zero-filled by the TMA unit (that is exactly Conv1d's "same" padding), and fp32 data in shared
-// memory is consumed directly by kind::tf32 (the tensor core reads the top 19 bits), so there
-// is no conversion pass either.  K loop = taps x (K / 32) pipeline steps of 4 MMAs (K = 8 each).
+// memory is consumed directly by kind::tf32, so there is no conversion pass either.
+// K loop = taps x ceil(K / 32) pipeline steps of 4 (12 when PRECISE) MMAs with K = 8 each.
 //
-// CTA = one 128 x BN output tile (BN in {256,192,128,96,80,64}), 6 warps:
+// CTA = one 128 x BN output tile, 6 warps:
 //   warp 0   : TMA producer (one elected lane)                    smem ring of STAGES slots
 //   warp 1   : TMEM allocator + MMA issuer (one elected lane)     full/empty mbarriers per slot
-//   warps 2-5: epilogue, thread == output row (TMEM lane): tcgen05.ld 32 columns at a time,
-//              bias / ReLU / tanh / residual in registers, 16-byte global stores.
+//   warps 2-5: PRECISE only: while the main loop runs they split each landed A tile in place into
+//              hi / lo (element-wise, so the swizzled layout is untouched) and hand the slot to the
+//              MMA warp through a third mbarrier; the weight hi / lo arrays are split once at load.
+//              Then the epilogue, thread == output row (TMEM lane): tcgen05.ld 32 columns at a
+//              time, bias / ReLU / tanh / residual in registers, 16-byte global stores (or the
+//              transposed V store for the attention kernel).
 // Convolutions tile each utterance separately (ceil(L/128) tiles) so the shifted boxes never
 // cross an utterance boundary; plain GEMMs (taps == 1) tile the flat [B*L, K] matrix.
 // Every mbarrier wait is bounded: a pipeline bug traps instead of hanging the GPU.
@@ -46,27 +55,40 @@ struct TcParams {
   float* vt_out; int vt_col0, vt_dk, vt_heads, vt_lpad, vt_L;
 };
 
-template <int BN>
+template <int BN, bool PRECISE>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 4;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = (PRECISE ? 2 : 1) * (A_BYTES + B_BYTES);   // [A(hi)][A lo][B hi][B lo]
   static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = BN > 128 ? 256 : (BN > 64 ? 128 : 64);
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr uint32_t IDESC = idesc_tf32(BM, BN);
+  static constexpr int A_LO = A_BYTES;                                  // offsets inside a stage
+  static constexpr int B_HI = PRECISE ? 2 * A_BYTES : A_BYTES;
+  static constexpr int B_LO = B_HI + B_BYTES;
+  static constexpr uint32_t TX_BYTES = A_BYTES + (PRECISE ? 2 : 1) * B_BYTES;
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128");
   static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment");
+  static_assert(STAGES >= 2, "pipeline depth");
 };
 
-template <int BN>
+__device__ __forceinline__ float rn_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+template <int BN, bool PRECISE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, TcParams p) {
-  using C = Cfg<BN>;
+tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                     const __grid_constant__ CUtensorMap tmap_b_lo, TcParams p) {
+  using C = Cfg<BN, PRECISE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + (size_t)C::STAGES * C::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
-  uint64_t* tmem_full_bar = empty_bar + C::STAGES;
+  uint64_t* split_bar = empty_bar + C::STAGES;
+  uint64_t* tmem_full_bar = split_bar + C::STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -78,13 +100,11 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   const int steps = p.taps * kchunks;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], 4); }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // whole warp: allocate the accumulator columns
-    tmem_alloc(tmem_slot, C::TMEM_COLS);
-  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);   // whole warp: accumulator columns
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -96,28 +116,59 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         const int slot = s % C::STAGES, round = s / C::STAGES;
         mbar_wait(&empty_bar[slot], (round & 1) ^ 1);
         const int j = s / kchunks, k0 = (s - j * kchunks) * BK;
-        uint8_t* a_dst = tiles + (size_t)slot * C::STAGE_BYTES;
-        mbar_expect_tx(&full_bar[slot], C::STAGE_BYTES);
-        tma_load_3d(a_dst, &tmap_a, &full_bar[slot], k0, t0 + j - p.pad, b);
-        tma_load_3d(a_dst + A_BYTES, &tmap_b, &full_bar[slot], k0, n0, j);
+        uint8_t* st = tiles + (size_t)slot * C::STAGE_BYTES;
+        mbar_expect_tx(&full_bar[slot], C::TX_BYTES);
+        tma_load_3d(st, &tmap_a, &full_bar[slot], k0, t0 + j - p.pad, b);
+        tma_load_3d(st + C::B_HI, &tmap_b, &full_bar[slot], k0, n0, j);
+        if (PRECISE) tma_load_3d(st + C::B_LO, &tmap_b_lo, &full_bar[slot], k0, n0, j);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ---- MMA issuer ----
       for (int s = 0; s < steps; ++s) {
         const int slot = s % C::STAGES, round = s / C::STAGES;
-        mbar_wait(&full_bar[slot], round & 1);
+        mbar_wait(PRECISE ? &split_bar[slot] : &full_bar[slot], round & 1);
         tcgen05_fence_after();
-        const uint32_t a_addr = smem_u32(tiles + (size_t)slot * C::STAGE_BYTES);
-        const uint64_t adesc = make_sw128_kmajor_desc(a_addr), bdesc = make_sw128_kmajor_desc(a_addr + A_BYTES);
+        const uint32_t base = smem_u32(tiles + (size_t)slot * C::STAGE_BYTES);
+        const uint64_t a_hi = make_sw128_kmajor_desc(base), b_hi = make_sw128_kmajor_desc(base + C::B_HI);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k)  // +32 bytes along K inside the swizzle row = +2 in descriptor units
-          umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, C::IDESC, (s | k) != 0);
+        for (int k = 0; k < BK / UMMA_K; ++k) {  // +32 bytes along K inside the swizzle row = +2 in descriptor units
+          if (PRECISE) {
+            const uint64_t a_lo = make_sw128_kmajor_desc(base + C::A_LO), b_lo = make_sw128_kmajor_desc(base + C::B_LO);
+            umma_tf32(tmem_base, a_lo + 2 * k, b_hi + 2 * k, C::IDESC, (s | k) != 0);   // small terms first
+            umma_tf32(tmem_base, a_hi + 2 * k, b_lo + 2 * k, C::IDESC, 1);
+            umma_tf32(tmem_base, a_hi + 2 * k, b_hi + 2 * k, C::IDESC, 1);
+          } else {
+            umma_tf32(tmem_base, a_hi + 2 * k, b_hi + 2 * k, C::IDESC, (s | k) != 0);
+          }
+        }
         tcgen05_commit(&empty_bar[slot]);    // slot reusable once these MMAs have read it
       }
       tcgen05_commit(tmem_full_bar);         // accumulator complete
     }
   } else {
+    if (PRECISE) {
+      // ---- operand split: A tile -> hi (in place) and lo (second buffer), same swizzled positions ----
+      const int tid = threadIdx.x - 64;      // 0..127
+      for (int s = 0; s < steps; ++s) {
+        const int slot = s % C::STAGES, round = s / C::STAGES;
+        mbar_wait(&full_bar[slot], round & 1);
+        float4* a = reinterpret_cast<float4*>(tiles + (size_t)slot * C::STAGE_BYTES);
+        float4* lo = reinterpret_cast<float4*>(tiles + (size_t)slot * C::STAGE_BYTES + C::A_LO);
+#pragma unroll
+        for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
+          const int idx = tid + i * 128;
+          const float4 x = a[idx];
+          float4 h, l;
+          h.x = rn_tf32(x.x); h.y = rn_tf32(x.y); h.z = rn_tf32(x.z); h.w = rn_tf32(x.w);
+          l.x = rn_tf32(x.x - h.x); l.y = rn_tf32(x.y - h.y); l.z = rn_tf32(x.z - h.z); l.w = rn_tf32(x.w - h.w);
+          a[idx] = h; lo[idx] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split_bar[slot]);
+      }
+    }
     // ---- epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31; thread == output row ----
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
@@ -170,20 +221,27 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   }
 }
 
+__global__ void split_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, long n) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float x = src[i], h = rn_tf32(x);
+    hi[i] = h; lo[i] = rn_tf32(x - h);
+  }
+}
+
 // ---- host side ----------------------------------------------------------------------------------
-template <int BN>
+template <int BN, bool PRECISE>
 int launch(const TapGemm& g, cudaStream_t st) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, PRECISE>;
   static bool configured = false;
   if (!configured) {
-    FS2_CUDA_CHECK(cudaFuncSetAttribute(tap_gemm_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    FS2_CUDA_CHECK(cudaFuncSetAttribute(tap_gemm_tf32_kernel<BN, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     configured = true;
   }
   TcParams p;
   p.K = g.K; p.taps = g.taps; p.pad = (g.taps - 1) / 2; p.N = g.N;
   p.bias = g.bias; p.resid = g.resid; p.ldr = g.ldr; p.out = g.out; p.ldo = g.ldo; p.act = g.act;
   p.vt_out = g.vt_out; p.vt_col0 = g.vt_col0; p.vt_dk = g.vt_dk; p.vt_heads = g.vt_heads; p.vt_lpad = g.vt_lpad; p.vt_L = g.L;
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mb_lo;
   int rc, m_tiles;
   const uint64_t row_bytes = (uint64_t)g.ldx * 4;
   if (g.taps == 1) {  // flat [B*L, K]
@@ -196,29 +254,59 @@ int launch(const TapGemm& g, cudaStream_t st) {
     m_tiles = p.tiles_per_utt * g.B;
     if ((rc = make_map(&ma, g.x, g.K, g.L, g.B, row_bytes, row_bytes * g.L, BM))) return rc;
   }
-  if ((rc = make_map(&mb, g.w, g.K, g.N, g.taps, (uint64_t)g.K * 4, (uint64_t)g.K * 4 * g.N, BN))) return rc;
+  const float* w_hi = PRECISE ? g.w_hi : g.w;
+  if ((rc = make_map(&mb, w_hi, g.K, g.N, g.taps, (uint64_t)g.K * 4, (uint64_t)g.K * 4 * g.N, BN))) return rc;
+  if ((rc = make_map(&mb_lo, PRECISE ? g.w_lo : w_hi, g.K, g.N, g.taps, (uint64_t)g.K * 4, (uint64_t)g.K * 4 * g.N, BN))) return rc;
   dim3 grid(g.N / BN, m_tiles);
-  tap_gemm_tf32_kernel<BN><<<grid, NUM_THREADS, C::SMEM, st>>>(ma, mb, p);
+  tap_gemm_tf32_kernel<BN, PRECISE><<<grid, NUM_THREADS, C::SMEM, st>>>(ma, mb, mb_lo, p);
   FS2_LAUNCH_CHECK();
+  return FS2_OK;
+}
+
+int check_common(const TapGemm& g, const char* who) {
+  FS2_REQUIRE(g.K % 4 == 0 && g.N % 16 == 0, "%s: K (%d) must be a multiple of 4 and N (%d) of 16", who, g.K, g.N);
+  FS2_REQUIRE(g.ldx % 4 == 0 && g.ldo % 4 == 0 && (!g.resid || g.ldr % 4 == 0), "%s: row strides must be 16-byte multiples", who);
+  FS2_REQUIRE((reinterpret_cast<uintptr_t>(g.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.w) & 15) == 0, "%s: operands must be 16-byte aligned", who);
+  FS2_REQUIRE((g.taps & 1) == 1, "%s: taps must be odd", who);
   return FS2_OK;
 }
 
 }  // namespace
 
 int tap_gemm_tf32(const TapGemm& g, cudaStream_t st) {
-  FS2_REQUIRE(g.K % 4 == 0 && g.N % 16 == 0, "tap_gemm_tf32: K (%d) must be a multiple of 4 and N (%d) of 16", g.K, g.N);
-  FS2_REQUIRE(g.ldx % 4 == 0 && g.ldo % 4 == 0 && (!g.resid || g.ldr % 4 == 0), "tap_gemm_tf32: row strides must be 16-byte multiples");
-  FS2_REQUIRE((reinterpret_cast<uintptr_t>(g.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.w) & 15) == 0, "tap_gemm_tf32: operands must be 16-byte aligned");
-  FS2_REQUIRE((g.taps & 1) == 1, "tap_gemm_tf32: taps must be odd");
+  int rc = check_common(g, "tap_gemm_tf32");
+  if (rc) return rc;
   if ((long)g.B * g.L == 0) return FS2_OK;
-  if (g.N % 256 == 0) return launch<256>(g, st);
-  if (g.N % 192 == 0) return launch<192>(g, st);
-  if (g.N % 128 == 0) return launch<128>(g, st);
-  if (g.N % 96 == 0) return launch<96>(g, st);
-  if (g.N % 80 == 0) return launch<80>(g, st);
-  if (g.N % 64 == 0) return launch<64>(g, st);
+  if (g.N % 256 == 0) return launch<256, false>(g, st);
+  if (g.N % 192 == 0) return launch<192, false>(g, st);
+  if (g.N % 128 == 0) return launch<128, false>(g, st);
+  if (g.N % 96 == 0) return launch<96, false>(g, st);
+  if (g.N % 80 == 0) return launch<80, false>(g, st);
+  if (g.N % 64 == 0) return launch<64, false>(g, st);
   set_error("tap_gemm_tf32: N=%d has no supported tile width", g.N);
   return FS2_ERR_INVALID;
+}
+
+int tap_gemm_3xtf32(const TapGemm& g, cudaStream_t st) {
+  int rc = check_common(g, "tap_gemm_3xtf32");
+  if (rc) return rc;
+  FS2_REQUIRE(g.w_hi && g.w_lo, "tap_gemm_3xtf32: split weights missing");
+  if ((long)g.B * g.L == 0) return FS2_OK;
+  // narrower tiles than the plain kernel: the stage holds four operand tiles and the encoder's M is small
+  if (g.N % 128 == 0) return launch<128, true>(g, st);
+  if (g.N % 96 == 0) return launch<96, true>(g, st);
+  if (g.N % 80 == 0) return launch<80, true>(g, st);
+  if (g.N % 64 == 0) return launch<64, true>(g, st);
+  set_error("tap_gemm_3xtf32: N=%d has no supported tile width", g.N);
+  return FS2_ERR_INVALID;
+}
+
+int split_tf32(const float* src, float* hi, float* lo, long n, cudaStream_t st) {
+  if (n == 0) return FS2_OK;
+  long blocks = (n + 255) / 256;
+  split_tf32_kernel<<<(int)(blocks > 1184 ? 1184 : blocks), 256, 0, st>>>(src, hi, lo, n);
+  FS2_LAUNCH_CHECK();
+  return FS2_OK;
 }
 
 }  // namespace fs2

@@ -43,11 +43,15 @@ extern "C" {
 #define FS2_DUR_F32 1
 #define FS2_DUR_I32 2
 
-/* arithmetic of the dense contractions of the decoder side (decoder embed, decoder FFT
- * blocks, mel linear, Postnet).  The encoder, the three predictors and every integer /
- * normalisation / gather kernel always run in fp32. */
-#define FS2_MATH_FP32 0 /* fp32 FMA on CUDA cores everywhere                                 */
-#define FS2_MATH_TF32 1 /* tcgen05 kind::tf32 tensor-core tiles fed by TMA, fp32 accumulate  */
+/* arithmetic of the dense contractions.
+ *   FS2_MATH_FP32: fp32 FMA on CUDA cores everywhere.
+ *   FS2_MATH_TF32: tcgen05 tensor-core tiles fed by TMA with fp32 (TMEM) accumulation:
+ *     decoder side (decoder embed, decoder FFT blocks incl. attention, mel linear, Postnet) in
+ *     plain kind::tf32; encoder GEMMs and the three predictors in 3xTF32 (hi/lo operand split,
+ *     fp32-class accuracy) because their outputs feed round() / bucketize().
+ * Normalisation, softmax statistics, gathers and every integer kernel are fp32 / exact in both. */
+#define FS2_MATH_FP32 0
+#define FS2_MATH_TF32 1
 
 typedef struct fs2_handle fs2_handle;
 
@@ -159,7 +163,9 @@ int fs2_bucketize(const float* vals, const float* bins, int n_edges, int64_t n, 
 /* F.one_hot(ids, n_bins).float(): the 4th/5th return value of _forward(is_inference=True) */
 int fs2_one_hot(const int64_t* ids, int64_t n, int n_bins, float* out, void* stream);
 /* out[b,t,:] = act(sum_j x[b,t+j-pad,:] . W[j] + bias) (+ resid); W [taps][N][K].
- * math_mode selects the kernel family (FS2_MATH_*). act: 0 none, 1 relu, 2 tanh */
+ * math_mode selects the kernel family: FS2_MATH_FP32, FS2_MATH_TF32, or 2 = 3xTF32 (the
+ * error-compensated tensor-core family FS2_MATH_TF32 uses for the encoder and the predictors).
+ * act: 0 none, 1 relu, 2 tanh */
 int fs2_op_tap_gemm(int math_mode, const float* x, int B, int L, int K, const float* w, const float* bias, int N, int taps,
                     int act, const float* resid, float* out, void* stream);
 /* qkv [B,L,3C] (q | k | v, heads contiguous inside each) -> ctx [B,L,C]; lens NULL => no mask */

@@ -226,6 +226,26 @@ def test_tap_gemm_vs_torch(prec, shape):
     close(got, y, tol, str(shape))
 
 
+@pytest.mark.parametrize("shape", [(3, 70, 256, 1024, 9, 1), (2, 333, 256, 768, 1, 0), (5, 41, 256, 256, 3, 1),
+                                   (1, 7, 1024, 256, 1, 0), (2, 130, 256, 80, 5, 0)])
+def test_tap_gemm_3xtf32_is_fp32_class(shape):
+    """The error-compensated tensor-core family used for the encoder / predictors in tf32 mode must sit at
+    fp32-level error (its outputs feed round() and bucketize())."""
+    B, L, K, N, taps, act = shape
+    g = torch.Generator().manual_seed(hash(shape) & 0xffff)
+    x = torch.randn(B, L, K, generator=g) * 2; w = torch.randn(N, K, taps, generator=g) / (K * taps) ** 0.5
+    bias = torch.randn(N, generator=g); resid = torch.randn(B, L, N, generator=g)
+    y = torch.nn.functional.conv1d(x.transpose(1, 2).double(), w.double(), bias.double(), padding=(taps - 1) // 2).transpose(1, 2)
+    y = torch.relu(y) if act == 1 else y
+    y = (y + resid.double()).float()
+    wp = w.permute(2, 0, 1).contiguous().cuda()
+    got3 = _tap_gemm(2, x.cuda(), wp, bias.cuda(), act, resid.cuda())
+    got32 = _tap_gemm(0, x.cuda(), wp, bias.cuda(), act, resid.cuda())
+    e3, e32 = float((got3.cpu() - y).abs().max()), float((got32.cpu() - y).abs().max())
+    print(f"3xtf32 max err {e3:.3e} vs fp32-FMA {e32:.3e} for {shape}")
+    close(got3, y, dict(max=2e-5, mean=2e-6), str(shape))
+
+
 @pytest.mark.parametrize("prec", PRECISIONS)
 @pytest.mark.parametrize("C,L,masked", [(256, 100, True), (384, 333, True), (384, 800, False), (256, 37, False)])
 def test_attention_vs_torch(prec, C, L, masked):
