@@ -247,8 +247,9 @@ def run_b200(args):
         import ctypes as C
         h = model._handle
         lib.fs2_profile_enable(h, 1)
-        for _ in range(3):
-            step(devin)
+        for _ in range(3):   # local forward only: the other ranks are not in this loop, so no collective here
+            with torch.no_grad():
+                model._forward(devin["xs"], devin["ilens"], devin["olens"], devin["ds"], devin["es"], devin["ps"], is_inference=False)
         torch.cuda.synchronize()
         n = lib.fs2_profile_classes()
         ms = (C.c_double * n)(); cnt = (C.c_int64 * n)(); fl = (C.c_double * n)(); by = (C.c_double * n)()

@@ -1,5 +1,6 @@
 // Tensor-core "tap GEMM" for sm_100a: tcgen05.mma kind::tf32 with TMEM accumulators, operands
-// staged in shared memory by TMA (cp.async.bulk.tensor, 128-byte swizzle), mbarrier pipeline.
+// staged in shared memory by TMA (cp.async.bulk.tensor, 128-byte swizzle), mbarrier pipelines,
+// persistent CTAs.
 //
 //   out[b,t,n] = act( sum_{j<taps} sum_{k<K} x[b, t+j-pad, k] * w[j][n][k] + bias[n] ) (+ resid[b,t,n])
 //
@@ -9,7 +10,7 @@
 //   * the encoder and the three predictors in *3xTF32* (PRECISE = true): every operand is split
 //     into hi = rn_tf32(x) and lo = rn_tf32(x - hi) and the product is accumulated as
 //     hi*hi + lo*hi + hi*lo in the fp32 TMEM accumulator (the dropped lo*lo term is ~2^-22
-//     relative), which gives fp32-class results on the tensor pipe.  Their outputs feed round() /
+//     relative), which gives near-fp32 results on the tensor pipe.  Their outputs feed round() /
 //     bucketize(), where plain tf32 noise (~1e-3) would flip integers.
 //
 // Why no im2col: activations are [B, time, channel] fp32 with channels innermost, which *is* the
@@ -20,16 +21,17 @@
 // memory is consumed directly by kind::tf32, so there is no conversion pass either.
 // K loop = taps x ceil(K / 32) pipeline steps of 4 (12 when PRECISE) MMAs with K = 8 each.
 //
-// CTA = one 128 x BN output tile, 6 warps:
-//   warp 0   : TMA producer (one elected lane)                    smem ring of STAGES slots
-//   warp 1   : TMEM allocator + MMA issuer (one elected lane)     full/empty mbarriers per slot
-//   warps 2-5: PRECISE only: while the main loop runs they split each landed A tile in place into
-//              hi / lo (element-wise, so the swizzled layout is untouched) and hand the slot to the
-//              MMA warp through a third mbarrier; the weight hi / lo arrays are split once at load.
-//              Then the epilogue, thread == output row (TMEM lane): tcgen05.ld 32 columns at a
-//              time, bias / ReLU / tanh / residual in registers, 16-byte global stores (or the
-//              transposed V store for the attention kernel).
-// Convolutions tile each utterance separately (ceil(L/128) tiles) so the shifted boxes never
+// One persistent CTA per SM walks the 128 x BN output tiles (n fastest, so concurrently running
+// CTAs share weight tiles in L2).  Three pipelines:
+//   smem ring   : warp 0 (TMA producer, one lane)  <-> warp 1 (MMA issuer, one lane), full/empty mbarriers
+//   TMEM        : two accumulator buffers; warp 1 fills buffer i&1 while warps 2-5 drain the other
+//   output      : warps 2-5 (thread == output row == TMEM lane): tcgen05.ld 32 columns -> bias / ReLU /
+//                 tanh / residual -> 128-byte-swizzled smem staging -> TMA tensor store (rows past the
+//                 utterance end are clipped by the TMA unit), double buffered with bulk-group waits
+//   PRECISE only: warps 6-9 split each landed A tile in place into hi / lo (element-wise, so the
+//                 swizzled layout is untouched) and hand the slot to the MMA warp through a third
+//                 mbarrier; the weight hi / lo arrays are split once at load time.
+// Convolutions tile each utterance separately (ceil(L/128) row tiles) so the shifted boxes never
 // cross an utterance boundary; plain GEMMs (taps == 1) tile the flat [B*L, K] matrix.
 // Every mbarrier wait is bounded: a pipeline bug traps instead of hanging the GPU.
 #include "tc_common.cuh"
@@ -42,26 +44,30 @@ constexpr int BM = 128;
 constexpr int BK = 32;                 // fp32 elements per pipeline step = one 128-byte swizzle row
 constexpr int UMMA_K = 8;              // tf32
 constexpr int A_BYTES = BM * BK * 4;   // 16 KB
-constexpr int NUM_THREADS = 192;
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int STAGING_BYTES = 2 * BM * 32 * 4;   // two [128 x 32] fp32 output boxes
+constexpr int RING_BUDGET = 227 * 1024 - STAGING_BYTES - 1024 /*align slack*/ - 512 /*barriers*/;
 
 struct TcParams {
-  int L, M_rows, tiles_per_utt;  // tiles_per_utt == 0: flat tiling over M_rows = B*L
-  int K, taps, pad, N;
-  const float* bias; const float* resid; int ldr;
-  float* out; int ldo; int act;
+  int L, tiles_per_utt;          // tiles_per_utt == 0: flat tiling, L = B*L rows
+  int m_tiles, n_tiles;
+  int K, taps, pad;
+  const float* bias; const float* resid; int ldr; int act;
   // optional: columns >= vt_col0 are the V third of a q|k|v projection and are stored transposed,
   // vt[(b*heads + h)*dk + d][t] with row pitch vt_lpad, for the attention kernel's K-major P.V operand
   float* vt_out; int vt_col0, vt_dk, vt_heads, vt_lpad, vt_L;
 };
 
+constexpr int pow2_at_least(int x) { return x <= 32 ? 32 : x <= 64 ? 64 : x <= 128 ? 128 : 256; }
+
 template <int BN, bool PRECISE>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = (PRECISE ? 2 : 1) * (A_BYTES + B_BYTES);   // [A(hi)][A lo][B hi][B lo]
-  static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
-  static constexpr int TMEM_COLS = BN > 128 ? 256 : (BN > 64 ? 128 : 64);
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
+  static constexpr int ACC_STRIDE = pow2_at_least(BN);     // TMEM columns per accumulator buffer
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int THREADS = PRECISE ? 320 : 192;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
   static constexpr uint32_t IDESC = idesc_tf32(BM, BN);
   static constexpr int A_LO = A_BYTES;                                  // offsets inside a stage
   static constexpr int B_HI = PRECISE ? 2 * A_BYTES : A_BYTES;
@@ -69,7 +75,7 @@ struct Cfg {
   static constexpr uint32_t TX_BYTES = A_BYTES + (PRECISE ? 2 : 1) * B_BYTES;
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128");
   static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment");
-  static_assert(STAGES >= 2, "pipeline depth");
+  static_assert(STAGES >= 2 && TMEM_COLS <= 512, "resources");
 };
 
 __device__ __forceinline__ float rn_tf32(float x) {
@@ -79,79 +85,170 @@ __device__ __forceinline__ float rn_tf32(float x) {
 }
 
 template <int BN, bool PRECISE>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(Cfg<BN, PRECISE>::THREADS, 1)
 tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                     const __grid_constant__ CUtensorMap tmap_b_lo, TcParams p) {
+                     const __grid_constant__ CUtensorMap tmap_b_lo, const __grid_constant__ CUtensorMap tmap_out, TcParams p) {
   using C = Cfg<BN, PRECISE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + (size_t)C::STAGES * C::STAGE_BYTES);
+  uint8_t* staging = tiles + (size_t)C::STAGES * C::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* split_bar = empty_bar + C::STAGES;
-  uint64_t* tmem_full_bar = split_bar + C::STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* acc_full = split_bar + C::STAGES;     // [2] MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;             // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  int b, t0;
-  if (p.tiles_per_utt > 0) { b = blockIdx.y / p.tiles_per_utt; t0 = (blockIdx.y - b * p.tiles_per_utt) * BM; }
-  else { b = 0; t0 = blockIdx.y * BM; }
   const int kchunks = (p.K + BK - 1) / BK;
   const int steps = p.taps * kchunks;
+  const int total_tiles = p.m_tiles * p.n_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], 4); }
-    mbar_init(tmem_full_bar, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);   // whole warp: accumulator columns
+  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);   // whole warp: both accumulator buffers
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  auto tile_coords = [&](int tile, int& n0, int& b, int& t0) {
+    const int mt = tile / p.n_tiles;
+    n0 = (tile - mt * p.n_tiles) * BN;
+    if (p.tiles_per_utt > 0) { b = mt / p.tiles_per_utt; t0 = (mt - b * p.tiles_per_utt) * BM; }
+    else { b = 0; t0 = mt * BM; }
+  };
+
   if (warp == 0) {
     if (lane == 0) {  // ---- TMA producer ----
-      for (int s = 0; s < steps; ++s) {
-        const int slot = s % C::STAGES, round = s / C::STAGES;
-        mbar_wait(&empty_bar[slot], (round & 1) ^ 1);
-        const int j = s / kchunks, k0 = (s - j * kchunks) * BK;
-        uint8_t* st = tiles + (size_t)slot * C::STAGE_BYTES;
-        mbar_expect_tx(&full_bar[slot], C::TX_BYTES);
-        tma_load_3d(st, &tmap_a, &full_bar[slot], k0, t0 + j - p.pad, b);
-        tma_load_3d(st + C::B_HI, &tmap_b, &full_bar[slot], k0, n0, j);
-        if (PRECISE) tma_load_3d(st + C::B_LO, &tmap_b_lo, &full_bar[slot], k0, n0, j);
+      int n = 0;      // ring position, runs across tiles
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int n0, b, t0;
+        tile_coords(tile, n0, b, t0);
+        for (int s = 0; s < steps; ++s, ++n) {
+          const int slot = n % C::STAGES, round = n / C::STAGES;
+          mbar_wait(&empty_bar[slot], (round & 1) ^ 1);
+          const int j = s / kchunks, k0 = (s - j * kchunks) * BK;
+          uint8_t* st = tiles + (size_t)slot * C::STAGE_BYTES;
+          mbar_expect_tx(&full_bar[slot], C::TX_BYTES);
+          tma_load_3d(st, &tmap_a, &full_bar[slot], k0, t0 + j - p.pad, b);
+          tma_load_3d(st + C::B_HI, &tmap_b, &full_bar[slot], k0, n0, j);
+          if (PRECISE) tma_load_3d(st + C::B_LO, &tmap_b_lo, &full_bar[slot], k0, n0, j);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ---- MMA issuer ----
-      for (int s = 0; s < steps; ++s) {
-        const int slot = s % C::STAGES, round = s / C::STAGES;
-        mbar_wait(PRECISE ? &split_bar[slot] : &full_bar[slot], round & 1);
+      int n = 0, it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1);   // epilogue has drained this buffer (first two uses pass)
         tcgen05_fence_after();
-        const uint32_t base = smem_u32(tiles + (size_t)slot * C::STAGE_BYTES);
-        const uint64_t a_hi = make_sw128_kmajor_desc(base), b_hi = make_sw128_kmajor_desc(base + C::B_HI);
+        const uint32_t d = tmem_base + (uint32_t)(acc * C::ACC_STRIDE);
+        for (int s = 0; s < steps; ++s, ++n) {
+          const int slot = n % C::STAGES, round = n / C::STAGES;
+          mbar_wait(PRECISE ? &split_bar[slot] : &full_bar[slot], round & 1);
+          tcgen05_fence_after();
+          const uint32_t base = smem_u32(tiles + (size_t)slot * C::STAGE_BYTES);
+          const uint64_t a_hi = make_sw128_kmajor_desc(base), b_hi = make_sw128_kmajor_desc(base + C::B_HI);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {  // +32 bytes along K inside the swizzle row = +2 in descriptor units
-          if (PRECISE) {
-            const uint64_t a_lo = make_sw128_kmajor_desc(base + C::A_LO), b_lo = make_sw128_kmajor_desc(base + C::B_LO);
-            umma_tf32(tmem_base, a_lo + 2 * k, b_hi + 2 * k, C::IDESC, (s | k) != 0);   // small terms first
-            umma_tf32(tmem_base, a_hi + 2 * k, b_lo + 2 * k, C::IDESC, 1);
-            umma_tf32(tmem_base, a_hi + 2 * k, b_hi + 2 * k, C::IDESC, 1);
-          } else {
-            umma_tf32(tmem_base, a_hi + 2 * k, b_hi + 2 * k, C::IDESC, (s | k) != 0);
+          for (int k = 0; k < BK / UMMA_K; ++k) {  // +32 bytes along K inside the swizzle row = +2 in descriptor units
+            if (PRECISE) {
+              const uint64_t a_lo = make_sw128_kmajor_desc(base + C::A_LO), b_lo = make_sw128_kmajor_desc(base + C::B_LO);
+              umma_tf32(d, a_lo + 2 * k, b_hi + 2 * k, C::IDESC, (s | k) != 0);   // small terms first
+              umma_tf32(d, a_hi + 2 * k, b_lo + 2 * k, C::IDESC, 1);
+              umma_tf32(d, a_hi + 2 * k, b_hi + 2 * k, C::IDESC, 1);
+            } else {
+              umma_tf32(d, a_hi + 2 * k, b_hi + 2 * k, C::IDESC, (s | k) != 0);
+            }
           }
+          tcgen05_commit(&empty_bar[slot]);    // slot reusable once these MMAs have read it
         }
-        tcgen05_commit(&empty_bar[slot]);    // slot reusable once these MMAs have read it
+        tcgen05_commit(&acc_full[acc]);        // accumulator complete
       }
-      tcgen05_commit(tmem_full_bar);         // accumulator complete
     }
-  } else {
-    if (PRECISE) {
-      // ---- operand split: A tile -> hi (in place) and lo (second buffer), same swizzled positions ----
-      const int tid = threadIdx.x - 64;      // 0..127
-      for (int s = 0; s < steps; ++s) {
-        const int slot = s % C::STAGES, round = s / C::STAGES;
+  } else if (warp < 6) {
+    // ---- epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31; thread == output row ----
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;
+    const bool elected = threadIdx.x == 64;      // warp 2 lane 0 issues the tensor stores
+    const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+    float v[32];
+    int it = 0, chunk_no = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      int n0, b, t0;
+      tile_coords(tile, n0, b, t0);
+      const int acc = it & 1;
+      mbar_wait(&acc_full[acc], (it >> 1) & 1);
+      tcgen05_fence_after();
+      const int t = t0 + row;
+      const bool row_ok = t < p.L;               // flat mode: L == total rows
+      const long m = (long)b * p.L + t;
+      const uint32_t taddr = tmem_base + lane_off + (uint32_t)(acc * C::ACC_STRIDE);
+      const bool to_vt = p.vt_out != nullptr && n0 >= p.vt_col0;   // tile-uniform (tile widths divide the V third)
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (to_vt) {
+          __syncwarp();
+          tmem_ld32(taddr + c0, v);
+          if (row_ok) {
+            // transposed store: for a fixed column the 32 lanes hold 32 consecutive time steps -> 128-byte rows
+            const long ub = m / p.vt_L; const int ut = (int)(m - ub * p.vt_L);
+            const int rel = n0 + c0 - p.vt_col0, hh = rel / p.vt_dk, d0 = rel - hh * p.vt_dk;
+            float* dst = p.vt_out + ((ub * p.vt_heads + hh) * p.vt_dk + d0) * (long)p.vt_lpad + ut;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c0 + i < BN) dst[(long)i * p.vt_lpad] = v[i] + (p.bias ? __ldg(p.bias + n0 + c0 + i) : 0.f);
+          }
+          continue;
+        }
+        const int buf = chunk_no & 1;
+        ++chunk_no;
+        if (elected) tma_store_wait_read<1>();   // the store issued from this staging buffer two chunks ago has read it
+        named_bar_sync(1, 128);
+        tmem_ld32(taddr + c0, v);
+        float4* srow = reinterpret_cast<float4*>(staging + (size_t)buf * (BM * 128) + (size_t)row * 128);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int n = n0 + c0 + q * 4;
+          float4 o = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          if (c0 + q * 4 < BN) {
+            if (p.bias) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+              o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+            }
+            if (p.act == ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            else if (p.act == ACT_TANH) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
+            if (p.resid && row_ok) {
+              const float4 rv = __ldg(reinterpret_cast<const float4*>(p.resid + m * p.ldr + n));
+              o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+            }
+          }
+          srow[q ^ (row & 7)] = o;               // 128-byte swizzle: 16-byte chunk index XOR (row mod 8)
+        }
+        fence_proxy_async();                     // generic-proxy smem writes -> visible to the TMA unit
+        named_bar_sync(1, 128);
+        if (elected) {
+          tma_store_3d(&tmap_out, staging + (size_t)buf * (BM * 128), n0 + c0, t0, b);
+          tma_store_commit();
+        }
+      }
+      // all TMEM reads of this tile are complete (every thread passed its last tcgen05.wait::ld)
+      tcgen05_fence_before();
+      named_bar_sync(1, 128);
+      if (elected) mbar_arrive(&acc_empty[acc]);
+    }
+    if (elected) tma_store_wait_all<0>();        // stores must complete before the CTA exits
+  } else if (PRECISE) {
+    // ---- operand split (warps 6..9): A tile -> hi (in place) and lo (second buffer), same swizzled positions ----
+    const int tid = threadIdx.x - 192;      // 0..127
+    int n = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int s = 0; s < steps; ++s, ++n) {
+        const int slot = n % C::STAGES, round = n / C::STAGES;
         mbar_wait(&full_bar[slot], round & 1);
         float4* a = reinterpret_cast<float4*>(tiles + (size_t)slot * C::STAGE_BYTES);
         float4* lo = reinterpret_cast<float4*>(tiles + (size_t)slot * C::STAGE_BYTES + C::A_LO);
@@ -164,52 +261,9 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           l.x = rn_tf32(x.x - h.x); l.y = rn_tf32(x.y - h.y); l.z = rn_tf32(x.z - h.z); l.w = rn_tf32(x.w - h.w);
           a[idx] = h; lo[idx] = l;
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core
         __syncwarp();
         if (lane == 0) mbar_arrive(&split_bar[slot]);
-      }
-    }
-    // ---- epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31; thread == output row ----
-    mbar_wait(tmem_full_bar, 0);
-    tcgen05_fence_after();
-    const int row = (warp & 3) * 32 + lane;
-    const int t = t0 + row;
-    const bool row_ok = t < p.L;               // flat mode: L == M_rows
-    const long m = (long)b * p.L + t;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    float v[32];
-    const bool to_vt = p.vt_out != nullptr && n0 >= p.vt_col0;   // tile-uniform (tile widths divide the V third)
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      __syncwarp();
-      tmem_ld32(lane_addr + c0, v);            // warp-collective: executed by all lanes regardless of row_ok
-      if (row_ok && to_vt) {
-        // transposed store: for a fixed column the 32 lanes hold 32 consecutive time steps -> 128-byte rows
-        const long ub = m / p.vt_L; const int ut = (int)(m - ub * p.vt_L);
-        const int rel = n0 + c0 - p.vt_col0, hh = rel / p.vt_dk, d0 = rel - hh * p.vt_dk;
-        float* dst = p.vt_out + ((ub * p.vt_heads + hh) * p.vt_dk + d0) * (long)p.vt_lpad + ut;
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c0 + i < BN) dst[(long)i * p.vt_lpad] = v[i] + (p.bias ? __ldg(p.bias + n0 + c0 + i) : 0.f);
-      } else if (row_ok) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int n = n0 + c0 + q * 4;
-          if (c0 + q * 4 < BN) {
-            float4 o = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-            if (p.bias) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-              o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-            }
-            if (p.act == ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            else if (p.act == ACT_TANH) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
-            if (p.resid) {
-              const float4 rv = __ldg(reinterpret_cast<const float4*>(p.resid + m * p.ldr + n));
-              o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
-            }
-            *reinterpret_cast<float4*>(p.out + m * p.ldo + n) = o;
-          }
-        }
       }
     }
   }
@@ -229,6 +283,16 @@ __global__ void split_tf32_kernel(const float* __restrict__ src, float* __restri
 }
 
 // ---- host side ----------------------------------------------------------------------------------
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 template <int BN, bool PRECISE>
 int launch(const TapGemm& g, cudaStream_t st) {
   using C = Cfg<BN, PRECISE>;
@@ -238,27 +302,31 @@ int launch(const TapGemm& g, cudaStream_t st) {
     configured = true;
   }
   TcParams p;
-  p.K = g.K; p.taps = g.taps; p.pad = (g.taps - 1) / 2; p.N = g.N;
-  p.bias = g.bias; p.resid = g.resid; p.ldr = g.ldr; p.out = g.out; p.ldo = g.ldo; p.act = g.act;
+  p.K = g.K; p.taps = g.taps; p.pad = (g.taps - 1) / 2;
+  p.bias = g.bias; p.resid = g.resid; p.ldr = g.ldr; p.act = g.act;
   p.vt_out = g.vt_out; p.vt_col0 = g.vt_col0; p.vt_dk = g.vt_dk; p.vt_heads = g.vt_heads; p.vt_lpad = g.vt_lpad; p.vt_L = g.L;
-  CUtensorMap ma, mb, mb_lo;
-  int rc, m_tiles;
-  const uint64_t row_bytes = (uint64_t)g.ldx * 4;
+  CUtensorMap ma, mb, mb_lo, mo;
+  int rc;
+  const uint64_t row_bytes = (uint64_t)g.ldx * 4, orow = (uint64_t)g.ldo * 4;
   if (g.taps == 1) {  // flat [B*L, K]
     const uint64_t M = (uint64_t)g.B * g.L;
-    p.L = (int)M; p.M_rows = (int)M; p.tiles_per_utt = 0;
-    m_tiles = (int)((M + BM - 1) / BM);
+    p.L = (int)M; p.tiles_per_utt = 0;
+    p.m_tiles = (int)((M + BM - 1) / BM);
     if ((rc = make_map(&ma, g.x, g.K, M, 1, row_bytes, row_bytes * M, BM))) return rc;
+    if ((rc = make_map(&mo, g.out, g.N, M, 1, orow, orow * M, BM))) return rc;
   } else {            // per-utterance tiles: shifted boxes zero-fill outside [0, L)
-    p.L = g.L; p.M_rows = g.B * g.L; p.tiles_per_utt = (g.L + BM - 1) / BM;
-    m_tiles = p.tiles_per_utt * g.B;
+    p.L = g.L; p.tiles_per_utt = (g.L + BM - 1) / BM;
+    p.m_tiles = p.tiles_per_utt * g.B;
     if ((rc = make_map(&ma, g.x, g.K, g.L, g.B, row_bytes, row_bytes * g.L, BM))) return rc;
+    if ((rc = make_map(&mo, g.out, g.N, g.L, g.B, orow, orow * g.L, BM))) return rc;
   }
+  p.n_tiles = g.N / BN;
   const float* w_hi = PRECISE ? g.w_hi : g.w;
   if ((rc = make_map(&mb, w_hi, g.K, g.N, g.taps, (uint64_t)g.K * 4, (uint64_t)g.K * 4 * g.N, BN))) return rc;
   if ((rc = make_map(&mb_lo, PRECISE ? g.w_lo : w_hi, g.K, g.N, g.taps, (uint64_t)g.K * 4, (uint64_t)g.K * 4 * g.N, BN))) return rc;
-  dim3 grid(g.N / BN, m_tiles);
-  tap_gemm_tf32_kernel<BN, PRECISE><<<grid, NUM_THREADS, C::SMEM, st>>>(ma, mb, mb_lo, p);
+  const int total = p.m_tiles * p.n_tiles;
+  const int grid = total < sm_count() ? total : sm_count();
+  tap_gemm_tf32_kernel<BN, PRECISE><<<grid, C::THREADS, C::SMEM, st>>>(ma, mb, mb_lo, mo, p);
   FS2_LAUNCH_CHECK();
   return FS2_OK;
 }
@@ -266,7 +334,8 @@ int launch(const TapGemm& g, cudaStream_t st) {
 int check_common(const TapGemm& g, const char* who) {
   FS2_REQUIRE(g.K % 4 == 0 && g.N % 16 == 0, "%s: K (%d) must be a multiple of 4 and N (%d) of 16", who, g.K, g.N);
   FS2_REQUIRE(g.ldx % 4 == 0 && g.ldo % 4 == 0 && (!g.resid || g.ldr % 4 == 0), "%s: row strides must be 16-byte multiples", who);
-  FS2_REQUIRE((reinterpret_cast<uintptr_t>(g.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.w) & 15) == 0, "%s: operands must be 16-byte aligned", who);
+  FS2_REQUIRE((reinterpret_cast<uintptr_t>(g.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.w) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(g.out) & 15) == 0, "%s: operands must be 16-byte aligned", who);
   FS2_REQUIRE((g.taps & 1) == 1, "%s: taps must be odd", who);
   return FS2_OK;
 }
