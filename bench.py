@@ -41,6 +41,7 @@ WORKLOADS = {
     # name: (B per GPU, T, L)
     "c2": (64, 100, 800),     # BASELINE.json configs[1]: batch=64 LJSpeech-length on 1xB200 (headline)
     "c4": (32, 250, 2000),    # configs[3]: long-form
+    "c5": (256, 100, 0),      # configs[4]: LengthRegulator stress (ds ~ U{1..15}, alpha = 4): LR kernels only
 }
 HOP, SR = 256, 22050
 
@@ -160,7 +161,77 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_length_regulator(args):
+    """BASELINE config 5: LengthRegulator alone, B=256, T=100, C=256, ds ~ U{1..15}, alpha=4.0 (round half even)
+    -> Lmax ~ 3.7k frames, ~0.97 GB written per step.  HBM-bound: report GB/s against the measured copy peak."""
+    from fastspeech2_b200 import LengthRegulator, _lib
+    from oracle import fs2_oracle as O
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    B, T, _ = WORKLOADS["c5"]
+    g = torch.Generator().manual_seed(1234)
+    hs = torch.randn(B, T, 256, generator=g)
+    ds = torch.randint(1, 16, (B, T), generator=g)
+    il = torch.full((B,), T, dtype=torch.int64)
+    hs_d, ds_d, il_d = hs.to(dev), ds.to(dev), il.to(dev)
+    hs_h, ds_h = hs.pin_memory(), ds.pin_memory()
+    lr = LengthRegulator()
+    out = lr(hs_d, ds_d, il_d, alpha=4.0)
+    Lmax = out.shape[1]
+    frames = int(torch.round(ds.float() * 4.0).long().sum())
+    algo_bytes = B * T * 256 * 4 + B * T * 8 + B * Lmax * 256 * 4
+    out_h = torch.empty(out.shape, dtype=torch.float32).pin_memory()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    n0 = lib.fs2_kernel_launches()
+    ms = timed(lambda: lr(hs_d, ds_d, il_d, alpha=4.0), args.steps, max(args.warmup, 3))
+    launches = (lib.fs2_kernel_launches() - n0) // (args.steps + max(args.warmup, 3))
+
+    def e2e():
+        o = lr(hs_h.to(dev, non_blocking=True), ds_h.to(dev, non_blocking=True), il_d, alpha=4.0)
+        out_h.copy_(o, non_blocking=True)
+    ms_e2e = timed(e2e, max(2, args.steps // 2), 1)
+    # the gather kernel alone (the plan kernel + the host read of Lmax are latency, not bandwidth)
+    from fastspeech2_b200 import length_regulator as _lrmod
+    cum, _, _, il_dev = _lrmod.plan(hs_d, ds_d, il_d, 4.0)
+    ms_gather = timed(lambda: _lrmod.gather(hs_d, cum, il_dev, Lmax), args.steps, 3)
+    hbm, _, _, src = peaks()
+    t0 = time.perf_counter(); ref = O.length_regulator(hs, ds.clone(), il, alpha=4.0); cpu_s = time.perf_counter() - t0
+    assert torch.equal(out.cpu(), ref), "LengthRegulator output differs from the oracle"
+    line = {
+        "metric": "mel-frames/sec (LengthRegulator only)", "value": frames / (ms * 1e-3), "unit": "frames/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 copy / i64 scan", "data": "synthetic",
+        "config": {"workload": "c5", "B": B, "T": T, "C": 256, "alpha": 4.0, "Lmax": Lmax, "bit_exact_vs_oracle": True,
+                   "l2": "0.97 GB output per step >> 126 MB L2; the 26 MB input is legitimately L2-resident (each row is read ~32x)"},
+        "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": hs_h.numel() * 4 + ds_h.numel() * 8, "d2h_bytes_per_step": out_h.numel() * 4},
+        "gpu_launches": int(launches * args.steps), "gpu_launches_per_step": int(launches),
+        "roofline": {"kernel": "length_gather_kernel", "bound": "hbm", "achieved": algo_bytes / (ms_gather * 1e-3) / 1e9, "peak": hbm,
+                     "unit": "GB/s", "frac": algo_bytes / (ms_gather * 1e-3) / 1e9 / hbm, "traffic": None,
+                     "avg_launch_ms": ms_gather, "algorithmic_bytes": algo_bytes, "peak_source": src,
+                     "whole_op_gbs": algo_bytes / (ms * 1e-3) / 1e9},
+        "cpu_baseline": {"value": frames / cpu_s, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": "one full-size call of the oracle (repeat_interleave per utterance; the reference's per-phoneme Python loop took 12.4 s in the survey)"},
+    }
+    print(json.dumps(line), flush=True)
+
+
 def run_b200(args):
+    if args.workload == "c5":
+        return run_length_regulator(args)
     import torch.distributed as dist
     from fastspeech2_b200 import FeedForwardTransformer, _lib, synthetic_state_dict
     from fastspeech2_b200.hparams import load_hp

@@ -16,8 +16,9 @@
 // of S, and accumulates O += P V^T and the row sums; no accumulator rescaling, O /= sum at the end.
 // That costs 1.5x the MMA work of a one-pass online softmax but keeps O untouched in TMEM.
 //
-// Warp roles (6 warps): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = softmax /
-// epilogue (thread == query row == TMEM lane).  TMEM: two S/P buffers (2 x 128 columns) so the
+// Warp roles (10 warps): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..9 = softmax /
+// epilogue (two threads per query row == TMEM lane, 64 score columns each; row statistics are
+// combined through shared memory once per pass).  TMEM: two S/P buffers (2 x 128 columns) so the
 // tensor core computes S_{j+1} while the softmax warps work on tile j, plus DK columns of O.
 // Shared memory: Q resident (DK/32 boxes of 16 KB) + a ring of 24 KB slots for K / V^T boxes.
 #include <math.h>
@@ -29,7 +30,7 @@ namespace {
 using namespace tc;
 
 constexpr int BQ = 128, BKV = 128, CH = 32;   // CH: fp32 per 128-byte swizzle row
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;   // TMA, MMA, 8 softmax / epilogue warps
 
 template <int DK>
 struct ACfg {
@@ -39,12 +40,12 @@ struct ACfg {
   static constexpr int V_BOX = DK * CH * 4;            // DK rows x 32 kv
   static constexpr int SLOT = V_BOX > K_BOX ? V_BOX : K_BOX;
   static constexpr int SLOTS = (212 * 1024 - Q_BYTES) / SLOT;
-  static constexpr size_t SMEM = (size_t)Q_BYTES + (size_t)SLOTS * SLOT + 1024 + 512;
+  static constexpr size_t SMEM = (size_t)Q_BYTES + (size_t)SLOTS * SLOT + 1024 + 512 + 2 * BQ * 4;
   static constexpr uint32_t IDESC_S = idesc_tf32(BQ, BKV);
   static constexpr uint32_t IDESC_O = idesc_tf32(BQ, DK);
   static constexpr int TMEM_COLS = 512;
   static constexpr int O_COL = 2 * BKV;                // S/P buffers at columns 0 and 128
-  static_assert(DK % CH == 0 && DK % 16 == 0 && DK <= 256, "d_k");
+  static_assert(DK % 64 == 0 && DK <= 256, "d_k");
   static_assert(SLOT % 1024 == 0 && SLOTS >= 3, "ring");
 };
 
@@ -68,6 +69,7 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_
   uint64_t* p_full = s_free + 2;               // [2] softmax -> MMA: P written
   uint64_t* o_full = p_full + 2;               // all P.V done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  float* xchg = reinterpret_cast<float*>(tmem_slot + 4);   // [2][BQ] row-statistic exchange between column halves
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
@@ -77,7 +79,7 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_
   if (threadIdx.x == 0) {
     for (int s = 0; s < A::SLOTS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(q_bar, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4); mbar_init(&p_full[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 8); mbar_init(&p_full[i], 8); }
     mbar_init(o_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -160,63 +162,66 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_
         tcgen05_commit(o_full);
       }
     } else {
-      // ---- softmax / epilogue warps: thread == query row ----
-      const int wq = warp & 3;
+      // ---- softmax / epilogue: 8 warps; warps w and w+4 share TMEM lane quarter w%4 and split the columns ----
+      const int wq = warp & 3, half = (warp - 2) >> 2;          // half 0: columns [0,64), half 1: [64,128)
+      const int row = wq * 32 + lane;
       const uint32_t lane_addr = tmem_base + ((uint32_t)(wq * 32) << 16);
-      float v[32];
+      float v[64];
       float m_row = -INFINITY;
-      // pass 1: exact row maximum of the raw scores over valid keys
+      // pass 1: exact row maximum of the raw scores over valid keys (this thread: its 64 columns of every tile)
       for (int j = 0; j < J; ++j) {
         mbar_wait(&s_full[j & 1], (j >> 1) & 1);
         tcgen05_fence_after();
-        const int kv0 = j * BKV;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BKV; c0 += 32) {
-          __syncwarp();
-          tmem_ld32(lane_addr + (uint32_t)((j & 1) * BKV + c0), v);
+        const int kv0 = j * BKV + half * 64;
+        __syncwarp();
+        const uint32_t ta = lane_addr + (uint32_t)((j & 1) * BKV + half * 64);
+        tmem_ld32_nowait(ta, v); tmem_ld32_nowait(ta + 32, v + 32); tmem_ld_wait_pin<64>(v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) if (kv0 + c0 + i < len) m_row = fmaxf(m_row, v[i]);
-        }
+        for (int i = 0; i < 64; ++i) if (kv0 + i < len) m_row = fmaxf(m_row, v[i]);
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[j & 1]);
       }
-      // pass 2: P = exp(scale * (s - max)) in place of S, row sums
+      xchg[half * BQ + row] = m_row;                             // combine the two column halves of each row
+      named_bar_sync(1, 256);
+      m_row = fmaxf(m_row, xchg[(half ^ 1) * BQ + row]);
+      named_bar_sync(1, 256);
+      // pass 2: P = exp2(scale*log2e * (s - max)) in place of S, partial row sums
       const float mb = m_row * p.scale_log2e;
       float l_row = 0.f;
       for (int j = 0; j < J; ++j) {
         const int g = J + j;
         mbar_wait(&s_full[g & 1], (g >> 1) & 1);
         tcgen05_fence_after();
-        const int kv0 = j * BKV;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BKV; c0 += 32) {
-          __syncwarp();
-          const uint32_t ta = lane_addr + (uint32_t)((g & 1) * BKV + c0);
-          tmem_ld32(ta, v);
+        const int kv0 = j * BKV + half * 64;
+        __syncwarp();
+        const uint32_t ta = lane_addr + (uint32_t)((g & 1) * BKV + half * 64);
+        tmem_ld32_nowait(ta, v); tmem_ld32_nowait(ta + 32, v + 32); tmem_ld_wait_pin<64>(v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float e = (kv0 + c0 + i < len) ? exp2f(fmaf(v[i], p.scale_log2e, -mb)) : 0.f;
-            v[i] = e; l_row += e;
-          }
-          tmem_st32(ta, v);
+        for (int i = 0; i < 64; ++i) {
+          const float e = (kv0 + i < len) ? fast_exp2(fmaf(v[i], p.scale_log2e, -mb)) : 0.f;
+          v[i] = e; l_row += e;
         }
+        tmem_st32(ta, v); tmem_st32(ta + 32, v + 32);
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[g & 1]);
       }
-      // epilogue: O / l -> ctx rows (0 for masked query rows)
+      xchg[half * BQ + row] = l_row;
+      named_bar_sync(1, 256);
+      l_row += xchg[(half ^ 1) * BQ + row];
+      // epilogue: O / l -> ctx rows (0 for masked query rows); each half stores DK/2 columns
       mbar_wait(o_full, 0);
       tcgen05_fence_after();
-      const int t = q0 + wq * 32 + lane;
+      const int t = q0 + row;
       const bool store = t < p.L;
       const float inv = (p.lens && t >= len) ? 0.f : 1.0f / l_row;
-      float* dst = p.ctx + ((long)b * p.L + t) * p.C + h * DK;
+      float* dst = p.ctx + ((long)b * p.L + t) * p.C + h * DK + half * (DK / 2);
 #pragma unroll 1
-      for (int c0 = 0; c0 < DK; c0 += 32) {
+      for (int c0 = 0; c0 < DK / 2; c0 += 32) {
         __syncwarp();
-        tmem_ld32(lane_addr + (uint32_t)(A::O_COL + c0), v);
+        tmem_ld32(lane_addr + (uint32_t)(A::O_COL + half * (DK / 2) + c0), v);
         if (store) {
 #pragma unroll
           for (int q = 0; q < 8; ++q)
@@ -227,7 +232,7 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_
   } else if (warp >= 2) {
     // no valid key at all (len == 0): the reference's masked_fill turns the NaN rows into 0
     const int t = q0 + (warp & 3) * 32 + lane;
-    if (t < p.L) {
+    if (t < p.L && warp < 6) {
       float* dst = p.ctx + ((long)b * p.L + t) * p.C + h * DK;
       for (int c = 0; c < DK; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
