@@ -25,10 +25,11 @@
 // CTAs share weight tiles in L2).  Three pipelines:
 //   smem ring   : warp 0 (TMA producer, one lane)  <-> warp 1 (MMA issuer, one lane), full/empty mbarriers
 //   TMEM        : two accumulator buffers; warp 1 fills buffer i&1 while warps 2-5 drain the other
-//   output      : warps 2-5 (thread == output row == TMEM lane): tcgen05.ld 32 columns -> bias / ReLU /
-//                 tanh / residual -> 128-byte-swizzled smem staging -> TMA tensor store (rows past the
-//                 utterance end are clipped by the TMA unit), double buffered with bulk-group waits
-//   PRECISE only: warps 6-9 split each landed A tile in place into hi / lo (element-wise, so the
+//   output      : two epilogue groups (warps 2-5 and 6-9; thread == output row == TMEM lane) take alternate
+//                 32-column chunks: tcgen05.ld -> bias / ReLU / tanh / residual -> 128-byte-swizzled smem
+//                 staging (one box per group) -> TMA tensor store (rows past the utterance end are
+//                 clipped by the TMA unit); the groups overlap each other's TMEM / store latency
+//   PRECISE only: warps 10-13 split each landed A tile in place into hi / lo (element-wise, so the
 //                 swizzled layout is untouched) and hand the slot to the MMA warp through a third
 //                 mbarrier; the weight hi / lo arrays are split once at load time.
 // Convolutions tile each utterance separately (ceil(L/128) row tiles) so the shifted boxes never
@@ -66,7 +67,7 @@ struct Cfg {
   static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
   static constexpr int ACC_STRIDE = pow2_at_least(BN);     // TMEM columns per accumulator buffer
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int THREADS = PRECISE ? 320 : 192;
+  static constexpr int THREADS = PRECISE ? 448 : 320;
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
   static constexpr uint32_t IDESC = idesc_tf32(BM, BN);
   static constexpr int A_LO = A_BYTES;                                  // offsets inside a stage
@@ -106,7 +107,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], 4); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);   // whole warp: both accumulator buffers
@@ -170,14 +171,16 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         tcgen05_commit(&acc_full[acc]);        // accumulator complete
       }
     }
-  } else if (warp < 6) {
-    // ---- epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31; thread == output row ----
-    const int wq = warp & 3;
+  } else if (warp < 10) {
+    // ---- epilogue: group 0 = warps 2..5, group 1 = warps 6..9; warp w owns TMEM lanes 32*(w%4) .. +31;
+    //      thread == output row; the groups take alternate 32-column chunks ----
+    const int wq = warp & 3, grp = (warp - 2) >> 2;
     const int row = wq * 32 + lane;
-    const bool elected = threadIdx.x == 64;      // warp 2 lane 0 issues the tensor stores
+    const bool elected = (threadIdx.x - 64) % 128 == 0;   // first lane of each group issues its tensor stores
+    uint8_t* stage = staging + (size_t)grp * (BM * 128);
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
     float v[32];
-    int it = 0, chunk_no = 0;
+    int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       int n0, b, t0;
       tile_coords(tile, n0, b, t0);
@@ -190,7 +193,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       const uint32_t taddr = tmem_base + lane_off + (uint32_t)(acc * C::ACC_STRIDE);
       const bool to_vt = p.vt_out != nullptr && n0 >= p.vt_col0;   // tile-uniform (tile widths divide the V third)
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = grp * 32; c0 < BN; c0 += 64) {
         if (to_vt) {
           __syncwarp();
           tmem_ld32(taddr + c0, v);
@@ -205,12 +208,10 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           }
           continue;
         }
-        const int buf = chunk_no & 1;
-        ++chunk_no;
-        if (elected) tma_store_wait_read<1>();   // the store issued from this staging buffer two chunks ago has read it
-        named_bar_sync(1, 128);
+        if (elected) tma_store_wait_read<0>();   // this group's previous store has read the staging box
+        named_bar_sync(1 + grp, 128);
         tmem_ld32(taddr + c0, v);
-        float4* srow = reinterpret_cast<float4*>(staging + (size_t)buf * (BM * 128) + (size_t)row * 128);
+        float4* srow = reinterpret_cast<float4*>(stage + (size_t)row * 128);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int n = n0 + c0 + q * 4;
@@ -230,21 +231,21 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           srow[q ^ (row & 7)] = o;               // 128-byte swizzle: 16-byte chunk index XOR (row mod 8)
         }
         fence_proxy_async();                     // generic-proxy smem writes -> visible to the TMA unit
-        named_bar_sync(1, 128);
+        named_bar_sync(1 + grp, 128);
         if (elected) {
-          tma_store_3d(&tmap_out, staging + (size_t)buf * (BM * 128), n0 + c0, t0, b);
+          tma_store_3d(&tmap_out, stage, n0 + c0, t0, b);
           tma_store_commit();
         }
       }
-      // all TMEM reads of this tile are complete (every thread passed its last tcgen05.wait::ld)
+      // this group's TMEM reads of the tile are complete (every thread passed its last tcgen05.wait::ld)
       tcgen05_fence_before();
-      named_bar_sync(1, 128);
+      named_bar_sync(1 + grp, 128);
       if (elected) mbar_arrive(&acc_empty[acc]);
     }
     if (elected) tma_store_wait_all<0>();        // stores must complete before the CTA exits
   } else if (PRECISE) {
-    // ---- operand split (warps 6..9): A tile -> hi (in place) and lo (second buffer), same swizzled positions ----
-    const int tid = threadIdx.x - 192;      // 0..127
+    // ---- operand split (warps 10..13): A tile -> hi (in place) and lo (second buffer), same swizzled positions ----
+    const int tid = threadIdx.x - 320;      // 0..127
     int n = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       for (int s = 0; s < steps; ++s, ++n) {
