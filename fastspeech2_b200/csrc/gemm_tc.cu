@@ -46,8 +46,7 @@ constexpr int BK = 32;                 // fp32 elements per pipeline step = one 
 constexpr int UMMA_K = 8;              // tf32
 constexpr int A_BYTES = BM * BK * 4;   // 16 KB
 constexpr int STAGING_BYTES = 2 * BM * 32 * 4;   // two [128 x 32] fp32 output boxes
-constexpr int BIAS_BYTES = 2 * 256 * 4;          // per-epilogue-group copy of the tile's bias slice
-constexpr int RING_BUDGET = 227 * 1024 - STAGING_BYTES - BIAS_BYTES - 1024 /*align slack*/ - 512 /*barriers*/;
+constexpr int RING_BUDGET = 227 * 1024 - STAGING_BYTES - 1024 /*align slack*/ - 512 /*barriers*/;
 
 struct TcParams {
   int L, tiles_per_utt;          // tiles_per_utt == 0: flat tiling, L = B*L rows
@@ -69,7 +68,7 @@ struct Cfg {
   static constexpr int ACC_STRIDE = pow2_at_least(BN);     // TMEM columns per accumulator buffer
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   static constexpr int THREADS = PRECISE ? 448 : 320;
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + BIAS_BYTES + 1024 + 512;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
   static constexpr uint32_t IDESC = idesc_tf32(BM, BN);
   static constexpr int A_LO = A_BYTES;                                  // offsets inside a stage
   static constexpr int B_HI = PRECISE ? 2 * A_BYTES : A_BYTES;
@@ -94,8 +93,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* staging = tiles + (size_t)C::STAGES * C::STAGE_BYTES;
-  float* bias_smem = reinterpret_cast<float*>(staging + STAGING_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES + BIAS_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* split_bar = empty_bar + C::STAGES;
   uint64_t* acc_full = split_bar + C::STAGES;     // [2] MMA -> epilogue
@@ -180,7 +178,6 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     const int row = wq * 32 + lane;
     const bool elected = (threadIdx.x - 64) % 128 == 0;   // first lane of each group issues its tensor stores
     uint8_t* stage = staging + (size_t)grp * (BM * 128);
-    float* bias_s = bias_smem + grp * 256;
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
     float v[32];
     int it = 0;
@@ -195,11 +192,16 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       const long m = (long)b * p.L + t;
       const uint32_t taddr = tmem_base + lane_off + (uint32_t)(acc * C::ACC_STRIDE);
       const bool to_vt = p.vt_out != nullptr && n0 >= p.vt_col0;   // tile-uniform (tile widths divide the V third)
-      // bias slice of this tile -> shared memory (global loads in the per-element path stall the whole epilogue)
-      for (int i = row; i < BN; i += 128) bias_s[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
-      named_bar_sync(1 + grp, 128);
 #pragma unroll 1
       for (int c0 = grp * 32; c0 < BN; c0 += 64) {
+        // bias (same 32 values for every row) and residual are fetched first so the loads are in flight across the
+        // barrier and the TMEM load; issued next to their use they stall the whole epilogue (ncu: long scoreboard)
+        float4 bv[8], rv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          bv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias && c0 + q * 4 < BN) bv[q] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + q * 4));
+        }
         if (to_vt) {
           __syncwarp();
           tmem_ld32(taddr + c0, v);
@@ -210,11 +212,13 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             float* dst = p.vt_out + ((ub * p.vt_heads + hh) * p.vt_dk + d0) * (long)p.vt_lpad + ut;
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (c0 + i < BN) dst[(long)i * p.vt_lpad] = v[i] + bias_s[c0 + i];
+              if (c0 + i < BN) {
+                const float4 bq = bv[i >> 2];
+                dst[(long)i * p.vt_lpad] = v[i] + ((i & 3) == 0 ? bq.x : (i & 3) == 1 ? bq.y : (i & 3) == 2 ? bq.z : bq.w);
+              }
           }
           continue;
         }
-        float4 rv[8];                            // residual prefetch: in flight across the barrier and the TMEM load
         if (p.resid && row_ok) {
 #pragma unroll
           for (int q = 0; q < 8; ++q)
@@ -228,8 +232,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         for (int q = 0; q < 8; ++q) {
           float4 o = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
           if (c0 + q * 4 < BN) {
-            const float4 bv = *reinterpret_cast<const float4*>(bias_s + c0 + q * 4);
-            o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+            o.x += bv[q].x; o.y += bv[q].y; o.z += bv[q].z; o.w += bv[q].w;
             if (p.act == ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
             else if (p.act == ACT_TANH) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
             if (p.resid && row_ok) { o.x += rv[q].x; o.y += rv[q].y; o.z += rv[q].z; o.w += rv[q].w; }
