@@ -116,7 +116,7 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_
         for (int j = 0; j < J; ++j) { if (j + 1 < J) push_k(j + 1); push_v(j); }
       }
     } else if (warp == 1) {
-      if (lane == 0) {  // ---- MMA issuer ----
+      {  // ---- MMA issuer: all 32 lanes run the loop, one lane is elected inside each tcgen05 asm ----
         mbar_wait(q_bar, 0);
         tcgen05_fence_after();
         const uint32_t q_addr = smem_u32(q_smem);
