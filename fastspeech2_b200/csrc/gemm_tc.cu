@@ -8,7 +8,7 @@
 //   * the decoder side in plain tf32 (one MMA per product): decoder input Linear, q|k|v and output
 //     projections, conv-FFN (k=9 and k=1), mel Linear, Postnet convolutions;
 //   * the encoder and the three predictors in *3xTF32* (PRECISE = true): every operand is split
-//     into hi = rn_tf32(x) and lo = rn_tf32(x - hi) and the product is accumulated as
+//     into hi = top 19 bits of x and lo = x - hi and the product is accumulated as
 //     hi*hi + lo*hi + hi*lo in the fp32 TMEM accumulator (the dropped lo*lo term is ~2^-22
 //     relative), which gives near-fp32 results on the tensor pipe.  Their outputs feed round() /
 //     bucketize(), where plain tf32 noise (~1e-3) would flip integers.
@@ -79,11 +79,9 @@ struct Cfg {
   static_assert(STAGES >= 2 && TMEM_COLS <= 512, "resources");
 };
 
-__device__ __forceinline__ float rn_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
+// tf32 split: hi keeps the top 19 bits (exactly what kind::tf32 reads), lo = x - hi is exact in fp32 and
+// is itself read as tf32 by the tensor core (relative error 2^-10 of lo = 2^-21 of x)
+__device__ __forceinline__ float hi_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
 template <int BN, bool PRECISE>
 __global__ void __launch_bounds__(Cfg<BN, PRECISE>::THREADS, 1)
@@ -267,8 +265,8 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           const int idx = tid + i * 128;
           const float4 x = a[idx];
           float4 h, l;
-          h.x = rn_tf32(x.x); h.y = rn_tf32(x.y); h.z = rn_tf32(x.z); h.w = rn_tf32(x.w);
-          l.x = rn_tf32(x.x - h.x); l.y = rn_tf32(x.y - h.y); l.z = rn_tf32(x.z - h.z); l.w = rn_tf32(x.w - h.w);
+          h.x = hi_tf32(x.x); h.y = hi_tf32(x.y); h.z = hi_tf32(x.z); h.w = hi_tf32(x.w);
+          l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
           a[idx] = h; lo[idx] = l;
         }
         fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core
@@ -287,8 +285,8 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 
 __global__ void split_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, long n) {
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    const float x = src[i], h = rn_tf32(x);
-    hi[i] = h; lo[i] = rn_tf32(x - h);
+    const float x = src[i], h = hi_tf32(x);
+    hi[i] = h; lo[i] = x - h;
   }
 }
 
