@@ -285,3 +285,63 @@ def test_layernorm_vs_torch(C):
     _lib.check(lib.fs2_op_layernorm(_lib.ptr(xc), _lib.ptr(rc), _lib.ptr(wc), _lib.ptr(bc), 1e-5, 1000, C, _lib.ptr(out),
                                     _lib.stream_ptr(out.device)), "fs2_op_layernorm")
     close(out, want, dict(max=1e-5, mean=1e-6), "layernorm")
+
+
+# ---- edge cases -------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_edge_shapes_vs_oracle(models, weights, prec):
+    """Smallest and most lopsided shapes: single phoneme, single frame rows, one long + one tiny utterance,
+    lengths that are not multiples of any tile size."""
+    cases = [
+        dict(B=1, T=1, L=3, ilens=[1], olens=[3]),
+        dict(B=2, T=3, L=5, ilens=[3, 1], olens=[5, 1]),
+        dict(B=3, T=37, L=301, ilens=[37, 2, 19], olens=[301, 2, 130]),
+        dict(B=1, T=129, L=1025, ilens=[129], olens=[1025]),
+    ]
+    for i, c in enumerate(cases):
+        bt = make_batch(c["B"], c["T"], c["L"], seed=40 + i, ilens=c["ilens"], olens=c["olens"])
+        with torch.no_grad():
+            want = O.forward_path(weights, bt["xs"], bt["ilens"], bt["olens"], bt["ds"].clone(), bt["es"], bt["ps"], False)
+            got = models[prec]._forward(*[bt[k].cuda() for k in ("xs", "ilens", "olens", "ds", "es", "ps")], is_inference=False)
+        valid = (torch.arange(c["L"])[None] < bt["olens"][:, None])
+        for name, g, w in (("before", got[0], want[0]), ("after", got[1], want[1])):
+            close(g.cpu()[valid], w[valid], TOL[prec], f"case {i} {name}")
+        close(got[2], want[2], TOL["fp32"], f"case {i} d_outs")
+
+
+def test_inference_batch_matches_oracle_durations(models, weights):
+    """is_inference=True on a ragged B=8 batch: integer durations must be identical to the CPU oracle in both
+    precision modes (encoder + duration predictor run exact-fp32 / 3xTF32), mels within tolerance given equal L."""
+    g = torch.Generator().manual_seed(77)
+    ilens = [64, 50, 47, 33, 21, 12, 5, 1]
+    xs = torch.zeros(8, 64, dtype=torch.int64)
+    for b, n in enumerate(ilens):
+        xs[b, :n] = torch.randint(1, 68, (n,), generator=g)
+    il = torch.tensor(ilens)
+    with torch.no_grad():
+        want = O.forward_path(weights, xs, il, is_inference=True)
+        for prec in PRECISIONS:
+            got = models[prec]._forward(xs.cuda(), il.cuda(), is_inference=True)
+            assert torch.equal(got[2].cpu(), want[2]), prec
+            assert torch.equal(got[3].argmax(-1).cpu(), want[3].argmax(-1)) and torch.equal(got[4].argmax(-1).cpu(), want[4].argmax(-1)), prec
+            close(got[1], want[1], TOL[prec], f"after {prec}")
+
+
+def test_positional_table_limit_is_loud(models):
+    m = models["fp32"]
+    xs = torch.ones(1, 10, dtype=torch.int64).cuda(); il = torch.tensor([10]).cuda()
+    ds = torch.full((1, 10), 600, dtype=torch.int64).cuda()       # 6000 frames > 5000-row positional table
+    with pytest.raises(_lib.Fs2Error, match="positional table"):
+        m._forward(xs, il, torch.tensor([6000]).cuda(), ds, torch.zeros(1, 6000).cuda(), torch.zeros(1, 6000).cuda())
+
+
+def test_sharded_synthesis_single_rank(models, weights):
+    """synthesize_sharded with no process group == plain batched inference."""
+    from fastspeech2_b200.sharded import synthesize_sharded
+    g = torch.Generator().manual_seed(78)
+    xs = torch.randint(1, 68, (4, 30), generator=g); il = torch.tensor([30, 30, 30, 30])
+    mels, olens = synthesize_sharded(models["fp32"], xs.cuda(), il.cuda())
+    with torch.no_grad():
+        want = O.forward_path(weights, xs, il, is_inference=True)
+    assert torch.equal(olens.cpu(), want[2].sum(1))
+    close(mels, want[1], TOL["fp32"], "sharded mels")
