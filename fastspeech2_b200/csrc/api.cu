@@ -105,6 +105,7 @@ int dense(const TapGemm& g, int math_mode, cudaStream_t st, int cls) {
   const double M = (double)g.B * g.L;
   ProfScope prof_scope(cls, 2.0 * M * g.N * g.K * g.taps,
                4.0 * (M * g.K + (double)g.taps * g.N * g.K + M * g.N * (g.resid ? 2 : 1)), st);
+  if (math_mode == FS2_MATH_TF32 && g.ln_gamma) return gemm_ln_tf32(g, st);
   return math_mode == MATH_3XTF32 ? tap_gemm_3xtf32(g, st) : math_mode == FS2_MATH_TF32 ? tap_gemm_tf32(g, st) : tap_gemm_fp32(g, st);
 }
 int norm_rows(const RowNorm& r, cudaStream_t st) {
@@ -135,12 +136,13 @@ RowNorm make_norm(const Norm& n, const float* x, int ldx, int64_t rows, int C, f
   return r;
 }
 
-// x <- FFT blocks(x); scratch buffers sized for [rows, .]
-int run_blocks(const std::vector<Block>& blocks, float* x, float* y, float* qkv, float* vt, float* ctx, float* hid,
-               const int64_t* lens, int B, int L, int C, int heads, int math_mode, bool is_dec, cudaStream_t st) {
+// FFT blocks on xin; the result lands in *result (one of the two ping-pong buffers xin / y)
+int run_blocks(const std::vector<Block>& blocks, float* xin, float* yin, float* qkv, float* vt, float* ctx, float* hid,
+               const int64_t* lens, int B, int L, int C, int heads, int math_mode, bool is_dec, cudaStream_t st, float** result) {
   const int64_t rows = (int64_t)B * L;
   const int c_qkv = is_dec ? P_DEC_QKV : P_ENC_GEMM, c_att = is_dec ? P_DEC_ATTN : P_ENC_ATTN;
   const int c_out = is_dec ? P_DEC_OUT : P_ENC_GEMM, c_w1 = is_dec ? P_DEC_W1 : P_ENC_GEMM, c_w2 = is_dec ? P_DEC_W2 : P_ENC_GEMM;
+  float *x = xin, *y = yin;
   for (const Block& k : blocks) {
     int rc;
     // q | k | v projection (attention.py:48-50), one GEMM with N = 3C
@@ -150,14 +152,31 @@ int run_blocks(const std::vector<Block>& blocks, float* x, float* y, float* qkv,
     }
     if ((rc = dense(gq, math_mode, st, c_qkv))) return rc;
     if ((rc = attention(math_mode, qkv, vt, round4(L), lens, B, L, C, heads, ctx, st, c_att))) return rc;
-    // y = x + linear_out(ctx) (attention.py:74, encoder.py:60); x = LN(y) (:61-62)
-    if ((rc = dense(make_gemm(k.out, ctx, C, B, L, ACT_NONE, x, C, y, C), math_mode, st, c_out))) return rc;
-    if ((rc = norm_rows(make_norm(k.ln1, y, C, rows, C, x, C), st))) return rc;
-    // conv-FFN: hid = relu(conv_k(x)); y = x + conv_1(hid); x = LN(y)  (modules.py:247-248, encoder.py:64-69)
+    // x = LN(x + linear_out(ctx)) (attention.py:74, encoder.py:60-62)
+    TapGemm go = make_gemm(k.out, ctx, C, B, L, ACT_NONE, x, C, y, C);
+    go.ln_gamma = k.ln1.g; go.ln_beta = k.ln1.b; go.ln_eps = k.ln1.eps;
+    if (math_mode == FS2_MATH_TF32 && gemm_ln_tf32_supported(go)) {   // fused: result in y, swap roles
+      if ((rc = dense(go, math_mode, st, c_out))) return rc;
+      float* t = x; x = y; y = t;
+    } else {
+      go.ln_gamma = nullptr;
+      if ((rc = dense(go, math_mode, st, c_out))) return rc;
+      if ((rc = norm_rows(make_norm(k.ln1, y, C, rows, C, x, C), st))) return rc;
+    }
+    // conv-FFN: hid = relu(conv_k(x)); x = LN(x + conv_1(hid))  (modules.py:247-248, encoder.py:64-69)
     if ((rc = dense(make_gemm(k.w1, x, C, B, L, ACT_RELU, nullptr, 0, hid, k.w1.N), math_mode, st, c_w1))) return rc;
-    if ((rc = dense(make_gemm(k.w2, hid, k.w1.N, B, L, ACT_NONE, x, C, y, C), math_mode, st, c_w2))) return rc;
-    if ((rc = norm_rows(make_norm(k.ln2, y, C, rows, C, x, C), st))) return rc;
+    TapGemm g2 = make_gemm(k.w2, hid, k.w1.N, B, L, ACT_NONE, x, C, y, C);
+    g2.ln_gamma = k.ln2.g; g2.ln_beta = k.ln2.b; g2.ln_eps = k.ln2.eps;
+    if (math_mode == FS2_MATH_TF32 && gemm_ln_tf32_supported(g2)) {
+      if ((rc = dense(g2, math_mode, st, c_w2))) return rc;
+      float* t = x; x = y; y = t;
+    } else {
+      g2.ln_gamma = nullptr;
+      if ((rc = dense(g2, math_mode, st, c_w2))) return rc;
+      if ((rc = norm_rows(make_norm(k.ln2, y, C, rows, C, x, C), st))) return rc;
+    }
   }
+  *result = x;
   return FS2_OK;
 }
 
@@ -465,10 +484,11 @@ int fs2_encode(fs2_handle* h, const int64_t* xs, const int64_t* ilens, int B, in
   const int precise = c.math_mode == FS2_MATH_TF32 ? MATH_3XTF32 : FS2_MATH_FP32;
   { ProfScope prof_scope(P_EMBED, 0, 8.0 * B * Tmax * c.adim, st);
     if ((rc = embed_posenc(xs, h->emb, c.idim, h->enc_pe, h->enc_alpha, B, Tmax, c.adim, p.x, st))) return rc; }
-  if ((rc = run_blocks(h->enc, p.x, p.y, p.qkv, nullptr, p.ctx, p.hid, ilens, B, Tmax, c.adim, c.aheads, precise, false, st))) return rc;
-  FS2_CUDA_CHECK(cudaMemcpyAsync(hs, p.x, (size_t)B * Tmax * c.adim * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  float* enc_out = nullptr;
+  if ((rc = run_blocks(h->enc, p.x, p.y, p.qkv, nullptr, p.ctx, p.hid, ilens, B, Tmax, c.adim, c.aheads, precise, false, st, &enc_out))) return rc;
+  FS2_CUDA_CHECK(cudaMemcpyAsync(hs, enc_out, (size_t)B * Tmax * c.adim * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (d_log || d_int)
-    if ((rc = run_predictor(h->dur, p.x, c.adim, B, Tmax, p.t1, p.t2, ilens, d_log, d_int, precise, st))) return rc;
+    if ((rc = run_predictor(h->dur, enc_out, c.adim, B, Tmax, p.t1, p.t2, ilens, d_log, d_int, precise, st))) return rc;
   return FS2_OK;
 }
 
@@ -515,9 +535,10 @@ int fs2_decode(fs2_handle* h, const float* hm, const int64_t* olens, const float
     r.relu_after = 1; r.pe = h->dec_pe; r.alpha = h->dec_alpha; r.L = L;
     if ((rc = norm_rows(r, st))) return rc;
   }
-  if ((rc = run_blocks(h->dec, p.x, p.y, p.qkv, p.vt, p.ctx, p.hid, olens, B, L, c.ddim, c.aheads, mode, true, st))) return rc;
+  float* dec_out = nullptr;
+  if ((rc = run_blocks(h->dec, p.x, p.y, p.qkv, p.vt, p.ctx, p.hid, olens, B, L, c.ddim, c.aheads, mode, true, st, &dec_out))) return rc;
   // mel linear (fastspeech.py:228-230)
-  if ((rc = dense(make_gemm(h->feat_out, p.x, c.ddim, B, L, ACT_NONE, nullptr, 0, before, c.odim), mode, st, P_FEAT_OUT))) return rc;
+  if ((rc = dense(make_gemm(h->feat_out, dec_out, c.ddim, B, L, ACT_NONE, nullptr, 0, before, c.odim), mode, st, P_FEAT_OUT))) return rc;
   // Postnet + residual (fastspeech.py:236-238, modules.py:350-359)
   const float* cur = before; int curC = c.odim;
   float* pp[2] = {p.q1, p.q2};
@@ -565,6 +586,15 @@ int fs2_op_tap_gemm(int math_mode, const float* x, int B, int L, int K, const fl
   if (!rc) rc = dense(make_gemm(d, x, K, B, L, act, resid, N, out, N), math_mode, st, P_DEC_W1);
   cudaFreeAsync(tmp, st);
   return rc;
+}
+int fs2_op_gemm_layernorm(const float* x, int64_t rows, int K, const float* w, const float* bias, const float* resid,
+                          const float* gamma, const float* beta, float eps, float* out, void* stream) {
+  FS2_REQUIRE(x && w && gamma && beta && out, "fs2_op_gemm_layernorm: null argument");
+  FS2_REQUIRE(rows < (1LL << 31), "fs2_op_gemm_layernorm: too many rows");
+  Dense d; d.w = w; d.bias = bias; d.N = 384; d.K = K; d.taps = 1;
+  TapGemm g = make_gemm(d, x, K, 1, (int)rows, ACT_NONE, resid, 384, out, 384);
+  g.ln_gamma = gamma; g.ln_beta = beta; g.ln_eps = eps;
+  return dense(g, FS2_MATH_TF32, (cudaStream_t)stream, P_DEC_OUT);
 }
 int fs2_op_attention(int math_mode, const float* qkv, const int64_t* lens, int B, int L, int C, int heads, float* ctx,
                      void* stream) {

@@ -52,11 +52,15 @@ struct TapGemm {
   float* out; int ldo;
   // 3xTF32 only: w split into hi = rn_tf32(w), lo = rn_tf32(w - hi), same [taps][N][K] layout
   const float* w_hi = nullptr; const float* w_lo = nullptr;
+  // tf32 family, N == 384, taps == 1: fuse LayerNorm over the full output row into the epilogue (gemm_ln_tc.cu)
+  const float* ln_gamma = nullptr; const float* ln_beta = nullptr; float ln_eps = 0.f;
   // tf32 family only: store output columns >= vt_col0 transposed into vt_out (see gemm_tc.cu)
   float* vt_out = nullptr; int vt_col0 = 0, vt_dk = 0, vt_heads = 0, vt_lpad = 0;
 };
 int tap_gemm_fp32(const TapGemm& g, cudaStream_t st);
 int tap_gemm_tf32(const TapGemm& g, cudaStream_t st);   // tcgen05 + TMA (gemm_tc.cu)
+bool gemm_ln_tf32_supported(const TapGemm& g);         // row-complete GEMM + residual + LayerNorm (gemm_ln_tc.cu)
+int gemm_ln_tf32(const TapGemm& g, cudaStream_t st);
 int tap_gemm_3xtf32(const TapGemm& g, cudaStream_t st); // same kernel, error-compensated split operands
 int split_tf32(const float* src, float* hi, float* lo, long n, cudaStream_t st);
 constexpr int MATH_3XTF32 = 2;                          // internal: FS2_MATH_TF32's choice for encoder + predictors

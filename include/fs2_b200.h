@@ -168,6 +168,10 @@ int fs2_one_hot(const int64_t* ids, int64_t n, int n_bins, float* out, void* str
  * act: 0 none, 1 relu, 2 tanh */
 int fs2_op_tap_gemm(int math_mode, const float* x, int B, int L, int K, const float* w, const float* bias, int N, int taps,
                     int act, const float* resid, float* out, void* stream);
+/* out = LayerNorm_384(x . w^T + bias + resid) * gamma + beta in one tcgen05 kernel (x [rows,K], w [384,K]);
+ * the fused form of core/encoder.py:60-62 / :67-69 used for the decoder blocks in FS2_MATH_TF32 */
+int fs2_op_gemm_layernorm(const float* x, int64_t rows, int K, const float* w, const float* bias, const float* resid,
+                          const float* gamma, const float* beta, float eps, float* out, void* stream);
 /* qkv [B,L,3C] (q | k | v, heads contiguous inside each) -> ctx [B,L,C]; lens NULL => no mask */
 int fs2_op_attention(int math_mode, const float* qkv, const int64_t* lens, int B, int L, int C, int heads, float* ctx,
                      void* stream);

@@ -273,6 +273,22 @@ def test_attention_vs_torch(prec, C, L, masked):
     close(ctx, want, tol, f"attention C={C} L={L} masked={masked}")
 
 
+@pytest.mark.parametrize("rows,K,with_resid", [(1000, 384, True), (51, 1024, True), (4097, 256, False)])
+def test_fused_gemm_layernorm_vs_torch(rows, K, with_resid):
+    """tcgen05 GEMM with residual + LayerNorm fused into the epilogue (decoder out-projection / conv-FFN w_2)."""
+    g = torch.Generator().manual_seed(rows + K)
+    x = torch.randn(rows, K, generator=g); w = torch.randn(384, K, generator=g) / K ** 0.5; bias = torch.randn(384, generator=g)
+    resid = torch.randn(rows, 384, generator=g); gamma = 1 + 0.1 * torch.randn(384, generator=g); beta = torch.randn(384, generator=g)
+    y = x.double() @ w.double().T + bias.double() + (resid.double() if with_resid else 0)
+    want = torch.nn.functional.layer_norm(y, (384,), gamma.double(), beta.double(), 1e-5).float()
+    out = torch.empty(rows, 384, device="cuda")
+    lib = _lib.load()
+    xc, wc, bc, rc, gc, btc = x.cuda(), w.cuda(), bias.cuda(), resid.cuda(), gamma.cuda(), beta.cuda()
+    _lib.check(lib.fs2_op_gemm_layernorm(_lib.ptr(xc), rows, K, _lib.ptr(wc), _lib.ptr(bc), _lib.ptr(rc) if with_resid else None,
+                                         _lib.ptr(gc), _lib.ptr(btc), 1e-5, _lib.ptr(out), _lib.stream_ptr(out.device)), "fs2_op_gemm_layernorm")
+    close(out, want, dict(max=1e-2, mean=1e-3), f"gemm+ln rows={rows} K={K}")
+
+
 @pytest.mark.parametrize("C", [256, 384])
 def test_layernorm_vs_torch(C):
     g = torch.Generator().manual_seed(C)
