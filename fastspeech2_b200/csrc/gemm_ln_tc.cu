@@ -128,6 +128,12 @@ gemm_ln_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int r0 = tile * BM;
       const long m = (long)r0 + row;
       const bool row_ok = m < p.M;
+      // while the tensor core runs this tile's main loop, pull this thread's share of the residual row into L2
+      // (6 x 128-byte lines): the pass-A loads then see L2 latency instead of an exposed HBM round trip per chunk
+      if (p.resid && row_ok) {
+#pragma unroll
+        for (int i = 0; i < L::CHUNKS_PER_GROUP; ++i) prefetch_l2(p.resid + m * p.ldr + grp * 32 + i * 64);
+      }
       mbar_wait(acc_full, it & 1);
       tcgen05_fence_after();
       // pass A: y = acc + bias + resid, kept in TMEM; partial row sum

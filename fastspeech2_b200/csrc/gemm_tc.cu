@@ -183,11 +183,14 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       int n0, b, t0;
       tile_coords(tile, n0, b, t0);
       const int acc = it & 1;
-      mbar_wait(&acc_full[acc], (it >> 1) & 1);
-      tcgen05_fence_after();
       const int t = t0 + row;
       const bool row_ok = t < p.L;               // flat mode: L == total rows
       const long m = (long)b * p.L + t;
+      if (p.resid && row_ok) {                   // residual rows -> L2 while the main loop of this tile runs
+        for (int c0 = grp * 32; c0 < BN; c0 += 64) prefetch_l2(p.resid + m * p.ldr + n0 + c0);
+      }
+      mbar_wait(&acc_full[acc], (it >> 1) & 1);
+      tcgen05_fence_after();
       const uint32_t taddr = tmem_base + lane_off + (uint32_t)(acc * C::ACC_STRIDE);
       const bool to_vt = p.vt_out != nullptr && n0 >= p.vt_col0;   // tile-uniform (tile widths divide the V third)
 #pragma unroll 1
