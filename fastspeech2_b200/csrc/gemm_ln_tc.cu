@@ -14,7 +14,7 @@
 // Epilogue (8 warps = two groups x 4 lane quarters; two threads per row, alternate 32-column chunks):
 //   pass A  y = acc + bias + resid  -> written back to TMEM, partial row sums
 //   pass B  partial sums of (y - mean)^2        (two-pass variance like nn.LayerNorm)
-//   pass C  (y - mean) * rstd * gamma + beta -> swizzled smem staging -> TMA tensor store
+//   pass C  (y - mean) * rstd * gamma + beta -> swizzled smem staging -> cooperative full-line global stores
 // Row statistics are exchanged between the two threads of a row through shared memory.
 #include "tc_common.cuh"
 
@@ -45,12 +45,12 @@ struct LnParams {
   int M, K;
   const float* bias; const float* resid; int ldr;
   const float* gamma; const float* beta; float eps;
+  float* out; int ldo;
 };
 
 template <int C>
 __global__ void __launch_bounds__(LN_THREADS, 1)
-gemm_ln_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const __grid_constant__ CUtensorMap tmap_out, LnParams p) {
+gemm_ln_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, LnParams p) {
   using L = LCfg<C>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -118,7 +118,8 @@ gemm_ln_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // ---- epilogue: group g = (warp-2)/4 takes the 32-column chunks g, g+2, g+4, ...; thread == row ----
     const int wq = warp & 3, grp = (warp - 2) >> 2;
     const int row = wq * 32 + lane;
-    const bool elected = (threadIdx.x - 64) % 128 == 0;
+    const int gtid = (threadIdx.x - 64) & 127;
+    const bool elected = gtid == 0;
     const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
     uint8_t* stage = staging + (size_t)grp * (BM * 128);
     float* xchg = reinterpret_cast<float*>(staging);          // [2][128] floats inside group 0's staging box
@@ -159,8 +160,7 @@ gemm_ln_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tmem_st32(taddr + c0, v);
       }
       tmem_st_wait();
-      if (elected && grp == 0) tma_store_wait_read<0>();      // xchg lives in group 0's staging box
-      named_bar_sync(3, 256);
+      named_bar_sync(3, 256);                                  // xchg lives in group 0's staging box: its last read-out is done
       xchg[grp * BM + row] = sum;
       named_bar_sync(3, 256);
       const float mean = (sum + xchg[(grp ^ 1) * BM + row]) * (1.0f / C);
@@ -188,7 +188,6 @@ gemm_ln_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           gv[q] = __ldg(reinterpret_cast<const float4*>(p.gamma + c0 + q * 4));
           bt[q] = __ldg(reinterpret_cast<const float4*>(p.beta + c0 + q * 4));
         }
-        if (elected) tma_store_wait_read<0>();
         named_bar_sync(1 + grp, 128);
         tmem_ld32(taddr + c0, v);
         float4* srow = reinterpret_cast<float4*>(stage + (size_t)row * 128);
@@ -199,15 +198,13 @@ gemm_ln_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           o.z = (v[q * 4 + 2] - mean) * rstd * gv[q].z + bt[q].z; o.w = (v[q * 4 + 3] - mean) * rstd * gv[q].w + bt[q].w;
           srow[q ^ (row & 7)] = o;
         }
-        fence_proxy_async();
         named_bar_sync(1 + grp, 128);
-        if (elected) { tma_store_3d(&tmap_out, stage, c0, r0, 0); tma_store_commit(); }
+        store_box_coalesced(stage, p.out + (long)r0 * p.ldo + c0, p.ldo, gtid, p.M - r0, 32);
       }
       tcgen05_fence_before();
       named_bar_sync(1 + grp, 128);
       if (elected) mbar_arrive(acc_empty);
     }
-    if (elected) tma_store_wait_all<0>();
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -243,18 +240,17 @@ int gemm_ln_tf32(const TapGemm& g, cudaStream_t st) {
     FS2_CUDA_CHECK(cudaFuncSetAttribute(gemm_ln_tf32_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
     configured = true;
   }
-  CUtensorMap ma, mb, mo;
+  CUtensorMap ma, mb;
   int rc;
-  const uint64_t arow = (uint64_t)g.ldx * 4, orow = (uint64_t)g.ldo * 4;
+  const uint64_t arow = (uint64_t)g.ldx * 4;
   if ((rc = make_map(&ma, g.x, g.K, M, 1, arow, arow * M, BM))) return rc;
   if ((rc = make_map(&mb, g.w, g.K, C, 1, (uint64_t)g.K * 4, (uint64_t)g.K * 4 * C, L::HALF))) return rc;
-  if ((rc = make_map(&mo, g.out, C, M, 1, orow, orow * M, BM))) return rc;
   LnParams p;
   p.M = (int)M; p.K = g.K; p.bias = g.bias; p.resid = g.resid; p.ldr = g.ldr;
-  p.gamma = g.ln_gamma; p.beta = g.ln_beta; p.eps = g.ln_eps;
+  p.gamma = g.ln_gamma; p.beta = g.ln_beta; p.eps = g.ln_eps; p.out = g.out; p.ldo = g.ldo;
   const int tiles = (int)((M + BM - 1) / BM);
   const int grid = tiles < sm_count_ln() ? tiles : sm_count_ln();
-  gemm_ln_tf32_kernel<C><<<grid, LN_THREADS, L::SMEM, st>>>(ma, mb, mo, p);
+  gemm_ln_tf32_kernel<C><<<grid, LN_THREADS, L::SMEM, st>>>(ma, mb, p);
   FS2_LAUNCH_CHECK();
   return FS2_OK;
 }

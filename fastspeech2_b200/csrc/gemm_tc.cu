@@ -27,8 +27,8 @@
 //   TMEM        : two accumulator buffers; warp 1 fills buffer i&1 while warps 2-5 drain the other
 //   output      : two epilogue groups (warps 2-5 and 6-9; thread == output row == TMEM lane) take alternate
 //                 32-column chunks: tcgen05.ld -> bias / ReLU / tanh / residual -> 128-byte-swizzled smem
-//                 staging (one box per group) -> TMA tensor store (rows past the utterance end are
-//                 clipped by the TMA unit); the groups overlap each other's TMEM / store latency
+//                 staging (one box per group) -> cooperative full-line global stores (rows past the
+//                 utterance end are predicated off); the groups overlap each other's latency
 //   PRECISE only: warps 10-13 split each landed A tile in place into hi / lo (element-wise, so the
 //                 swizzled layout is untouched) and hand the slot to the MMA warp through a third
 //                 mbarrier; the weight hi / lo arrays are split once at load time.
@@ -53,6 +53,7 @@ struct TcParams {
   int m_tiles, n_tiles;
   int K, taps, pad;
   const float* bias; const float* resid; int ldr; int act;
+  float* out; int ldo;
   // optional: columns >= vt_col0 are the V third of a q|k|v projection and are stored transposed,
   // vt[(b*heads + h)*dk + d][t] with row pitch vt_lpad, for the attention kernel's K-major P.V operand
   float* vt_out; int vt_col0, vt_dk, vt_heads, vt_lpad, vt_L;
@@ -86,7 +87,7 @@ __device__ __forceinline__ float hi_tf32(float x) { return __uint_as_float(__flo
 template <int BN, bool PRECISE>
 __global__ void __launch_bounds__(Cfg<BN, PRECISE>::THREADS, 1)
 tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                     const __grid_constant__ CUtensorMap tmap_b_lo, const __grid_constant__ CUtensorMap tmap_out, TcParams p) {
+                     const __grid_constant__ CUtensorMap tmap_b_lo, TcParams p) {
   using C = Cfg<BN, PRECISE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -174,7 +175,8 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     //      thread == output row; the groups take alternate 32-column chunks ----
     const int wq = warp & 3, grp = (warp - 2) >> 2;
     const int row = wq * 32 + lane;
-    const bool elected = (threadIdx.x - 64) % 128 == 0;   // first lane of each group issues its tensor stores
+    const int gtid = (threadIdx.x - 64) & 127;            // thread index inside the group
+    const bool elected = gtid == 0;
     uint8_t* stage = staging + (size_t)grp * (BM * 128);
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
     float v[32];
@@ -225,8 +227,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           for (int q = 0; q < 8; ++q)
             if (c0 + q * 4 < BN) rv[q] = __ldg(reinterpret_cast<const float4*>(p.resid + m * p.ldr + n0 + c0 + q * 4));
         }
-        if (elected) tma_store_wait_read<0>();   // this group's previous store has read the staging box
-        named_bar_sync(1 + grp, 128);
+        named_bar_sync(1 + grp, 128);            // the previous box has been read out by the whole group
         tmem_ld32(taddr + c0, v);
         float4* srow = reinterpret_cast<float4*>(stage + (size_t)row * 128);
 #pragma unroll
@@ -240,19 +241,14 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           }
           srow[q ^ (row & 7)] = o;               // 128-byte swizzle: 16-byte chunk index XOR (row mod 8)
         }
-        fence_proxy_async();                     // generic-proxy smem writes -> visible to the TMA unit
         named_bar_sync(1 + grp, 128);
-        if (elected) {
-          tma_store_3d(&tmap_out, stage, n0 + c0, t0, b);
-          tma_store_commit();
-        }
+        store_box_coalesced(stage, p.out + ((long)b * p.L + t0) * p.ldo + n0 + c0, p.ldo, gtid, p.L - t0, BN - c0);
       }
       // this group's TMEM reads of the tile are complete (every thread passed its last tcgen05.wait::ld)
       tcgen05_fence_before();
       named_bar_sync(1 + grp, 128);
       if (elected) mbar_arrive(&acc_empty[acc]);
     }
-    if (elected) tma_store_wait_all<0>();        // stores must complete before the CTA exits
   } else if (PRECISE) {
     // ---- operand split (warps 10..13): A tile -> hi (in place) and lo (second buffer), same swizzled positions ----
     const int tid = threadIdx.x - 320;      // 0..127
@@ -314,22 +310,20 @@ int launch(const TapGemm& g, cudaStream_t st) {
   }
   TcParams p;
   p.K = g.K; p.taps = g.taps; p.pad = (g.taps - 1) / 2;
-  p.bias = g.bias; p.resid = g.resid; p.ldr = g.ldr; p.act = g.act;
+  p.bias = g.bias; p.resid = g.resid; p.ldr = g.ldr; p.act = g.act; p.out = g.out; p.ldo = g.ldo;
   p.vt_out = g.vt_out; p.vt_col0 = g.vt_col0; p.vt_dk = g.vt_dk; p.vt_heads = g.vt_heads; p.vt_lpad = g.vt_lpad; p.vt_L = g.L;
-  CUtensorMap ma, mb, mb_lo, mo;
+  CUtensorMap ma, mb, mb_lo;
   int rc;
-  const uint64_t row_bytes = (uint64_t)g.ldx * 4, orow = (uint64_t)g.ldo * 4;
+  const uint64_t row_bytes = (uint64_t)g.ldx * 4;
   if (g.taps == 1) {  // flat [B*L, K]
     const uint64_t M = (uint64_t)g.B * g.L;
     p.L = (int)M; p.tiles_per_utt = 0;
     p.m_tiles = (int)((M + BM - 1) / BM);
     if ((rc = make_map(&ma, g.x, g.K, M, 1, row_bytes, row_bytes * M, BM))) return rc;
-    if ((rc = make_map(&mo, g.out, g.N, M, 1, orow, orow * M, BM))) return rc;
   } else {            // per-utterance tiles: shifted boxes zero-fill outside [0, L)
     p.L = g.L; p.tiles_per_utt = (g.L + BM - 1) / BM;
     p.m_tiles = p.tiles_per_utt * g.B;
     if ((rc = make_map(&ma, g.x, g.K, g.L, g.B, row_bytes, row_bytes * g.L, BM))) return rc;
-    if ((rc = make_map(&mo, g.out, g.N, g.L, g.B, orow, orow * g.L, BM))) return rc;
   }
   p.n_tiles = g.N / BN;
   const float* w_hi = PRECISE ? g.w_hi : g.w;
@@ -337,7 +331,7 @@ int launch(const TapGemm& g, cudaStream_t st) {
   if ((rc = make_map(&mb_lo, PRECISE ? g.w_lo : w_hi, g.K, g.N, g.taps, (uint64_t)g.K * 4, (uint64_t)g.K * 4 * g.N, BN))) return rc;
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < sm_count() ? total : sm_count();
-  tap_gemm_tf32_kernel<BN, PRECISE><<<grid, C::THREADS, C::SMEM, st>>>(ma, mb, mb_lo, mo, p);
+  tap_gemm_tf32_kernel<BN, PRECISE><<<grid, C::THREADS, C::SMEM, st>>>(ma, mb, mb_lo, p);
   FS2_LAUNCH_CHECK();
   return FS2_OK;
 }

@@ -52,6 +52,20 @@ template <int N>
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// Cooperative store of a [128 x 32] fp32 box that 128 threads staged row-per-thread with the 128-byte swizzle
+// (16-byte chunk index XOR row%8): lanes 8i..8i+7 write one full 128-byte row segment, a warp writes 4 rows per
+// instruction -> full-line coalesced global stores without going through the TMA queue (which the operand loads
+// keep busy: a TMA store per chunk cost ~2 us of queueing, profiles/README.md).
+__device__ __forceinline__ void store_box_coalesced(const uint8_t* stage, float* out, long ldo, int tid, int rows_valid, int cols_valid) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int idx = tid + 128 * i, r = idx >> 3, ch = idx & 7;
+    if (r < rows_valid && ch * 4 < cols_valid) {
+      const float4 v = *reinterpret_cast<const float4*>(stage + r * 128 + ((ch ^ (r & 7)) << 4));
+      *reinterpret_cast<float4*>(out + (long)r * ldo + ch * 4) = v;
+    }
+  }
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
