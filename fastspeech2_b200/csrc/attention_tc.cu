@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_tf32_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constant__ CUtensorMap tmap_vt, AParams p) {
   using A = ACfg<DK>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* q_smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* q_smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint8_t* ring = q_smem + A::Q_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)A::SLOTS * A::SLOT);
   uint64_t* full_bar = bars;                   // [SLOTS]

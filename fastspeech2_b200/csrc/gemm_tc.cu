@@ -90,7 +90,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                      const __grid_constant__ CUtensorMap tmap_b_lo, TcParams p) {
   using C = Cfg<BN, PRECISE>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (no generic LD/ST)
   uint8_t* staging = tiles + (size_t)C::STAGES * C::STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
