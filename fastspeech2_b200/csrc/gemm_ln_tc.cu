@@ -14,7 +14,7 @@
 // Epilogue (8 warps = two groups x 4 lane quarters; two threads per row, alternate 32-column chunks):
 //   pass A  y = acc + bias + resid  -> written back to TMEM, partial row sums
 //   pass B  partial sums of (y - mean)^2        (two-pass variance like nn.LayerNorm)
-//   pass C  (y - mean) * rstd * gamma + beta -> swizzled smem staging -> cooperative full-line global stores
+//   pass C  (y - mean) * rstd * gamma + beta -> four 256-bit global stores per thread and chunk
 // Row statistics are exchanged between the two threads of a row through shared memory.
 #include "tc_common.cuh"
 
@@ -31,7 +31,7 @@ struct LCfg {
   static constexpr int HALF = C / 2;                      // one MMA / one TMA box of weight rows
   static constexpr int B_BYTES = C * BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGING_BYTES = 2 * BM * 32 * 4;
+  static constexpr int STAGING_BYTES = 2 * BM * 4;         // row-statistic exchange between the two threads of a row
   static constexpr int STAGES = (227 * 1024 - STAGING_BYTES - 1024 - 512) / STAGE_BYTES;
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
   static constexpr uint32_t IDESC = idesc_tf32(BM, HALF);
@@ -67,7 +67,7 @@ gemm_ln_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < L::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(acc_full, 1); mbar_init(acc_empty, 2);
+    mbar_init(acc_full, 1); mbar_init(acc_empty, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, L::TMEM_COLS);
@@ -118,11 +118,8 @@ gemm_ln_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // ---- epilogue: group g = (warp-2)/4 takes the 32-column chunks g, g+2, g+4, ...; thread == row ----
     const int wq = warp & 3, grp = (warp - 2) >> 2;
     const int row = wq * 32 + lane;
-    const int gtid = (threadIdx.x - 64) & 127;
-    const bool elected = gtid == 0;
     const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
-    uint8_t* stage = staging + (size_t)grp * (BM * 128);
-    float* xchg = reinterpret_cast<float*>(staging);          // [2][128] floats inside group 0's staging box
+    float* xchg = reinterpret_cast<float*>(staging);          // [2][128] floats
     float v[32];
     int it = 0;
     for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, ++it) {
@@ -160,7 +157,6 @@ gemm_ln_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tmem_st32(taddr + c0, v);
       }
       tmem_st_wait();
-      named_bar_sync(3, 256);                                  // xchg lives in group 0's staging box: its last read-out is done
       xchg[grp * BM + row] = sum;
       named_bar_sync(3, 256);
       const float mean = (sum + xchg[(grp ^ 1) * BM + row]) * (1.0f / C);
@@ -177,7 +173,7 @@ gemm_ln_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       xchg[grp * BM + row] = ssq;
       named_bar_sync(3, 256);
       const float rstd = 1.0f / sqrtf((ssq + xchg[(grp ^ 1) * BM + row]) * (1.0f / C) + p.eps);
-      named_bar_sync(3, 256);                                  // xchg reads done before group 0 reuses its box
+      named_bar_sync(3, 256);                                  // xchg reads done before the next tile rewrites it
       // pass C: normalise, affine, stage, TMA store
 #pragma unroll 1
       for (int i = 0; i < L::CHUNKS_PER_GROUP; ++i) {
@@ -188,22 +184,22 @@ gemm_ln_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           gv[q] = __ldg(reinterpret_cast<const float4*>(p.gamma + c0 + q * 4));
           bt[q] = __ldg(reinterpret_cast<const float4*>(p.beta + c0 + q * 4));
         }
-        named_bar_sync(1 + grp, 128);
+        __syncwarp();
         tmem_ld32(taddr + c0, v);
-        float4* srow = reinterpret_cast<float4*>(stage + (size_t)row * 128);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          float4 o;
-          o.x = (v[q * 4 + 0] - mean) * rstd * gv[q].x + bt[q].x; o.y = (v[q * 4 + 1] - mean) * rstd * gv[q].y + bt[q].y;
-          o.z = (v[q * 4 + 2] - mean) * rstd * gv[q].z + bt[q].z; o.w = (v[q * 4 + 3] - mean) * rstd * gv[q].w + bt[q].w;
-          srow[q ^ (row & 7)] = o;
+          v[q * 4 + 0] = (v[q * 4 + 0] - mean) * rstd * gv[q].x + bt[q].x; v[q * 4 + 1] = (v[q * 4 + 1] - mean) * rstd * gv[q].y + bt[q].y;
+          v[q * 4 + 2] = (v[q * 4 + 2] - mean) * rstd * gv[q].z + bt[q].z; v[q * 4 + 3] = (v[q * 4 + 3] - mean) * rstd * gv[q].w + bt[q].w;
         }
-        named_bar_sync(1 + grp, 128);
-        store_box_coalesced(stage, p.out + (long)r0 * p.ldo + c0, p.ldo, gtid, p.M - r0, 32);
+        if (row_ok) {
+          float* dst = p.out + m * p.ldo + c0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) st_global_v8(dst + q * 8, v + q * 8);
+        }
       }
       tcgen05_fence_before();
-      named_bar_sync(1 + grp, 128);
-      if (elected) mbar_arrive(acc_empty);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
     }
   }
   tcgen05_fence_before();
@@ -230,7 +226,8 @@ bool gemm_ln_tf32_supported(const TapGemm& g) { return g.taps == 1 && g.N == 384
 
 int gemm_ln_tf32(const TapGemm& g, cudaStream_t st) {
   FS2_REQUIRE(gemm_ln_tf32_supported(g), "gemm_ln_tf32: unsupported shape (N=%d taps=%d)", g.N, g.taps);
-  FS2_REQUIRE(g.ldx % 4 == 0 && g.ldo % 4 == 0 && (!g.resid || g.ldr % 4 == 0), "gemm_ln_tf32: row strides must be 16-byte multiples");
+  FS2_REQUIRE(g.ldx % 4 == 0 && g.ldo % 8 == 0 && (!g.resid || g.ldr % 4 == 0) && (reinterpret_cast<uintptr_t>(g.out) & 31) == 0,
+              "gemm_ln_tf32: row strides / output alignment");
   constexpr int C = 384;
   using L = LCfg<C>;
   const uint64_t M = (uint64_t)g.B * g.L;

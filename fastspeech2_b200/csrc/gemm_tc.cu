@@ -26,9 +26,9 @@
 //   smem ring   : warp 0 (TMA producer, one lane)  <-> warp 1 (MMA issuer, one lane), full/empty mbarriers
 //   TMEM        : two accumulator buffers; warp 1 fills buffer i&1 while warps 2-5 drain the other
 //   output      : two epilogue groups (warps 2-5 and 6-9; thread == output row == TMEM lane) take alternate
-//                 32-column chunks: tcgen05.ld -> bias / ReLU / tanh / residual -> 128-byte-swizzled smem
-//                 staging (one box per group) -> cooperative full-line global stores (rows past the
-//                 utterance end are predicated off); the groups overlap each other's latency
+//                 32-column chunks: tcgen05.ld -> bias / ReLU / tanh / residual in registers -> four
+//                 256-bit global stores per thread (sector-complete, no shared-memory transpose, no
+//                 barriers; rows past the utterance end are predicated off)
 //   PRECISE only: warps 10-13 split each landed A tile in place into hi / lo (element-wise, so the
 //                 swizzled layout is untouched) and hand the slot to the MMA warp through a third
 //                 mbarrier; the weight hi / lo arrays are split once at load time.
@@ -45,7 +45,7 @@ constexpr int BM = 128;
 constexpr int BK = 32;                 // fp32 elements per pipeline step = one 128-byte swizzle row
 constexpr int UMMA_K = 8;              // tf32
 constexpr int A_BYTES = BM * BK * 4;   // 16 KB
-constexpr int STAGING_BYTES = 2 * BM * 32 * 4;   // two [128 x 32] fp32 output boxes
+constexpr int STAGING_BYTES = 0;                 // the epilogue stores straight from registers (STG.256)
 constexpr int RING_BUDGET = 227 * 1024 - STAGING_BYTES - 1024 /*align slack*/ - 512 /*barriers*/;
 
 struct TcParams {
@@ -106,7 +106,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], 4); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);   // whole warp: both accumulator buffers
@@ -175,9 +175,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     //      thread == output row; the groups take alternate 32-column chunks ----
     const int wq = warp & 3, grp = (warp - 2) >> 2;
     const int row = wq * 32 + lane;
-    const int gtid = (threadIdx.x - 64) & 127;            // thread index inside the group
-    const bool elected = gtid == 0;
-    uint8_t* stage = staging + (size_t)grp * (BM * 128);
+
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
     float v[32];
     int it = 0;
@@ -227,27 +225,29 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           for (int q = 0; q < 8; ++q)
             if (c0 + q * 4 < BN) rv[q] = __ldg(reinterpret_cast<const float4*>(p.resid + m * p.ldr + n0 + c0 + q * 4));
         }
-        named_bar_sync(1 + grp, 128);            // the previous box has been read out by the whole group
+        __syncwarp();
         tmem_ld32(taddr + c0, v);
-        float4* srow = reinterpret_cast<float4*>(stage + (size_t)row * 128);
+        if (row_ok) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 o = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-          if (c0 + q * 4 < BN) {
-            o.x += bv[q].x; o.y += bv[q].y; o.z += bv[q].z; o.w += bv[q].w;
-            if (p.act == ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            else if (p.act == ACT_TANH) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
-            if (p.resid && row_ok) { o.x += rv[q].x; o.y += rv[q].y; o.z += rv[q].z; o.w += rv[q].w; }
+          for (int q = 0; q < 8; ++q) {
+            if (c0 + q * 4 < BN) {
+              float* o = v + q * 4;
+              o[0] += bv[q].x; o[1] += bv[q].y; o[2] += bv[q].z; o[3] += bv[q].w;
+              if (p.act == ACT_RELU) { o[0] = fmaxf(o[0], 0.f); o[1] = fmaxf(o[1], 0.f); o[2] = fmaxf(o[2], 0.f); o[3] = fmaxf(o[3], 0.f); }
+              else if (p.act == ACT_TANH) { o[0] = tanhf(o[0]); o[1] = tanhf(o[1]); o[2] = tanhf(o[2]); o[3] = tanhf(o[3]); }
+              if (p.resid) { o[0] += rv[q].x; o[1] += rv[q].y; o[2] += rv[q].z; o[3] += rv[q].w; }
+            }
           }
-          srow[q ^ (row & 7)] = o;               // 128-byte swizzle: 16-byte chunk index XOR (row mod 8)
+          float* dst = p.out + m * p.ldo + n0 + c0;      // this thread's row: four sector-complete 32-byte stores
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (c0 + q * 8 < BN) st_global_v8(dst + q * 8, v + q * 8);
         }
-        named_bar_sync(1 + grp, 128);
-        store_box_coalesced(stage, p.out + ((long)b * p.L + t0) * p.ldo + n0 + c0, p.ldo, gtid, p.L - t0, BN - c0);
       }
-      // this group's TMEM reads of the tile are complete (every thread passed its last tcgen05.wait::ld)
+      // this warp's TMEM reads of the tile are complete (every lane passed its last tcgen05.wait::ld)
       tcgen05_fence_before();
-      named_bar_sync(1 + grp, 128);
-      if (elected) mbar_arrive(&acc_empty[acc]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
     }
   } else if (PRECISE) {
     // ---- operand split (warps 10..13): A tile -> hi (in place) and lo (second buffer), same swizzled positions ----
@@ -342,6 +342,7 @@ int check_common(const TapGemm& g, const char* who) {
   FS2_REQUIRE((reinterpret_cast<uintptr_t>(g.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.w) & 15) == 0 &&
               (reinterpret_cast<uintptr_t>(g.out) & 15) == 0, "%s: operands must be 16-byte aligned", who);
   FS2_REQUIRE((g.taps & 1) == 1, "%s: taps must be odd", who);
+  FS2_REQUIRE(g.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(g.out) & 31) == 0, "%s: output rows must be 32-byte aligned (256-bit stores)", who);
   return FS2_OK;
 }
 
