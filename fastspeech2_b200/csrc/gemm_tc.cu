@@ -177,6 +177,9 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     const int row = wq * 32 + lane;
 
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+    const int act = p.act, ldr = p.ldr, ldo = p.ldo;
+    const float* __restrict__ bias = p.bias; const float* __restrict__ resid = p.resid; float* __restrict__ out = p.out;
+    const bool has_res = resid != nullptr, has_bias = bias != nullptr;
     float v[32];
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -186,8 +189,8 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       const int t = t0 + row;
       const bool row_ok = t < p.L;               // flat mode: L == total rows
       const long m = (long)b * p.L + t;
-      if (p.resid && row_ok) {                   // residual rows -> L2 while the main loop of this tile runs
-        for (int c0 = grp * 32; c0 < BN; c0 += 64) prefetch_l2(p.resid + m * p.ldr + n0 + c0);
+      if (has_res && row_ok) {                   // residual rows -> L2 while the main loop of this tile runs
+        for (int c0 = grp * 32; c0 < BN; c0 += 64) prefetch_l2(resid + m * ldr + n0 + c0);
       }
       mbar_wait(&acc_full[acc], (it >> 1) & 1);
       tcgen05_fence_after();
@@ -201,7 +204,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           bv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias && c0 + q * 4 < BN) bv[q] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + q * 4));
+          if (has_bias && c0 + q * 4 < BN) bv[q] = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + q * 4));
         }
         if (to_vt) {
           __syncwarp();
@@ -220,28 +223,40 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           }
           continue;
         }
-        if (p.resid && row_ok) {
+        const bool full = c0 + 32 <= BN;          // all 32 columns of the chunk exist (always, except the N = 80 tail)
+        if (has_res && row_ok) {
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            if (c0 + q * 4 < BN) rv[q] = __ldg(reinterpret_cast<const float4*>(p.resid + m * p.ldr + n0 + c0 + q * 4));
+            if (full || c0 + q * 4 < BN) rv[q] = __ldg(reinterpret_cast<const float4*>(resid + m * ldr + n0 + c0 + q * 4));
         }
         __syncwarp();
         tmem_ld32(taddr + c0, v);
         if (row_ok) {
+          // flags were hoisted into registers and the activation switch sits outside the element loops: the
+          // per-element predicate / constant-bank reloads of the first version made this epilogue latency-bound
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            if (c0 + q * 4 < BN) {
-              float* o = v + q * 4;
-              o[0] += bv[q].x; o[1] += bv[q].y; o[2] += bv[q].z; o[3] += bv[q].w;
-              if (p.act == ACT_RELU) { o[0] = fmaxf(o[0], 0.f); o[1] = fmaxf(o[1], 0.f); o[2] = fmaxf(o[2], 0.f); o[3] = fmaxf(o[3], 0.f); }
-              else if (p.act == ACT_TANH) { o[0] = tanhf(o[0]); o[1] = tanhf(o[1]); o[2] = tanhf(o[2]); o[3] = tanhf(o[3]); }
-              if (p.resid) { o[0] += rv[q].x; o[1] += rv[q].y; o[2] += rv[q].z; o[3] += rv[q].w; }
-            }
+          for (int q = 0; q < 8; ++q) { v[q * 4] += bv[q].x; v[q * 4 + 1] += bv[q].y; v[q * 4 + 2] += bv[q].z; v[q * 4 + 3] += bv[q].w; }
+          if (act == ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          } else if (act == ACT_TANH) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
           }
-          float* dst = p.out + m * p.ldo + n0 + c0;      // this thread's row: four sector-complete 32-byte stores
+          if (has_res) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (c0 + q * 8 < BN) st_global_v8(dst + q * 8, v + q * 8);
+            for (int q = 0; q < 8; ++q)
+              if (full || c0 + q * 4 < BN) { v[q * 4] += rv[q].x; v[q * 4 + 1] += rv[q].y; v[q * 4 + 2] += rv[q].z; v[q * 4 + 3] += rv[q].w; }
+          }
+          float* dst = out + m * ldo + n0 + c0;          // this thread's row: four sector-complete 32-byte stores
+          if (full) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) st_global_v8(dst + q * 8, v + q * 8);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (c0 + q * 8 < BN) st_global_v8(dst + q * 8, v + q * 8);
+          }
         }
       }
       // this warp's TMEM reads of the tile are complete (every lane passed its last tcgen05.wait::ld)
