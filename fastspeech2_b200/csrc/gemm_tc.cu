@@ -45,7 +45,7 @@ constexpr int BM = 128;
 constexpr int BK = 32;                 // fp32 elements per pipeline step = one 128-byte swizzle row
 constexpr int UMMA_K = 8;              // tf32
 constexpr int A_BYTES = BM * BK * 4;   // 16 KB
-constexpr int STAGING_BYTES = 0;                 // the epilogue stores straight from registers (STG.256)
+constexpr int STAGING_BYTES = 8 * 1024;          // bias[N] (N <= 2048) staged once per CTA; outputs go straight from registers
 constexpr int RING_BUDGET = 227 * 1024 - STAGING_BYTES - 1024 /*align slack*/ - 512 /*barriers*/;
 
 struct TcParams {
@@ -68,7 +68,8 @@ struct Cfg {
   static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
   static constexpr int ACC_STRIDE = pow2_at_least(BN);     // TMEM columns per accumulator buffer
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int THREADS = PRECISE ? 448 : 320;
+  static constexpr int GROUPS = PRECISE ? 2 : 4;       // epilogue warp groups (4 warps each), alternate 32-column chunks
+  static constexpr int THREADS = 64 + GROUPS * 128 + (PRECISE ? 128 : 0);
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
   static constexpr uint32_t IDESC = idesc_tf32(BM, BN);
   static constexpr int A_LO = A_BYTES;                                  // offsets inside a stage
@@ -106,7 +107,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], 4); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4 * C::GROUPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);   // whole warp: both accumulator buffers
@@ -114,6 +115,12 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  float* bias_s = reinterpret_cast<float*>(staging);      // whole bias vector, read back as broadcast LDS in the epilogue
+  {
+    const int N = p.n_tiles * BN;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) bias_s[i] = p.bias ? __ldg(p.bias + i) : 0.f;
+  }
+  __syncthreads();
 
   auto tile_coords = [&](int tile, int& n0, int& b, int& t0) {
     const int mt = tile / p.n_tiles;
@@ -170,16 +177,16 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         tcgen05_commit(&acc_full[acc]);        // accumulator complete
       }
     }
-  } else if (warp < 10) {
-    // ---- epilogue: group 0 = warps 2..5, group 1 = warps 6..9; warp w owns TMEM lanes 32*(w%4) .. +31;
+  } else if (warp < 2 + 4 * C::GROUPS) {
+    // ---- epilogue: group g = warps 2+4g .. 5+4g; warp w owns TMEM lanes 32*(w%4) .. +31;
     //      thread == output row; the groups take alternate 32-column chunks ----
     const int wq = warp & 3, grp = (warp - 2) >> 2;
     const int row = wq * 32 + lane;
 
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
     const int act = p.act, ldr = p.ldr, ldo = p.ldo;
-    const float* __restrict__ bias = p.bias; const float* __restrict__ resid = p.resid; float* __restrict__ out = p.out;
-    const bool has_res = resid != nullptr, has_bias = bias != nullptr;
+    const float* __restrict__ resid = p.resid; float* __restrict__ out = p.out;
+    const bool has_res = resid != nullptr;
     float v[32];
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -190,22 +197,18 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       const bool row_ok = t < p.L;               // flat mode: L == total rows
       const long m = (long)b * p.L + t;
       if (has_res && row_ok) {                   // residual rows -> L2 while the main loop of this tile runs
-        for (int c0 = grp * 32; c0 < BN; c0 += 64) prefetch_l2(resid + m * ldr + n0 + c0);
+        for (int c0 = grp * 32; c0 < BN; c0 += 32 * C::GROUPS) prefetch_l2(resid + m * ldr + n0 + c0);
       }
       mbar_wait(&acc_full[acc], (it >> 1) & 1);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + lane_off + (uint32_t)(acc * C::ACC_STRIDE);
       const bool to_vt = p.vt_out != nullptr && n0 >= p.vt_col0;   // tile-uniform (tile widths divide the V third)
 #pragma unroll 1
-      for (int c0 = grp * 32; c0 < BN; c0 += 64) {
-        // bias (same 32 values for every row) and residual are fetched first so the loads are in flight across the
-        // barrier and the TMEM load; issued next to their use they stall the whole epilogue (ncu: long scoreboard)
-        float4 bv[8], rv[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          bv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (has_bias && c0 + q * 4 < BN) bv[q] = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + q * 4));
-        }
+      for (int c0 = grp * 32; c0 < BN; c0 += 32 * C::GROUPS) {
+        // the residual is fetched first so the loads are in flight across the TMEM load; the bias comes from shared
+        // memory (global loads next to their use stalled the whole epilogue: ncu long-scoreboard samples)
+        float4 rv[8];
+        const float4* bq = reinterpret_cast<const float4*>(bias_s + n0 + c0);
         if (to_vt) {
           __syncwarp();
           tmem_ld32(taddr + c0, v);
@@ -216,10 +219,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             float* dst = p.vt_out + ((ub * p.vt_heads + hh) * p.vt_dk + d0) * (long)p.vt_lpad + ut;
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (c0 + i < BN) {
-                const float4 bq = bv[i >> 2];
-                dst[(long)i * p.vt_lpad] = v[i] + ((i & 3) == 0 ? bq.x : (i & 3) == 1 ? bq.y : (i & 3) == 2 ? bq.z : bq.w);
-              }
+              if (c0 + i < BN) dst[(long)i * p.vt_lpad] = v[i] + bias_s[n0 + c0 + i];
           }
           continue;
         }
@@ -235,7 +235,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           // flags were hoisted into registers and the activation switch sits outside the element loops: the
           // per-element predicate / constant-bank reloads of the first version made this epilogue latency-bound
 #pragma unroll
-          for (int q = 0; q < 8; ++q) { v[q * 4] += bv[q].x; v[q * 4 + 1] += bv[q].y; v[q * 4 + 2] += bv[q].z; v[q * 4 + 3] += bv[q].w; }
+          for (int q = 0; q < 8; ++q) { const float4 b4 = bq[q]; v[q * 4] += b4.x; v[q * 4 + 1] += b4.y; v[q * 4 + 2] += b4.z; v[q * 4 + 3] += b4.w; }
           if (act == ACT_RELU) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -265,8 +265,8 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
     }
   } else if (PRECISE) {
-    // ---- operand split (warps 10..13): A tile -> hi (in place) and lo (second buffer), same swizzled positions ----
-    const int tid = threadIdx.x - 320;      // 0..127
+    // ---- operand split (the last 4 warps): A tile -> hi (in place) and lo (second buffer), same swizzled positions ----
+    const int tid = threadIdx.x - (64 + 128 * C::GROUPS);      // 0..127
     int n = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       for (int s = 0; s < steps; ++s, ++n) {
@@ -357,6 +357,7 @@ int check_common(const TapGemm& g, const char* who) {
   FS2_REQUIRE((reinterpret_cast<uintptr_t>(g.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.w) & 15) == 0 &&
               (reinterpret_cast<uintptr_t>(g.out) & 15) == 0, "%s: operands must be 16-byte aligned", who);
   FS2_REQUIRE((g.taps & 1) == 1, "%s: taps must be odd", who);
+  FS2_REQUIRE(g.N <= 2048, "%s: N (%d) exceeds the staged bias vector (2048)", who, g.N);
   FS2_REQUIRE(g.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(g.out) & 31) == 0, "%s: output rows must be 32-byte aligned (256-bit stores)", who);
   return FS2_OK;
 }
