@@ -35,6 +35,8 @@
 // Convolutions tile each utterance separately (ceil(L/128) row tiles) so the shifted boxes never
 // cross an utterance boundary; plain GEMMs (taps == 1) tile the flat [B*L, K] matrix.
 // Every mbarrier wait is bounded: a pipeline bug traps instead of hanging the GPU.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace fs2 {
@@ -57,6 +59,7 @@ struct TcParams {
   // optional: columns >= vt_col0 are the V third of a q|k|v projection and are stored transposed,
   // vt[(b*heads + h)*dk + d][t] with row pitch vt_lpad, for the attention kernel's K-major P.V operand
   float* vt_out; int vt_col0, vt_dk, vt_heads, vt_lpad, vt_L;
+  int debug;   // FS2_GEMM_DEBUG: bit0 skip tcgen05.ld, bit1 skip stores (profiling experiments only)
 };
 
 constexpr int pow2_at_least(int x) { return x <= 32 ? 32 : x <= 64 ? 64 : x <= 128 ? 128 : 256; }
@@ -68,7 +71,7 @@ struct Cfg {
   static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
   static constexpr int ACC_STRIDE = pow2_at_least(BN);     // TMEM columns per accumulator buffer
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int GROUPS = PRECISE ? 2 : 4;       // epilogue warp groups (4 warps each), alternate 32-column chunks
+  static constexpr int GROUPS = 2;       // epilogue warp groups (4 warps each), alternate 32-column chunks
   static constexpr int THREADS = 64 + GROUPS * 128 + (PRECISE ? 128 : 0);
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
   static constexpr uint32_t IDESC = idesc_tf32(BM, BN);
@@ -230,8 +233,8 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             if (full || c0 + q * 4 < BN) rv[q] = __ldg(reinterpret_cast<const float4*>(resid + m * ldr + n0 + c0 + q * 4));
         }
         __syncwarp();
-        tmem_ld32(taddr + c0, v);
-        if (row_ok) {
+        if (!(p.debug & 1)) tmem_ld32(taddr + c0, v);
+        if (row_ok && !(p.debug & 2)) {
           // flags were hoisted into registers and the activation switch sits outside the element loops: the
           // per-element predicate / constant-bank reloads of the first version made this epilogue latency-bound
 #pragma unroll
@@ -326,6 +329,7 @@ int launch(const TapGemm& g, cudaStream_t st) {
   TcParams p;
   p.K = g.K; p.taps = g.taps; p.pad = (g.taps - 1) / 2;
   p.bias = g.bias; p.resid = g.resid; p.ldr = g.ldr; p.act = g.act; p.out = g.out; p.ldo = g.ldo;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FS2_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
   p.vt_out = g.vt_out; p.vt_col0 = g.vt_col0; p.vt_dk = g.vt_dk; p.vt_heads = g.vt_heads; p.vt_lpad = g.vt_lpad; p.vt_L = g.L;
   CUtensorMap ma, mb, mb_lo;
   int rc;
