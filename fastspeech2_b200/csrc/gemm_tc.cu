@@ -32,8 +32,10 @@
 //   PRECISE only: warps 10-13 split each landed A tile in place into hi / lo (element-wise, so the
 //                 swizzled layout is untouched) and hand the slot to the MMA warp through a third
 //                 mbarrier; the weight hi / lo arrays are split once at load time.
-// Convolutions tile each utterance separately (ceil(L/128) row tiles) so the shifted boxes never
-// cross an utterance boundary; plain GEMMs (taps == 1) tile the flat [B*L, K] matrix.
+// Convolutions tile each utterance separately so the shifted boxes never cross an utterance boundary:
+// floor(L/128) full row tiles per utterance, and the tails (L % 128 rows, in 16-row granules loaded by
+// separate small TMA boxes) of several utterances packed into shared tiles, so no tensor-core rows are
+// spent on padding (at L = 800 that was 12 %).  Plain GEMMs (taps == 1) tile the flat [B*L, K] matrix.
 // Every mbarrier wait is bounded: a pipeline bug traps instead of hanging the GPU.
 #include <stdlib.h>
 
@@ -53,6 +55,9 @@ constexpr int RING_BUDGET = 227 * 1024 - STAGING_BYTES - 1024 /*align slack*/ - 
 struct TcParams {
   int L, tiles_per_utt;          // tiles_per_utt == 0: flat tiling, L = B*L rows
   int m_tiles, n_tiles;
+  // convolutions (tiles_per_utt > 0): every utterance has `full` 128-row tiles; its tail (L % 128 rows, `gn` granules
+  // of 16 rows) shares a packed tile with the tails of upt - 1 other utterances, so no MMA rows are wasted on padding
+  int B, full, gn, upt, full_tiles;
   int K, taps, pad;
   const float* bias; const float* resid; int ldr; int act;
   float* out; int ldo;
@@ -91,7 +96,7 @@ __device__ __forceinline__ float hi_tf32(float x) { return __uint_as_float(__flo
 template <int BN, bool PRECISE>
 __global__ void __launch_bounds__(Cfg<BN, PRECISE>::THREADS, 1)
 tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                     const __grid_constant__ CUtensorMap tmap_b_lo, TcParams p) {
+                     const __grid_constant__ CUtensorMap tmap_b_lo, const __grid_constant__ CUtensorMap tmap_a16, TcParams p) {
   using C = Cfg<BN, PRECISE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (no generic LD/ST)
@@ -125,26 +130,38 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   }
   __syncthreads();
 
-  auto tile_coords = [&](int tile, int& n0, int& b, int& t0) {
+  // packed < 0: ordinary tile (utterance b, rows t0 .. t0+127); packed >= 0: index of a packed tail tile
+  auto tile_coords = [&](int tile, int& n0, int& b, int& t0, int& packed) {
     const int mt = tile / p.n_tiles;
     n0 = (tile - mt * p.n_tiles) * BN;
-    if (p.tiles_per_utt > 0) { b = mt / p.tiles_per_utt; t0 = (mt - b * p.tiles_per_utt) * BM; }
-    else { b = 0; t0 = mt * BM; }
+    packed = -1;
+    if (p.tiles_per_utt == 0) { b = 0; t0 = mt * BM; }
+    else if (mt < p.full_tiles) { b = mt / p.full; t0 = (mt - b * p.full) * BM; }
+    else { packed = mt - p.full_tiles; b = packed * p.upt; t0 = p.full * BM; }
   };
 
   if (warp == 0) {
     if (lane == 0) {  // ---- TMA producer ----
       int n = 0;      // ring position, runs across tiles
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int n0, b, t0;
-        tile_coords(tile, n0, b, t0);
+        int n0, b, t0, packed;
+        tile_coords(tile, n0, b, t0, packed);
         for (int s = 0; s < steps; ++s, ++n) {
           const int slot = n % C::STAGES, round = n / C::STAGES;
           mbar_wait(&empty_bar[slot], (round & 1) ^ 1);
           const int j = s / kchunks, k0 = (s - j * kchunks) * BK;
           uint8_t* st = tiles + (size_t)slot * C::STAGE_BYTES;
           mbar_expect_tx(&full_bar[slot], C::TX_BYTES);
-          tma_load_3d(st, &tmap_a, &full_bar[slot], k0, t0 + j - p.pad, b);
+          if (packed < 0) {
+            tma_load_3d(st, &tmap_a, &full_bar[slot], k0, t0 + j - p.pad, b);
+          } else {
+            // eight 16-row boxes: granule g belongs to utterance b + g / gn (zero-filled past the batch or past L)
+            for (int g = 0; g < 8; ++g) {
+              const int u = g / p.gn, gi = g - u * p.gn;
+              const int bb = u < p.upt ? b + u : p.B;      // p.B is out of bounds in dim 2 -> the box is all zeros
+              tma_load_3d(st + g * (16 * 128), &tmap_a16, &full_bar[slot], k0, t0 + gi * 16 + j - p.pad, bb);
+            }
+          }
           tma_load_3d(st + C::B_HI, &tmap_b, &full_bar[slot], k0, n0, j);
           if (PRECISE) tma_load_3d(st + C::B_LO, &tmap_b_lo, &full_bar[slot], k0, n0, j);
         }
@@ -193,11 +210,17 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     float v[32];
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      int n0, b, t0;
-      tile_coords(tile, n0, b, t0);
+      int n0, b, t0, packed;
+      tile_coords(tile, n0, b, t0, packed);
       const int acc = it & 1;
-      const int t = t0 + row;
-      const bool row_ok = t < p.L;               // flat mode: L == total rows
+      int t = t0 + row;
+      bool row_ok = t < p.L;                     // flat mode: L == total rows
+      if (packed >= 0) {                         // packed tail tile: 16-row granule g of the tile -> utterance b + g / gn
+        const int g = row >> 4, u = g / p.gn, gi = g - u * p.gn;
+        b += u;
+        t = t0 + gi * 16 + (row & 15);
+        row_ok = u < p.upt && b < p.B && t < p.L;
+      }
       const long m = (long)b * p.L + t;
       if (has_res && row_ok) {                   // residual rows -> L2 while the main loop of this tile runs
         for (int c0 = grp * 32; c0 < BN; c0 += 32 * C::GROUPS) prefetch_l2(resid + m * ldr + n0 + c0);
@@ -331,18 +354,26 @@ int launch(const TapGemm& g, cudaStream_t st) {
   p.bias = g.bias; p.resid = g.resid; p.ldr = g.ldr; p.act = g.act; p.out = g.out; p.ldo = g.ldo;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FS2_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
   p.vt_out = g.vt_out; p.vt_col0 = g.vt_col0; p.vt_dk = g.vt_dk; p.vt_heads = g.vt_heads; p.vt_lpad = g.vt_lpad; p.vt_L = g.L;
-  CUtensorMap ma, mb, mb_lo;
+  CUtensorMap ma, mb, mb_lo, ma16;
   int rc;
   const uint64_t row_bytes = (uint64_t)g.ldx * 4;
   if (g.taps == 1) {  // flat [B*L, K]
     const uint64_t M = (uint64_t)g.B * g.L;
     p.L = (int)M; p.tiles_per_utt = 0;
     p.m_tiles = (int)((M + BM - 1) / BM);
+    p.B = 1; p.full = 0; p.gn = 1; p.upt = 1; p.full_tiles = 0;
     if ((rc = make_map(&ma, g.x, g.K, M, 1, row_bytes, row_bytes * M, BM))) return rc;
+    ma16 = ma;
   } else {            // per-utterance tiles: shifted boxes zero-fill outside [0, L)
     p.L = g.L; p.tiles_per_utt = (g.L + BM - 1) / BM;
-    p.m_tiles = p.tiles_per_utt * g.B;
+    p.B = g.B; p.full = g.L / BM;
+    const int tail = g.L % BM;
+    p.gn = tail ? (tail + 15) / 16 : 1;
+    p.upt = tail ? 8 / p.gn : 1;
+    p.full_tiles = p.full * g.B;
+    p.m_tiles = p.full_tiles + (tail ? (g.B + p.upt - 1) / p.upt : 0);
     if ((rc = make_map(&ma, g.x, g.K, g.L, g.B, row_bytes, row_bytes * g.L, BM))) return rc;
+    if ((rc = make_map(&ma16, g.x, g.K, g.L, g.B, row_bytes, row_bytes * g.L, 16))) return rc;
   }
   p.n_tiles = g.N / BN;
   const float* w_hi = PRECISE ? g.w_hi : g.w;
@@ -350,7 +381,7 @@ int launch(const TapGemm& g, cudaStream_t st) {
   if ((rc = make_map(&mb_lo, PRECISE ? g.w_lo : w_hi, g.K, g.N, g.taps, (uint64_t)g.K * 4, (uint64_t)g.K * 4 * g.N, BN))) return rc;
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < sm_count() ? total : sm_count();
-  tap_gemm_tf32_kernel<BN, PRECISE><<<grid, C::THREADS, C::SMEM, st>>>(ma, mb, mb_lo, p);
+  tap_gemm_tf32_kernel<BN, PRECISE><<<grid, C::THREADS, C::SMEM, st>>>(ma, mb, mb_lo, ma16, p);
   FS2_LAUNCH_CHECK();
   return FS2_OK;
 }
