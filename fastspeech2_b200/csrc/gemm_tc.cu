@@ -367,9 +367,10 @@ int launch(const TapGemm& g, cudaStream_t st) {
   } else {            // per-utterance tiles: shifted boxes zero-fill outside [0, L)
     p.L = g.L; p.tiles_per_utt = (g.L + BM - 1) / BM;
     p.B = g.B; p.full = g.L / BM;
-    const int tail = g.L % BM;
+    int tail = g.L % BM;
     p.gn = tail ? (tail + 15) / 16 : 1;
     p.upt = tail ? 8 / p.gn : 1;
+    if (tail && p.upt == 1) { p.full += 1; tail = 0; p.gn = 1; }   // tail > 64 rows: nothing to share, keep one ordinary (partly empty) tile
     p.full_tiles = p.full * g.B;
     p.m_tiles = p.full_tiles + (tail ? (g.B + p.upt - 1) / p.upt : 0);
     if ((rc = make_map(&ma, g.x, g.K, g.L, g.B, row_bytes, row_bytes * g.L, BM))) return rc;
