@@ -111,6 +111,15 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/ncu_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(p)).get(kernel, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -233,7 +242,7 @@ def run_length_regulator(args):
                 "h2d_bytes_per_step": hs_h.numel() * 4 + ds_h.numel() * 8, "d2h_bytes_per_step": out_h.numel() * 4},
         "gpu_launches": int(launches * args.steps), "gpu_launches_per_step": int(launches),
         "roofline": {"kernel": "length_gather_kernel", "bound": "hbm", "achieved": algo_bytes / (ms_gather * 1e-3) / 1e9, "peak": hbm,
-                     "unit": "GB/s", "frac": algo_bytes / (ms_gather * 1e-3) / 1e9 / hbm, "traffic": None,
+                     "unit": "GB/s", "frac": algo_bytes / (ms_gather * 1e-3) / 1e9 / hbm, "traffic": ncu_traffic("length_gather_kernel"),
                      "avg_launch_ms": ms_gather, "algorithmic_bytes": algo_bytes, "peak_source": src,
                      "whole_op_gbs": algo_bytes / (ms * 1e-3) / 1e9},
         "cpu_baseline": {"value": frames / cpu_s, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
@@ -362,7 +371,8 @@ def run_b200(args):
         pk = prof[top]
         achieved = pk["flop"] / (pk["ms"] * 1e-3) / 1e12 if pk["ms"] > 0 else 0.0
         roof = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-                "frac": achieved / tensor_peak, "traffic": None,
+                "frac": achieved / tensor_peak, "traffic": ncu_traffic(top),
+                "algorithmic_bytes_per_launch": pk["bytes"] / pk["launches"], "algorithmic_flop_per_launch": pk["flop"] / pk["launches"],
                 "avg_launch_ms": pk["ms"] / pk["launches"], "share_of_step": pk["ms"] / tot,
                 "peak_source": peak_src + ("; tf32 dense = 1/2 of the measured sustained bf16 rate" if args.precision == "tf32"
                                            else "; fp32 FMA pipe = 148 SM x 128 lanes x 2 x 1.965 GHz (nominal)"),
