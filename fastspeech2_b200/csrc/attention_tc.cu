@@ -11,10 +11,11 @@
 //          P.V product has a K-major B operand too (kv contiguous)
 //   P    : written by the softmax warps straight into TMEM and consumed from there as the A operand.
 //
-// CTA = 128 queries of one (batch, head).  Softmax is two-pass: pass 1 streams K once to get the
-// exact row maxima (S tiles only), pass 2 recomputes S, writes P = exp(s - max) into TMEM in place
-// of S, and accumulates O += P V^T and the row sums; no accumulator rescaling, O /= sum at the end.
-// That costs 1.5x the MMA work of a one-pass online softmax but keeps O untouched in TMEM.
+// CTA = 128 queries of one (batch, head).  Softmax is single-pass ("online") with a *lazy* reference
+// maximum: P = exp2(c*(s - m_ref)) is written into TMEM in place of S and O += P V^T accumulates in TMEM;
+// m_ref only moves (and O, l are rescaled by exp2(c*(m_ref_old - m_ref_new)) through tcgen05.ld/st) when a
+// tile's row maximum exceeds it by more than 2^8 in the exp2 domain, which after the first tile is rare, so the
+// accumulator is almost never touched.  O / l at the end is exact for any reference (no overflow: P <= 2^8).
 //
 // Warp roles (10 warps): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..9 = softmax /
 // epilogue (two threads per query row == TMEM lane, 64 score columns each; row statistics are
@@ -39,8 +40,8 @@ struct ACfg {
   static constexpr int K_BOX = BKV * CH * 4;           // 16 KB: 128 kv rows x 32 dk
   static constexpr int V_BOX = DK * CH * 4;            // DK rows x 32 kv
   static constexpr int SLOT = V_BOX > K_BOX ? V_BOX : K_BOX;
-  static constexpr int SLOTS = (212 * 1024 - Q_BYTES) / SLOT;
-  static constexpr size_t SMEM = (size_t)Q_BYTES + (size_t)SLOTS * SLOT + 1024 + 512 + 2 * BQ * 4;
+  static constexpr int SLOTS = (211 * 1024 - Q_BYTES) / SLOT;
+  static constexpr size_t SMEM = (size_t)Q_BYTES + (size_t)SLOTS * SLOT + 1024 + 512 + 4 * BQ * 4;
   static constexpr uint32_t IDESC_S = idesc_tf32(BQ, BKV);
   static constexpr uint32_t IDESC_O = idesc_tf32(BQ, DK);
   static constexpr int TMEM_COLS = 512;
@@ -65,11 +66,11 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_
   uint64_t* empty_bar = bars + A::SLOTS;       // [SLOTS]
   uint64_t* q_bar = bars + 2 * A::SLOTS;       // Q landed
   uint64_t* s_full = q_bar + 1;                // [2] MMA -> softmax: S tile ready
-  uint64_t* s_free = s_full + 2;               // [2] softmax -> MMA: pass-1 tile consumed
-  uint64_t* p_full = s_free + 2;               // [2] softmax -> MMA: P written
+  uint64_t* pv_done = s_full + 2;              // [2] (only [0] used) MMA -> softmax: P.V of the previous tile has finished
+  uint64_t* p_full = pv_done + 2;              // [2] softmax -> MMA: P written
   uint64_t* o_full = p_full + 2;               // all P.V done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
-  float* xchg = reinterpret_cast<float*>(tmem_slot + 4);   // [2][BQ] row-statistic exchange between column halves
+  float* xchg = reinterpret_cast<float*>(tmem_slot + 4);   // [2 tiles][2 halves][BQ] row-statistic exchange between column halves
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
@@ -79,7 +80,7 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_
   if (threadIdx.x == 0) {
     for (int s = 0; s < A::SLOTS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(q_bar, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 8); mbar_init(&p_full[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&pv_done[i], 1); mbar_init(&p_full[i], 8); }
     mbar_init(o_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -111,8 +112,7 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_
             tma_load_3d(ring + (size_t)slot * A::SLOT, &tmap_vt, &full_bar[slot], j * BKV + c * CH, 0, b * p.heads + h);
           }
         };
-        for (int j = 0; j < J; ++j) push_k(j);          // pass 1
-        push_k(0);                                      // pass 2
+        push_k(0);
         for (int j = 0; j < J; ++j) { if (j + 1 < J) push_k(j + 1); push_v(j); }
       }
     } else if (warp == 1) {
@@ -121,13 +121,9 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_
         tcgen05_fence_after();
         const uint32_t q_addr = smem_u32(q_smem);
         int n = 0;
-        // S tile number g (pass 1: g = j, pass 2: g = J + j) goes to S buffer g & 1
+        // S tile j goes to S/P buffer j & 1; S_{j+2} reuses it after P.V_j, which is issued earlier in this thread
         auto issue_s = [&](int g) {
           const uint32_t d = tmem_base + (uint32_t)((g & 1) * BKV);
-          if (g >= 2 && g - 2 < J) {   // buffer last held a pass-1 tile: wait until the softmax warps have read it
-            mbar_wait(&s_free[g & 1], ((g - 2) >> 1) & 1);
-            tcgen05_fence_after();
-          }
           for (int c = 0; c < A::QCH; ++c, ++n) {
             const int slot = n % A::SLOTS;
             mbar_wait(&full_bar[slot], (n / A::SLOTS) & 1);
@@ -140,14 +136,12 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_
           }
           tcgen05_commit(&s_full[g & 1]);
         };
-        for (int j = 0; j < J; ++j) issue_s(j);
-        issue_s(J);
+        issue_s(0);
         for (int j = 0; j < J; ++j) {
-          const int g = J + j;
-          if (j + 1 < J) issue_s(g + 1);
-          mbar_wait(&p_full[g & 1], (j >> 1) & 1);     // j-th pass-2 tile; buffer parity alternates with j
+          if (j + 1 < J) issue_s(j + 1);                 // the tensor core computes S_{j+1} while the softmax warps work on tile j
+          mbar_wait(&p_full[j & 1], (j >> 1) & 1);
           tcgen05_fence_after();
-          const uint32_t p_tmem = tmem_base + (uint32_t)((g & 1) * BKV);
+          const uint32_t p_tmem = tmem_base + (uint32_t)((j & 1) * BKV);
           for (int c = 0; c < BKV / CH; ++c, ++n) {
             const int slot = n % A::SLOTS;
             mbar_wait(&full_bar[slot], (n / A::SLOTS) & 1);
@@ -158,6 +152,7 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_
               umma_tf32_ts(tmem_base + A::O_COL, p_tmem + c * CH + k * 8, bdesc + 2 * k, A::IDESC_O, (j | c | k) != 0);
             tcgen05_commit(&empty_bar[slot]);
           }
+          tcgen05_commit(&pv_done[0]);                   // lets the softmax warps rescale O if tile j+1 raises the reference max
         }
         tcgen05_commit(o_full);
       }
@@ -167,8 +162,8 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_
       const int row = wq * 32 + lane;
       const uint32_t lane_addr = tmem_base + ((uint32_t)(wq * 32) << 16);
       float v[64];
-      float m_row = -INFINITY;
-      // pass 1: exact row maximum of the raw scores over valid keys (this thread: its 64 columns of every tile)
+      float m_ref = -INFINITY, l_row = 0.f;     // reference maximum (raw-score domain) and row sum relative to it
+      const float c_exp = p.scale_log2e;
       for (int j = 0; j < J; ++j) {
         mbar_wait(&s_full[j & 1], (j >> 1) & 1);
         tcgen05_fence_after();
@@ -176,38 +171,48 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_
         __syncwarp();
         const uint32_t ta = lane_addr + (uint32_t)((j & 1) * BKV + half * 64);
         tmem_ld32_nowait(ta, v); tmem_ld32_nowait(ta + 32, v + 32); tmem_ld_wait_pin<64>(v);
+        float tmax = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 64; ++i) if (kv0 + i < len) m_row = fmaxf(m_row, v[i]);
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[j & 1]);
-      }
-      xchg[half * BQ + row] = m_row;                             // combine the two column halves of each row
-      named_bar_sync(1, 256);
-      m_row = fmaxf(m_row, xchg[(half ^ 1) * BQ + row]);
-      named_bar_sync(1, 256);
-      // pass 2: P = exp2(scale*log2e * (s - max)) in place of S, partial row sums
-      const float mb = m_row * p.scale_log2e;
-      float l_row = 0.f;
-      for (int j = 0; j < J; ++j) {
-        const int g = J + j;
-        mbar_wait(&s_full[g & 1], (g >> 1) & 1);
-        tcgen05_fence_after();
-        const int kv0 = j * BKV + half * 64;
-        __syncwarp();
-        const uint32_t ta = lane_addr + (uint32_t)((g & 1) * BKV + half * 64);
-        tmem_ld32_nowait(ta, v); tmem_ld32_nowait(ta + 32, v + 32); tmem_ld_wait_pin<64>(v);
+        for (int i = 0; i < 64; ++i) if (kv0 + i < len) tmax = fmaxf(tmax, v[i]);
+        float* xr = xchg + (j & 1) * 2 * BQ;                     // double-buffered exchange: one barrier per tile
+        xr[half * BQ + row] = tmax;
+        named_bar_sync(1, 256);
+        tmax = fmaxf(tmax, xr[(half ^ 1) * BQ + row]);           // both threads of the row now hold the tile's row maximum
+        // lazy reference update: move m_ref only if the tile exceeds it by more than 2^8 in the exp2 domain
+        const bool bump = (tmax - m_ref) * c_exp > 8.0f;          // first tile: m_ref = -inf -> always
+        if (__any_sync(0xffffffffu, bump)) {
+          const float alpha = bump ? fast_exp2((m_ref - tmax) * c_exp) : 1.0f;   // exp2(-inf) = 0 on the first tile
+          if (j > 0) {   // O holds tiles 0..j-1: wait until P.V_{j-1} has landed, then scale this thread's half of the row
+            mbar_wait(&pv_done[0], (j - 1) & 1);
+            tcgen05_fence_after();
+            float o[32];
+#pragma unroll 1
+            for (int c0 = 0; c0 < DK / 2; c0 += 32) {
+              const uint32_t oa = lane_addr + (uint32_t)(A::O_COL + half * (DK / 2) + c0);
+              __syncwarp();
+              tmem_ld32(oa, o);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] *= alpha;
+              tmem_st32(oa, o);
+            }
+            tmem_st_wait();
+          }
+          l_row *= alpha;
+          if (bump) m_ref = tmax;
+        }
+        const float mb = m_ref * c_exp;
 #pragma unroll
         for (int i = 0; i < 64; ++i) {
-          const float e = (kv0 + i < len) ? fast_exp2(fmaf(v[i], p.scale_log2e, -mb)) : 0.f;
+          const float e = (kv0 + i < len) ? fast_exp2(fmaf(v[i], c_exp, -mb)) : 0.f;
           v[i] = e; l_row += e;
         }
         tmem_st32(ta, v); tmem_st32(ta + 32, v + 32);
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[g & 1]);
+        if (lane == 0) mbar_arrive(&p_full[j & 1]);
       }
+      named_bar_sync(1, 256);                                     // last exchange buffer is free again
       xchg[half * BQ + row] = l_row;
       named_bar_sync(1, 256);
       l_row += xchg[(half ^ 1) * BQ + row];
