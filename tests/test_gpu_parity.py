@@ -361,3 +361,25 @@ def test_sharded_synthesis_single_rank(models, weights):
         want = O.forward_path(weights, xs, il, is_inference=True)
     assert torch.equal(olens.cpu(), want[2].sum(1))
     close(mels, want[1], TOL["fp32"], "sharded mels")
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_cuda_graph_replay_matches_eager(models, prec):
+    """One captured CUDA graph per shape: replay with new inputs must equal the eager path bit for bit, and the
+    deferred length validation must still raise."""
+    m = models[prec]
+    a = make_batch(4, 30, 260, seed=91, ilens=[30, 22, 9, 30], olens=[260, 180, 77, 259])
+    b = make_batch(4, 30, 260, seed=92, ilens=[30, 30, 30, 12], olens=[260, 260, 255, 101])
+    A = [a[k].cuda() for k in ("xs", "ilens", "olens", "ds", "es", "ps")]
+    B_ = [b[k].cuda() for k in ("xs", "ilens", "olens", "ds", "es", "ps")]
+    g = m.graphed_forward(*A)
+    with torch.no_grad():
+        for inp in (B_, A, B_):
+            want = [t.clone() for t in m._forward(*inp, is_inference=False)]
+            got = g(*inp)
+            for w, o in zip(want, got):
+                assert torch.equal(w, o)
+    bad = [t.clone() for t in A]
+    bad[3][0, 0] += 5                                 # durations no longer sum to olens
+    with pytest.raises(RuntimeError, match="length mismatch"):
+        g(*bad)
