@@ -24,7 +24,7 @@
 // One persistent CTA per SM walks the 128 x BN output tiles (n fastest, so concurrently running
 // CTAs share weight tiles in L2).  Three pipelines:
 //   smem ring   : warp 0 (TMA producer, one lane)  <-> warp 1 (MMA issuer, one lane), full/empty mbarriers
-//   TMEM        : two accumulator buffers; warp 1 fills buffer i&1 while warps 2-5 drain the other
+//   TMEM        : 2 (BN > 128) or 4 accumulator buffers; warp 1 fills buffer i % NACC while the epilogue drains older ones
 //   output      : two epilogue groups (warps 2-5 and 6-9; thread == output row == TMEM lane) take alternate
 //                 32-column chunks: tcgen05.ld -> bias / ReLU / tanh / residual in registers -> four
 //                 256-bit global stores per thread (sector-complete, no shared-memory transpose, no
@@ -75,7 +75,8 @@ struct Cfg {
   static constexpr int STAGE_BYTES = (PRECISE ? 2 : 1) * (A_BYTES + B_BYTES);   // [A(hi)][A lo][B hi][B lo]
   static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
   static constexpr int ACC_STRIDE = pow2_at_least(BN);     // TMEM columns per accumulator buffer
-  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int NACC = 512 / ACC_STRIDE > 4 ? 4 : 512 / ACC_STRIDE;   // accumulator buffers in flight (2 for BN > 128, else 4)
+  static constexpr int TMEM_COLS = NACC * ACC_STRIDE;
   static constexpr int GROUPS = 2;       // epilogue warp groups (4 warps each), alternate 32-column chunks
   static constexpr int THREADS = 64 + GROUPS * 128 + (PRECISE ? 128 : 0);
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
@@ -104,9 +105,9 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* split_bar = empty_bar + C::STAGES;
-  uint64_t* acc_full = split_bar + C::STAGES;     // [2] MMA -> epilogue
-  uint64_t* acc_empty = acc_full + 2;             // [2] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* acc_full = split_bar + C::STAGES;     // [NACC] MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 4;             // [NACC] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kchunks = (p.K + BK - 1) / BK;
@@ -115,7 +116,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], 4); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4 * C::GROUPS); }
+    for (int i = 0; i < C::NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4 * C::GROUPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);   // whole warp: both accumulator buffers
@@ -171,8 +172,8 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     {  // ---- MMA issuer: all 32 lanes run the loop, one lane is elected inside each tcgen05 asm ----
       int n = 0, it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1);   // epilogue has drained this buffer (first two uses pass)
+        const int acc = it % C::NACC;
+        mbar_wait(&acc_empty[acc], ((it / C::NACC) & 1) ^ 1);   // epilogue has drained this buffer (first NACC uses pass)
         tcgen05_fence_after();
         const uint32_t d = tmem_base + (uint32_t)(acc * C::ACC_STRIDE);
         for (int s = 0; s < steps; ++s, ++n) {
@@ -212,7 +213,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       int n0, b, t0, packed;
       tile_coords(tile, n0, b, t0, packed);
-      const int acc = it & 1;
+      const int acc = it % C::NACC;
       int t = t0 + row;
       bool row_ok = t < p.L;                     // flat mode: L == total rows
       if (packed >= 0) {                         // packed tail tile: 16-row granule g of the tile -> utterance b + g / gn
@@ -225,7 +226,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       if (has_res && row_ok) {                   // residual rows -> L2 while the main loop of this tile runs
         for (int c0 = grp * 32; c0 < BN; c0 += 32 * C::GROUPS) prefetch_l2(resid + m * ldr + n0 + c0);
       }
-      mbar_wait(&acc_full[acc], (it >> 1) & 1);
+      mbar_wait(&acc_full[acc], (it / C::NACC) & 1);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + lane_off + (uint32_t)(acc * C::ACC_STRIDE);
       const bool to_vt = p.vt_out != nullptr && n0 >= p.vt_col0;   // tile-uniform (tile widths divide the V third)
@@ -404,6 +405,12 @@ int tap_gemm_tf32(const TapGemm& g, cudaStream_t st) {
   int rc = check_common(g, "tap_gemm_tf32");
   if (rc) return rc;
   if ((long)g.B * g.L == 0) return FS2_OK;
+  {
+    static int force = -1;   // FS2_GEMM_BN: tile-width override for experiments
+    if (force < 0) { const char* e = getenv("FS2_GEMM_BN"); force = e ? atoi(e) : 0; }
+    if (force == 128 && g.N % 128 == 0) return launch<128, false>(g, st);
+    if (force == 64 && g.N % 64 == 0) return launch<64, false>(g, st);
+  }
   if (g.N % 256 == 0) return launch<256, false>(g, st);
   if (g.N % 192 == 0) return launch<192, false>(g, st);
   if (g.N % 128 == 0) return launch<128, false>(g, st);
