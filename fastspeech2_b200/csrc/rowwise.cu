@@ -169,16 +169,18 @@ __device__ __forceinline__ void block_accumulate(float v, double* dst) {
 __global__ void loss_mel_kernel(const float* __restrict__ before, const float* __restrict__ after,
                                 const float* __restrict__ ys, int ld_ys_time, const int64_t* __restrict__ olens, int L,
                                 int odim, double* acc) {
-  // grid: (chunks over L*odim, B)
-  int b = blockIdx.y;
-  long valid = (long)olens[b] * odim;
+  // grid: (chunks, B).  The valid part of an utterance is one contiguous run of olens[b]*odim floats in all three
+  // tensors (odim % 4 == 0), so the kernel streams 16-byte vectors: HBM-bound, 3 x 4 bytes per valid element.
+  const int b = blockIdx.y;
+  const long nvec = (long)olens[b] * odim / 4;
+  const float4* pb = reinterpret_cast<const float4*>(before + (long)b * L * odim);
+  const float4* pa = reinterpret_cast<const float4*>(after + (long)b * L * odim);
+  const float4* py = reinterpret_cast<const float4*>(ys + (long)b * ld_ys_time * odim);
   float s0 = 0.f, s1 = 0.f;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < valid; i += (long)gridDim.x * blockDim.x) {
-    long t = i / odim; int c = (int)(i - t * odim);
-    float y = ys[((long)b * ld_ys_time + t) * odim + c];
-    long o = (long)b * L * odim + i;
-    s0 += fabsf(before[o] - y);
-    s1 += fabsf(after[o] - y);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
+    const float4 y = __ldg(py + i), x0 = __ldg(pb + i), x1 = __ldg(pa + i);
+    s0 += (fabsf(x0.x - y.x) + fabsf(x0.y - y.y)) + (fabsf(x0.z - y.z) + fabsf(x0.w - y.w));
+    s1 += (fabsf(x1.x - y.x) + fabsf(x1.y - y.y)) + (fabsf(x1.z - y.z) + fabsf(x1.w - y.w));
   }
   block_accumulate(s0, acc + 0);
   block_accumulate(s1, acc + 1);
@@ -314,9 +316,10 @@ int masked_losses(const float* before, const float* after, const float* ys, int 
                   const int64_t* ilens, const int64_t* olens, int B, int T, int L, int odim, float* out7, void* scratch,
                   cudaStream_t st) {
   double* acc = reinterpret_cast<double*>(scratch);
+  FS2_REQUIRE(odim % 4 == 0 && (reinterpret_cast<uintptr_t>(ys) & 15) == 0, "masked_losses: odim must be a multiple of 4 and ys 16-byte aligned");
   FS2_CUDA_CHECK(cudaMemsetAsync(acc, 0, 8 * sizeof(double), st));
   if (B > 0) {
-    dim3 g1(grid_for((long)L * odim, 256, 64), B), g2(grid_for(L > T ? L : T, 256, 16), B);
+    dim3 g1(grid_for((long)L * odim / 4, 256, 32), B), g2(grid_for(L > T ? L : T, 256, 16), B);
     loss_mel_kernel<<<g1, 256, 0, st>>>(before, after, ys, ld_ys_time, olens, L, odim, acc);
     FS2_LAUNCH_CHECK();
     loss_seq_kernel<<<g2, 256, 0, st>>>(d_out, ds, ds_dtype, e_out, p_out, es, ps, ilens, olens, T, L, acc);
