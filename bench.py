@@ -360,6 +360,21 @@ def run_b200(args):
         prof = {lib.fs2_profile_label(i).decode(): {"ms": ms[i], "launches": cnt[i], "flop": fl[i], "bytes": by[i]}
                 for i in range(n) if cnt[i]}
 
+    # secondary figure: the literal inference mode (predicted durations, unmasked decoder, one host read of Lmax)
+    inf = None
+    if rank == 0 and args.gpus == 1:
+        with torch.no_grad():
+            out = model._forward(devin["xs"], devin["ilens"], is_inference=True, _one_hot=False)
+            inf_frames = int(out[2].sum())
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); e0.record()
+            for _ in range(5):
+                model._forward(devin["xs"], devin["ilens"], is_inference=True, _one_hot=False)
+            e1.record(); torch.cuda.synchronize()
+        inf = {"value": inf_frames / (e0.elapsed_time(e1) / 5 * 1e-3), "unit": "frames/s", "ms_per_step": e0.elapsed_time(e1) / 5,
+               "frames_per_batch": inf_frames, "Lmax": int(out[1].shape[1]),
+               "note": "is_inference=True: durations predicted on the device, decoder unmasked over the [B,Lmax] rectangle, eager launches"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -407,6 +422,8 @@ def run_b200(args):
         "model_tflops": value * mf / 1e6,
         "mflop_per_frame": mf,
     }
+    if inf:
+        line["inference_mode"] = inf
     if roof:
         line["roofline"] = roof
     if cpu_fps:

@@ -383,3 +383,28 @@ def test_cuda_graph_replay_matches_eager(models, prec):
     bad[3][0, 0] += 5                                 # durations no longer sum to olens
     with pytest.raises(RuntimeError, match="length mismatch"):
         g(*bad)
+
+
+def test_random_shapes_tf32_vs_fp32_paths(models):
+    """Shape stress: 24 random (B, T, L) with ragged lengths through both kernel families (the exact-fp32 CUDA-core
+    path is already pinned to the oracle; the tensor-core path must agree with it within the tf32 tolerance).  Catches
+    tile-boundary bugs: packed tail tiles, partial attention tiles, single-tile cases, odd L (transposed-V row pitch)."""
+    g = torch.Generator().manual_seed(2024)
+    for case in range(24):
+        B = int(torch.randint(1, 7, (1,), generator=g))
+        T = int(torch.randint(1, 90, (1,), generator=g))
+        ilens = [T] + [int(torch.randint(1, T + 1, (1,), generator=g)) for _ in range(B - 1)]
+        olens = [il * int(torch.randint(1, 12, (1,), generator=g)) + int(torch.randint(0, 5, (1,), generator=g)) for il in ilens]
+        L = max(olens)
+        olens[olens.index(L)] = L
+        bt = make_batch(B, T, L, seed=500 + case, ilens=ilens, olens=olens)
+        args = [bt[k].cuda() for k in ("xs", "ilens", "olens", "ds", "es", "ps")]
+        with torch.no_grad():
+            ref = models["fp32"]._forward(*args, is_inference=False)
+            got = models["tf32"]._forward(*args, is_inference=False)
+        valid = (torch.arange(L)[None] < bt["olens"][:, None]).cuda()
+        for name, r, o in (("before", ref[0], got[0]), ("after", ref[1], got[1])):
+            err = (r - o).abs()[valid]
+            assert torch.isfinite(o).all(), (case, name)
+            assert float(err.max()) <= 1e-2 and float(err.mean()) <= 1e-3, (case, B, T, L, name, float(err.max()), float(err.mean()))
+        assert float((ref[2] - got[2]).abs().max()) <= 2e-4, (case, "d_outs")
