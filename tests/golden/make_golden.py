@@ -153,5 +153,25 @@ def main():
         vals_p=vals_p, ids_p=model.pitch_predictor.to_one_hot(vals_p).argmax(-1), e_bins=eb, p_bins=pb)
 
 
+def collate_fixture():
+    """Reference collate_tts (dataset/dataloader.py:96-118) on seeded synthetic items."""
+    from dataset.dataloader import collate_tts
+    g = np.random.RandomState(15)
+    items = []
+    for i, (T, L) in enumerate([(7, 31), (12, 50), (3, 9), (12, 44)]):
+        d = g.randint(1, 6, size=T); d[-1] += L - d.sum() if d.sum() <= L else 0
+        items.append((g.randint(1, 68, size=T), g.randn(L, 80).astype(np.float32), f"utt{i}", L, d.astype(np.int64),
+                      g.rand(L).astype(np.float32) * 100, g.rand(L).astype(np.float32) * 500))
+    out = collate_tts(items)
+    npz("collate", **{f"x{i}": it[0] for i, it in enumerate(items)}, **{f"mel{i}": it[1] for i, it in enumerate(items)},
+        **{f"d{i}": it[4] for i, it in enumerate(items)}, **{f"e{i}": it[5] for i, it in enumerate(items)},
+        **{f"p{i}": it[6] for i, it in enumerate(items)},
+        inputs=out[0], ilens=out[1], mels=out[2], labels=out[3], olens=out[4], durations=out[6], energys=out[7], pitches=out[8])
+
+
 if __name__ == "__main__":
-    main()
+    if "--collate-only" in sys.argv:
+        collate_fixture()
+    else:
+        main()
+        collate_fixture()

@@ -1,0 +1,53 @@
+"""Input side: collate parity with the reference's collate_tts (golden fixture), pinned collator,
+bucket sampler.  CPU only."""
+import numpy as np
+import torch
+
+from fastspeech2_b200.data import BucketBatchSampler, PinnedCollator, collate_tts
+
+T_ = torch.from_numpy
+
+
+def items_from(g):
+    return [(g[f"x{i}"], g[f"mel{i}"], f"utt{i}", g[f"mel{i}"].shape[0], g[f"d{i}"], g[f"e{i}"], g[f"p{i}"]) for i in range(4)]
+
+
+def check(out, g):
+    for k, i in (("inputs", 0), ("ilens", 1), ("mels", 2), ("labels", 3), ("olens", 4), ("durations", 6), ("energys", 7), ("pitches", 8)):
+        assert out[i].dtype == T_(g[k]).dtype and torch.equal(out[i], T_(g[k])), k
+    assert out[5] == ["utt0", "utt1", "utt2", "utt3"]
+
+
+def test_collate_matches_reference(golden):
+    g = golden("collate")
+    check(collate_tts(items_from(g)), g)
+
+
+def test_pinned_collator_matches_and_reuses_buffers(golden):
+    g = golden("collate")
+    pc = PinnedCollator(max_batch=8, max_T=20, max_L=64, pin=False)
+    out = pc(items_from(g))
+    check(out, g)
+    ptr = out[2].data_ptr()
+    out2 = pc(items_from(g)[:2])                     # smaller batch: same storage, stale tail must be zero
+    assert out2[2].data_ptr() == ptr and out2[2].shape == (2, 50, 80)
+    ref2 = collate_tts(items_from(g)[:2])
+    for i in (0, 1, 2, 3, 4, 6, 7, 8):
+        assert torch.equal(out2[i], ref2[i])
+    moved = PinnedCollator.to_device(out2, "cpu")
+    assert moved[5] == ["utt0", "utt1"] and torch.equal(moved[0], ref2[0])
+
+
+def test_bucket_sampler_partitions_and_cuts_padding():
+    rng = np.random.RandomState(0)
+    lengths = (rng.gamma(4.0, 140.0, size=2000) + 100).astype(int)    # LJSpeech-like mel lengths
+    s = BucketBatchSampler(lengths, batch_size=16, seed=3)
+    batches = list(s)
+    flat = sorted(i for b in batches for i in b)
+    assert flat == list(range(2000)) and len(batches) == len(s)
+    assert list(BucketBatchSampler(lengths, 16, seed=3)) == batches               # deterministic per seed/epoch
+    s.set_epoch(1)
+    assert list(s) != batches
+    rand_waste = 1.0 - float(np.mean(lengths)) / float(np.mean([lengths[np.array(b)].max() for b in
+                        np.array_split(rng.permutation(2000), 125)]))
+    assert s.padding_waste() < 0.1 < rand_waste
