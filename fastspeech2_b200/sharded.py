@@ -73,47 +73,3 @@ def synthesize_sharded(model, xs: torch.Tensor, ilens: torch.Tensor, group: Opti
     if world == 1:
         return after, olens
     return gather_mels(after, olens, group)
-
-
-class OverlappedMelGather:
-    """The path's one collective, issued on its own stream so that it overlaps the next batch's compute.
-
-    `submit(mel)` snapshots the rank's `[B, L, odim]` mel shard (device-to-device copy on the compute stream, so the
-    producer may overwrite `mel` right away -- e.g. the static output of a replayed CUDA graph) and enqueues the
-    NCCL all-gather on a side stream behind it; `result()` makes the compute stream wait for the last gather and
-    returns the `[world*B, L, odim]` tensor.  Two snapshot / result slots alternate, so one gather can be in
-    flight while the next batch is being synthesised."""
-
-    def __init__(self, shape, device, group: Optional[dist.ProcessGroup] = None, dtype=torch.float32):
-        self.group = group
-        self.world = dist.get_world_size(group)
-        B, L, D = shape
-        self.snap = [torch.empty((B, L, D), dtype=dtype, device=device) for _ in range(2)]
-        self.out = [torch.empty((self.world * B, L, D), dtype=dtype, device=device) for _ in range(2)]
-        self.stream = torch.cuda.Stream(device=device)
-        self.done = [torch.cuda.Event() for _ in range(2)]
-        self.i = 0
-        self.pending = [False, False]
-
-    def submit(self, mel: torch.Tensor) -> None:
-        k = self.i & 1
-        self.i += 1
-        cur = torch.cuda.current_stream(mel.device)
-        if self.pending[k]:
-            cur.wait_event(self.done[k])              # slot k's previous gather has read its snapshot
-        self.snap[k].copy_(mel, non_blocking=True)
-        self.stream.wait_stream(cur)
-        with torch.cuda.stream(self.stream):
-            dist.all_gather_into_tensor(self.out[k], self.snap[k], group=self.group)
-            self.done[k].record(self.stream)
-        self.pending[k] = True
-
-    def result(self) -> torch.Tensor:
-        k = (self.i - 1) & 1
-        torch.cuda.current_stream(self.out[k].device).wait_event(self.done[k])
-        return self.out[k]
-
-    def drain(self) -> None:
-        for k in range(2):
-            if self.pending[k]:
-                torch.cuda.current_stream(self.out[k].device).wait_event(self.done[k])

@@ -52,10 +52,3 @@ def test_gather_mels_world2_ragged():
 
 def test_gather_mels_world2_equal_single_collective():
     mp.spawn(_worker, args=(2, _free_port(), True), nprocs=2, join=True)
-
-
-def test_overlapped_gather_needs_cuda_but_partition_logic_is_shared():
-    """OverlappedMelGather uses CUDA streams/events (GPU only, exercised by bench.py --gpus N); its slot arithmetic is
-    trivial, the partition + ordering logic it relies on is `gather_mels` / `shard_bounds`, covered above."""
-    from fastspeech2_b200.sharded import OverlappedMelGather
-    assert callable(OverlappedMelGather.submit) and callable(OverlappedMelGather.result) and callable(OverlappedMelGather.drain)
