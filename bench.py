@@ -387,7 +387,7 @@ def run_b200(args):
     h2d = sum(host[k].numel() * host[k].element_size() for k in keys)
     d2h = mel_host.numel() * 4
     mf = mflop_per_frame(T, L)
-    tensor_peak = (tf_sus / 2.0) if args.precision == "tf32" else 2 * 148 * 128 * 1.965e9 / 1e12
+    tensor_peak = (tf_sus / 2.0) if args.precision == "tf32" else (tf_sus / 6.0) if args.precision == "3xtf32" else 2 * 148 * 128 * 1.965e9 / 1e12
     roof = None
     if prof:
         tot = sum(v["ms"] for v in prof.values())
@@ -441,7 +441,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default=os.environ.get("FS2_PRECISION", "tf32"), choices=["fp32", "tf32"])
+    ap.add_argument("--precision", default=os.environ.get("FS2_PRECISION", "tf32"), choices=["fp32", "tf32", "3xtf32"])
     ap.add_argument("--cpu-sample-batch", type=int, default=8)
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (default), 0: eager launches")
     args = ap.parse_args()

@@ -322,11 +322,13 @@ struct Packer {
     }
     // decoder (fastspeech.py:119-136; input layer core/encoder.py:118-125)
     if ((rc = dense("decoder.embed.0.weight", "decoder.embed.0.bias", c.ddim, c.adim, 1, &h->dec_in))) return rc;
+    if ((rc = split(&h->dec_in))) return rc;                                   // hi/lo copies serve FS2_MATH_3XTF32
     if ((rc = norm("decoder.embed.1.", c.ddim, 1e-5f, &h->dec_in_ln))) return rc;
     if ((rc = copy("decoder.embed.4.alpha", 1, &h->dec_alpha))) return rc;
     if ((rc = copy("decoder.embed.4.pe", (int64_t)c.pe_len * c.ddim, &h->dec_pe))) return rc;
-    if ((rc = blocks("decoder", c.dlayers, c.ddim, c.dunits, c.ffn_kernel, false, &h->dec))) return rc;
+    if ((rc = blocks("decoder", c.dlayers, c.ddim, c.dunits, c.ffn_kernel, true, &h->dec))) return rc;
     if ((rc = dense("feat_out.weight", "feat_out.bias", c.odim, c.ddim, 1, &h->feat_out))) return rc;
+    if ((rc = split(&h->feat_out))) return rc;
     // Postnet: Conv1d(no bias) + BatchNorm1d(eval) folded into weight scale + bias (modules.py:283-348)
     h->postnet.assign(c.postnet_layers, Dense());
     for (int i = 0; i < c.postnet_layers; ++i) {
@@ -339,6 +341,7 @@ struct Packer {
       if (!counting && (rc = fold_batchnorm((const float*)g->data, (const float*)b->data, (const float*)mu->data,
                                             (const float*)var->data, 1e-5f, cout, scale, shift, st))) return rc;
       if ((rc = dense(p + "0.weight", "", cout, cin, c.postnet_filts, &h->postnet[i], scale, shift))) return rc;
+      if ((rc = split(&h->postnet[i]))) return rc;
     }
     return FS2_OK;
   }
@@ -386,7 +389,7 @@ int fs2_create(fs2_handle** out, const fs2_config* cfg, int device) {
   FS2_REQUIRE((cfg->ffn_kernel & 1) && (cfg->pred_kernel & 1) && (cfg->postnet_filts & 1), "fs2_create: kernel sizes must be odd");
   FS2_REQUIRE(cfg->postnet_layers >= 1, "fs2_create: postnet_layers == 0 is not supported");
   FS2_REQUIRE(cfg->n_bins % 4 == 0, "fs2_create: n_bins must be a multiple of 4");
-  FS2_REQUIRE(cfg->math_mode == FS2_MATH_FP32 || cfg->math_mode == FS2_MATH_TF32, "fs2_create: bad math_mode");
+  FS2_REQUIRE(cfg->math_mode >= FS2_MATH_FP32 && cfg->math_mode <= FS2_MATH_3XTF32, "fs2_create: bad math_mode");
   FS2_CUDA_CHECK(cudaSetDevice(device));
   fs2_handle* h = new fs2_handle();
   h->cfg = *cfg;
@@ -424,7 +427,7 @@ int fs2_profile_read(fs2_handle* h, double* ms, int64_t* launches, double* flop,
 
 int fs2_set_math_mode(fs2_handle* h, int math_mode) {
   FS2_REQUIRE(h, "fs2_set_math_mode: null handle");
-  FS2_REQUIRE(math_mode == FS2_MATH_FP32 || math_mode == FS2_MATH_TF32, "fs2_set_math_mode: bad mode %d", math_mode);
+  FS2_REQUIRE(math_mode >= FS2_MATH_FP32 && math_mode <= FS2_MATH_3XTF32, "fs2_set_math_mode: bad mode %d", math_mode);
   h->cfg.math_mode = math_mode;
   return FS2_OK;
 }
@@ -481,7 +484,7 @@ int fs2_encode(fs2_handle* h, const int64_t* xs, const int64_t* ilens, int B, in
   int rc;
   // the encoder's output feeds round() in the duration predictor: exact fp32 FMA in FS2_MATH_FP32,
   // error-compensated 3xTF32 on the tensor cores in FS2_MATH_TF32 (never plain tf32)
-  const int precise = c.math_mode == FS2_MATH_TF32 ? MATH_3XTF32 : FS2_MATH_FP32;
+  const int precise = c.math_mode == FS2_MATH_FP32 ? FS2_MATH_FP32 : MATH_3XTF32;
   { ProfScope prof_scope(P_EMBED, 0, 8.0 * B * Tmax * c.adim, st);
     if ((rc = embed_posenc(xs, h->emb, c.idim, h->enc_pe, h->enc_alpha, B, Tmax, c.adim, p.x, st))) return rc; }
   float* enc_out = nullptr;
@@ -519,7 +522,7 @@ int fs2_decode(fs2_handle* h, const float* hm, const int64_t* olens, const float
   DecodePlan p = plan_decode(c, b, rows, B, L);
   if (!b.ok()) { set_error("fs2_decode: workspace too small (%zu < %zu)", ws_bytes, b.off); return FS2_ERR_WORKSPACE; }
   const int mode = c.math_mode;
-  const int precise = mode == FS2_MATH_TF32 ? MATH_3XTF32 : FS2_MATH_FP32;
+  const int precise = mode == FS2_MATH_FP32 ? FS2_MATH_FP32 : MATH_3XTF32;
   int rc;
   // energy / pitch predictors on the length-regulated states (fastspeech.py:195-196,214-216); fp32
   if ((rc = run_predictor(h->energy, hm, c.adim, B, L, p.t1, p.t2, olens, e_out, nullptr, precise, st))) return rc;

@@ -63,7 +63,7 @@ bool gemm_ln_tf32_supported(const TapGemm& g);         // row-complete GEMM + re
 int gemm_ln_tf32(const TapGemm& g, cudaStream_t st);
 int tap_gemm_3xtf32(const TapGemm& g, cudaStream_t st); // same kernel, error-compensated split operands
 int split_tf32(const float* src, float* hi, float* lo, long n, cudaStream_t st);
-constexpr int MATH_3XTF32 = 2;                          // internal: FS2_MATH_TF32's choice for encoder + predictors
+constexpr int MATH_3XTF32 = FS2_MATH_3XTF32;            // also what FS2_MATH_TF32 uses for the encoder + predictors
 
 // Row LayerNorm with the fusions the path needs.
 struct RowNorm {

@@ -49,9 +49,12 @@ extern "C" {
  *     decoder side (decoder embed, decoder FFT blocks incl. attention, mel linear, Postnet) in
  *     plain kind::tf32; encoder GEMMs and the three predictors in 3xTF32 (hi/lo operand split,
  *     fp32-class accuracy) because their outputs feed round() / bucketize().
- * Normalisation, softmax statistics, gathers and every integer kernel are fp32 / exact in both. */
+ *   FS2_MATH_3XTF32: every dense contraction in 3xTF32 on the tensor cores (decoder side too); attention cores on
+ *     the exact-fp32 kernel.  ~1e-4-class results at about a third of the fp32 mode's run time.
+ * Normalisation, softmax statistics, gathers and every integer kernel are fp32 / exact in all modes. */
 #define FS2_MATH_FP32 0
 #define FS2_MATH_TF32 1
+#define FS2_MATH_3XTF32 2
 
 typedef struct fs2_handle fs2_handle;
 

@@ -5,6 +5,7 @@ Tolerances (stated, per SURVEY.md section 7 "fp32 tolerance vs tensor cores"):
   FS2_MATH_FP32 : max-abs <= 1e-4 on mels (output rms ~0.6; the oracle's own fp32 noise floor
                   vs fp64 is 2.4e-6, long K=3456 fp32 reductions in a different order add ~1e-5)
   FS2_MATH_TF32 : max-abs <= 1e-2, mean-abs <= 1e-3 on mels (tf32 operands: 10-bit mantissa)
+  FS2_MATH_3XTF32: max-abs <= 1e-3, mean-abs <= 1e-4 (operand rounding compensated; tensor-core accumulation rounds to zero)
   integer outputs (durations, bucket ids, LengthRegulator rows): bit-exact in both modes.
 """
 import numpy as np
@@ -18,8 +19,8 @@ from oracle import fs2_oracle as O
 
 pytestmark = pytest.mark.gpu
 T_ = torch.from_numpy
-TOL = {"fp32": dict(max=1e-4, mean=1e-5), "tf32": dict(max=1e-2, mean=1e-3)}
-PRECISIONS = ["fp32", "tf32"]
+TOL = {"fp32": dict(max=1e-4, mean=1e-5), "tf32": dict(max=1e-2, mean=1e-3), "3xtf32": dict(max=1e-3, mean=1e-4)}
+PRECISIONS = ["fp32", "tf32", "3xtf32"]
 
 
 def close(got, want, tol, what=""):
@@ -89,7 +90,7 @@ def test_golden_forward_loss(models, golden, prec):
     import json, os
     from conftest import GOLDEN
     assert [list(r.keys())[0] for r in report] == json.load(open(os.path.join(GOLDEN, "report_keys.json")))
-    rel = 1e-4 if prec == "fp32" else 2e-3
+    rel = {"fp32": 1e-4, "tf32": 2e-3, "3xtf32": 3e-4}[prec]
     got = np.array([list(r.values())[0] for r in report])
     assert np.all(np.abs(got - gl["report"]) <= rel * np.maximum(1.0, np.abs(gl["report"]))), (got, gl["report"])
     assert abs(float(loss) - float(gl["loss"])) <= rel * max(1.0, abs(float(gl["loss"])))
@@ -104,7 +105,7 @@ def test_reference_unit_test_twin(models, golden, prec):
     y = torch.ones(2, 100, 80).cuda(); dur = torch.ones(2, 100).cuda(); e = torch.ones(2, 100).cuda(); p = torch.ones(2, 100).cuda()
     with torch.no_grad():
         loss, report = models[prec](x, il, y, il.clone(), dur, e, p)
-    rel = 1e-4 if prec == "fp32" else 2e-3
+    rel = {"fp32": 1e-4, "tf32": 2e-3, "3xtf32": 3e-4}[prec]
     got = np.array([list(r.values())[0] for r in report])
     assert np.all(np.abs(got - gl["report"]) <= rel * np.maximum(1.0, np.abs(gl["report"]))), (got, gl["report"])
 
@@ -209,7 +210,7 @@ def _tap_gemm(mode, x, w, bias, act, resid):
     return out
 
 
-@pytest.mark.parametrize("prec", PRECISIONS)
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
 @pytest.mark.parametrize("shape", [(3, 70, 256, 1024, 9, 1), (2, 333, 384, 384, 1, 0), (5, 41, 80, 256, 5, 2),
                                    (2, 130, 256, 80, 5, 0), (1, 7, 1024, 384, 1, 0), (4, 100, 256, 256, 3, 1)])
 def test_tap_gemm_vs_torch(prec, shape):
@@ -248,7 +249,7 @@ def test_tap_gemm_3xtf32_is_fp32_class(shape):
     close(got3, y, dict(max=5e-4, mean=5e-5), str(shape))
 
 
-@pytest.mark.parametrize("prec", PRECISIONS)
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
 @pytest.mark.parametrize("C,L,masked", [(256, 100, True), (384, 333, True), (384, 800, False), (256, 37, False)])
 def test_attention_vs_torch(prec, C, L, masked):
     B, H = 3, 2
