@@ -375,6 +375,23 @@ def run_b200(args):
                "frames_per_batch": inf_frames, "Lmax": int(out[1].shape[1]),
                "note": "is_inference=True: durations predicted on the device, decoder unmasked over the [B,Lmax] rectangle, eager launches"}
 
+    # serving latency of one ~50-phoneme utterance through model.inference (BASELINE config 1 shape; eager launches,
+    # one host read of the predicted length)
+    lat = None
+    if rank == 0 and args.gpus == 1:
+        x1 = make_batch(1, 50, 400, seed=7)["xs"][0].to(dev)
+        with torch.no_grad():
+            for _ in range(3):
+                mel1 = model.inference(x1)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(20):
+                mel1 = model.inference(x1)
+            torch.cuda.synchronize()
+        lat_ms = (time.perf_counter() - t0) / 20 * 1e3
+        lat = {"ms": lat_ms, "frames": int(mel1.shape[0]), "rtf": (lat_ms * 1e-3) / (mel1.shape[0] * HOP / SR),
+               "note": "model.inference(x) for one 50-phoneme utterance, wall clock incl. the host read of Lmax"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -424,6 +441,8 @@ def run_b200(args):
     }
     if inf:
         line["inference_mode"] = inf
+    if lat:
+        line["single_utterance_latency"] = lat
     if roof:
         line["roofline"] = roof
     if cpu_fps:
