@@ -40,32 +40,8 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-// smem -> global tensor store (bulk async group); OOB parts of the box are clipped by the TMA unit
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// Cooperative store of a [128 x 32] fp32 box that 128 threads staged row-per-thread with the 128-byte swizzle
-// (16-byte chunk index XOR row%8): lanes 8i..8i+7 write one full 128-byte row segment, a warp writes 4 rows per
-// instruction -> full-line coalesced global stores without going through the TMA queue (which the operand loads
-// keep busy: a TMA store per chunk cost ~2 us of queueing, profiles/README.md).
-__device__ __forceinline__ void store_box_coalesced(const uint8_t* stage, float* out, long ldo, int tid, int rows_valid, int cols_valid) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int idx = tid + 128 * i, r = idx >> 3, ch = idx & 7;
-    if (r < rows_valid && ch * 4 < cols_valid) {
-      const float4 v = *reinterpret_cast<const float4*>(stage + r * 128 + ((ch ^ (r & 7)) << 4));
-      *reinterpret_cast<float4*>(out + (long)r * ldo + ch * 4) = v;
-    }
-  }
-}
 // 256-bit global store (STG.E.256): one full 32-byte sector per thread, so row-per-thread epilogues write
 // sector-complete data without a shared-memory transpose
 // L1::no_allocate: the epilogue-only microbenchmark writes 4.8 TB/s with it vs 3.9 TB/s without (.cs: no change)
