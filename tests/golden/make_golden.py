@@ -38,6 +38,8 @@ from fastspeech import FeedForwardTransformer  # noqa: E402  (the reference)
 from core.duration_modeling.length_regulator import LengthRegulator  # noqa: E402
 from utils.hparams import HParam  # noqa: E402
 from fastspeech2_b200.weights import ModelDims, synthetic_state_dict  # noqa: E402
+sys.path.insert(0, os.path.dirname(HERE))
+from _synth import seeded_energy_pitch  # noqa: E402  (tests/_synth.py, shared with the tests)
 
 WEIGHT_SEED = 7
 torch.set_num_threads(1)  # deterministic reduction order for the fixtures
@@ -169,9 +171,50 @@ def collate_fixture():
         inputs=out[0], ilens=out[1], mels=out[2], labels=out[3], olens=out[4], durations=out[6], energys=out[7], pitches=out[8])
 
 
+def filelist_twin():
+    """SURVEY 8d "ragged twin" of c2: the first 64 rows of the reference's filelists/train_filelist.txt (real phoneme
+    ids through the reference's own phonemes_to_sequence, real durations, dataset/dataloader.py:47-64), teacher-forced
+    through the live reference.  The full outputs are ~40 MB, so the fixture keeps every d_outs, the mels of the
+    shortest and the longest utterance, e/p predictions of eight utterances, and per-utterance means of the rest."""
+    from dataset.texts import phonemes_to_sequence
+    with open(os.path.join(REF, "filelists", "train_filelist.txt")) as f:
+        rows = [line.strip().split("|") for line in f][:64]
+    ids = [phonemes_to_sequence(r[3].split()) for r in rows]
+    durs = [[int(v) for v in r[2].split()][:len(i)] for r, i in zip(rows, ids)]
+    B, T = len(ids), max(len(i) for i in ids)
+    xs = torch.zeros(B, T, dtype=torch.int64)
+    ds = torch.zeros(B, T, dtype=torch.int64)
+    for b, (i, d) in enumerate(zip(ids, durs)):
+        xs[b, :len(i)] = torch.tensor(i)
+        ds[b, :len(d)] = torch.tensor(d)
+    ilens = torch.tensor([len(i) for i in ids])
+    olens = ds.sum(1)
+    L = int(olens.max())
+    es, ps = seeded_energy_pitch(16, olens, L)
+    model, _ = build_reference()
+    torch.set_num_threads(os.cpu_count())
+    with torch.no_grad():
+        b_, a_, d_, e_, p_ = model._forward(xs, ilens, olens, ds.clone(), es, ps, is_inference=False)
+    torch.set_num_threads(1)
+    lo, hi = int(olens.argmin()), int(olens.argmax())
+    keep = sorted({lo, hi, 0, 9, 18, 27, 45, 63})
+    valid = (torch.arange(L)[None, :] < olens[:, None]).float()
+    npz("filelist64", xs=xs, ilens=ilens, olens=olens, ds=ds, es_seed=16,
+        d_outs=d_, mel_rows=np.array([lo, hi]), after_lo=a_[lo, :olens[lo]], after_hi=a_[hi, :olens[hi]],
+        before_lo=b_[lo, :olens[lo]],
+        ep_rows=np.array(keep), e_sel=e_[keep], p_sel=p_[keep],
+        after_mean=(a_.double() * valid[..., None]).sum((1, 2)) / (olens.double() * 80),
+        after_absmean=(a_.double().abs() * valid[..., None]).sum((1, 2)) / (olens.double() * 80),
+        before_mean=(b_.double() * valid[..., None]).sum((1, 2)) / (olens.double() * 80),
+        e_mean=(e_.double() * valid).sum(1) / olens.double(), p_mean=(p_.double() * valid).sum(1) / olens.double())
+
+
 if __name__ == "__main__":
     if "--collate-only" in sys.argv:
         collate_fixture()
+    elif "--filelist-only" in sys.argv:
+        filelist_twin()
     else:
         main()
         collate_fixture()
+        filelist_twin()

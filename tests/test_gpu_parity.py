@@ -52,11 +52,42 @@ def test_golden_teacher_forced(models, golden, prec):
     xs, il, ol, ds, es, ps = cuda(g, "xs", "ilens", "olens", "ds", "es", "ps")
     with torch.no_grad():
         b, a, d, e, p = models[prec]._forward(xs, il, ol, ds, es, ps, is_inference=False)
-    close(d, g["d_outs"], TOL["fp32"], "d_outs")       # encoder + predictors are fp32 in both modes
+    close(d, g["d_outs"], TOL["fp32"], "d_outs")       # encoder + predictors: fp32 or 3xTF32 in every mode
     close(e, g["e_outs"], dict(max=2e-4, mean=2e-5), "e_outs")
     close(p, g["p_outs"], dict(max=2e-4, mean=2e-5), "p_outs")
     close(b, g["before"], TOL[prec], "before")
     close(a, g["after"], TOL[prec], "after")
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_golden_filelist_twin(models, golden, prec):
+    """SURVEY 8d ragged twin of c2: first 64 rows of the reference's train filelist (real phonemes and durations,
+    T 31..116, L 222..856) through the live reference; the fixture keeps all d_outs, two mels, eight e/p rows and
+    per-utterance means of everything else (tests/golden/make_golden.py::filelist_twin)."""
+    from _synth import seeded_energy_pitch
+    g = golden("filelist64")
+    olens = T_(g["olens"])
+    L = int(olens.max())
+    es, ps = seeded_energy_pitch(int(g["es_seed"]), olens, L)
+    xs, il, ol, ds = cuda(g, "xs", "ilens", "olens", "ds")
+    with torch.no_grad():
+        b, a, d, e, p = models[prec]._forward(xs, il, ol, ds, es.cuda(), ps.cuda(), is_inference=False)
+    close(d, g["d_outs"], TOL["fp32"], "d_outs")
+    rows = T_(g["ep_rows"]).cuda()
+    close(e[rows], g["e_sel"], dict(max=2e-4, mean=2e-5), "e_outs")
+    close(p[rows], g["p_sel"], dict(max=2e-4, mean=2e-5), "p_outs")
+    lo, hi = (int(v) for v in g["mel_rows"])
+    close(a[lo, :olens[lo]], g["after_lo"], TOL[prec], "after[shortest]")
+    close(a[hi, :olens[hi]], g["after_hi"], TOL[prec], "after[longest]")
+    close(b[lo, :olens[lo]], g["before_lo"], TOL[prec], "before[shortest]")
+    valid = (torch.arange(L)[None, :] < olens[:, None]).double().cuda()
+    n = olens.double().cuda()
+    mean_tol = dict(max=TOL[prec]["mean"], mean=TOL[prec]["mean"])          # a mean over >= 222*80 values
+    close((a.double() * valid[..., None]).sum((1, 2)) / (n * 80), g["after_mean"], mean_tol, "after means")
+    close((a.double().abs() * valid[..., None]).sum((1, 2)) / (n * 80), g["after_absmean"], mean_tol, "after abs means")
+    close((b.double() * valid[..., None]).sum((1, 2)) / (n * 80), g["before_mean"], mean_tol, "before means")
+    close((e.double() * valid).sum(1) / n, g["e_mean"], dict(max=2e-5, mean=2e-5), "e means")
+    close((p.double() * valid).sum(1) / n, g["p_mean"], dict(max=2e-5, mean=2e-5), "p means")
 
 
 @pytest.mark.parametrize("prec", PRECISIONS)

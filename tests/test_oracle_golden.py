@@ -57,6 +57,27 @@ def test_unit_test_shapes(golden, weights):
     close([list(r.values())[0] for r in report], gl["report"], 1e-5)
 
 
+def test_filelist_twin(golden, weights):
+    """c2's ragged twin: 64 real filelist rows through the live reference, subset fixture."""
+    from _synth import seeded_energy_pitch
+    g = golden("filelist64")
+    olens = T(g["olens"])
+    L = int(olens.max())
+    es, ps = seeded_energy_pitch(int(g["es_seed"]), olens, L)
+    torch.set_num_threads(os.cpu_count())            # ~2.5 TFLOP of fp32; the summation order differs -> 1e-5, not 0
+    with torch.no_grad():
+        b, a, d, e, p = O.forward_path(weights, T(g["xs"]), T(g["ilens"]), olens, T(g["ds"]).clone(), es, ps, False)
+    torch.set_num_threads(1)
+    lo, hi = (int(v) for v in g["mel_rows"])
+    close(d, g["d_outs"], 1e-5)
+    close(e[T(g["ep_rows"])], g["e_sel"], 1e-5); close(p[T(g["ep_rows"])], g["p_sel"], 1e-5)
+    close(a[lo, :olens[lo]], g["after_lo"], 1e-5); close(a[hi, :olens[hi]], g["after_hi"], 1e-5)
+    close(b[lo, :olens[lo]], g["before_lo"], 1e-5)
+    valid = (torch.arange(L)[None, :] < olens[:, None]).double()
+    close((a.double() * valid[..., None]).sum((1, 2)) / (olens.double() * 80), g["after_mean"], 1e-6)
+    close((b.double() * valid[..., None]).sum((1, 2)) / (olens.double() * 80), g["before_mean"], 1e-6)
+
+
 def test_inference_ragged(golden, weights):
     g = golden("inf_ragged")
     torch.set_num_threads(1)
