@@ -2,6 +2,7 @@
 // the host-side sequencing of the kernels for each stage of FeedForwardTransformer._forward
 // (fastspeech.py:169-243).  No kernel lives here.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -25,6 +26,7 @@ struct Dense {           // one Linear / Conv1d in kernel layout
   const float* w = nullptr;     // [taps][N][K]
   const float* w_hi = nullptr;  // 3xTF32 split of w (encoder / predictors only)
   const float* w_lo = nullptr;
+  const __half* w_h = nullptr;  // fp16 copy (decoder conv-FFN, FS2_MATH_F16)
   const float* bias = nullptr;  // [N] or nullptr
   int N = 0, K = 0, taps = 1;
 };
@@ -35,12 +37,12 @@ struct Predictor { Dense conv[4]; Norm ln[4]; const float* head_w = nullptr; con
 
 // ---- per-kernel-class CUDA-event profiler (bench.py roofline; off by default) -------------
 enum ProfClass {
-  P_EMBED, P_ENC_GEMM, P_ENC_ATTN, P_PRED_GEMM, P_ROWNORM, P_VAR_EMBED, P_DEC_IN, P_DEC_QKV, P_DEC_ATTN, P_DEC_OUT,
-  P_DEC_W1, P_DEC_W2, P_FEAT_OUT, P_POSTNET, P_COUNT
+  P_EMBED, P_ENC_QKV, P_ENC_ATTN, P_ENC_OUT, P_ENC_W1, P_ENC_W2, P_PRED_GEMM, P_ROWNORM, P_VAR_EMBED, P_DEC_IN, P_DEC_QKV,
+  P_DEC_ATTN, P_DEC_OUT, P_DEC_W1, P_DEC_W2, P_FEAT_OUT, P_POSTNET, P_COUNT
 };
 static const char* kProfLabels[P_COUNT] = {
-  "embed_posenc", "enc.tap_gemm", "enc.attention", "predictor.tap_gemm", "row_norm", "variance_embed_add", "dec.embed_linear",
-  "dec.qkv_proj", "dec.attention", "dec.out_proj", "dec.ffn_w1_conv9", "dec.ffn_w2", "feat_out", "postnet.conv5"};
+  "embed_posenc", "enc.qkv_proj", "enc.attention", "enc.out_proj", "enc.ffn_w1_conv9", "enc.ffn_w2", "predictor.tap_gemm", "row_norm",
+  "variance_embed_add", "dec.embed_linear", "dec.qkv_proj", "dec.attention", "dec.out_proj", "dec.ffn_w1_conv9", "dec.ffn_w2", "feat_out", "postnet.conv5"};
 struct ProfRec { int cls; cudaEvent_t a, b; double flop, bytes; };
 struct Profiler {
   bool on = false;
@@ -105,7 +107,8 @@ int dense(const TapGemm& g, int math_mode, cudaStream_t st, int cls) {
   const double M = (double)g.B * g.L;
   ProfScope prof_scope(cls, 2.0 * M * g.N * g.K * g.taps,
                4.0 * (M * g.K + (double)g.taps * g.N * g.K + M * g.N * (g.resid ? 2 : 1)), st);
-  if (math_mode == FS2_MATH_TF32 && g.ln_gamma) return gemm_ln_tf32(g, st);
+  if (math_mode == FS2_MATH_TF32 && g.ln_gamma) return gemm_ln_tf32(g, st);   // fp16 operands / fp16 copy handled inside
+  if (g.x_h) return tap_gemm_f16(g, st);
   return math_mode == MATH_3XTF32 ? tap_gemm_3xtf32(g, st) : math_mode == FS2_MATH_TF32 ? tap_gemm_tf32(g, st) : tap_gemm_fp32(g, st);
 }
 int norm_rows(const RowNorm& r, cudaStream_t st) {
@@ -124,7 +127,7 @@ inline int round4(int x) { return (x + 3) & ~3; }
 TapGemm make_gemm(const Dense& d, const float* x, int ldx, int B, int L, int act, const float* resid, int ldr, float* out,
                   int ldo) {
   TapGemm g;
-  g.x = x; g.ldx = ldx; g.B = B; g.L = L; g.K = d.K; g.w = d.w; g.w_hi = d.w_hi; g.w_lo = d.w_lo; g.bias = d.bias; g.N = d.N; g.taps = d.taps;
+  g.x = x; g.ldx = ldx; g.B = B; g.L = L; g.K = d.K; g.w = d.w; g.w_hi = d.w_hi; g.w_lo = d.w_lo; g.w_h = d.w_h; g.bias = d.bias; g.N = d.N; g.taps = d.taps;
   g.act = act; g.resid = resid; g.ldr = ldr; g.out = out; g.ldo = ldo;
   return g;
 }
@@ -136,13 +139,23 @@ RowNorm make_norm(const Norm& n, const float* x, int ldx, int64_t rows, int C, f
   return r;
 }
 
+// FS2_F16_PARTS (debug / bisecting): which pieces of FS2_MATH_F16 beyond the conv-FFN are on.  2 = LayerNorm-fused
+// projections (gemm_ln_tc.cu) with fp16 operands / fp16 copy, 4 = mel projection + Postnet in f16, 8 = q|k|v in f16.
+int f16_parts_mask() {
+  static int m = -1;
+  if (m < 0) { const char* e = getenv("FS2_F16_PARTS"); m = e ? atoi(e) : 14; }
+  return m;
+}
+
 // FFT blocks on xin; the result lands in *result (one of the two ping-pong buffers xin / y)
 int run_blocks(const std::vector<Block>& blocks, float* xin, float* yin, float* qkv, float* vt, float* ctx, float* hid,
-               const int64_t* lens, int B, int L, int C, int heads, int math_mode, bool is_dec, cudaStream_t st, float** result) {
+               const int64_t* lens, int B, int L, int C, int heads, int math_mode, bool is_dec, cudaStream_t st, float** result,
+               __half* xh = nullptr) {
   const int64_t rows = (int64_t)B * L;
-  const int c_qkv = is_dec ? P_DEC_QKV : P_ENC_GEMM, c_att = is_dec ? P_DEC_ATTN : P_ENC_ATTN;
-  const int c_out = is_dec ? P_DEC_OUT : P_ENC_GEMM, c_w1 = is_dec ? P_DEC_W1 : P_ENC_GEMM, c_w2 = is_dec ? P_DEC_W2 : P_ENC_GEMM;
+  const int c_qkv = is_dec ? P_DEC_QKV : P_ENC_QKV, c_att = is_dec ? P_DEC_ATTN : P_ENC_ATTN;
+  const int c_out = is_dec ? P_DEC_OUT : P_ENC_OUT, c_w1 = is_dec ? P_DEC_W1 : P_ENC_W1, c_w2 = is_dec ? P_DEC_W2 : P_ENC_W2;
   float *x = xin, *y = yin;
+  const int f16_parts = f16_parts_mask();
   for (const Block& k : blocks) {
     int rc;
     // q | k | v projection (attention.py:48-50), one GEMM with N = 3C
@@ -150,30 +163,44 @@ int run_blocks(const std::vector<Block>& blocks, float* xin, float* yin, float* 
     if (math_mode == FS2_MATH_TF32) {  // V third stored transposed for the tensor-core attention (gemm_tc.cu epilogue)
       gq.vt_out = vt; gq.vt_col0 = 2 * C; gq.vt_dk = C / heads; gq.vt_heads = heads; gq.vt_lpad = round4(L);
     }
+    if (xh && (f16_parts & 8)) { gq.x_h = xh; gq.ldx_h = C; }   // xh holds the fp16 copy of x here (written by the LayerNorm before)
     if ((rc = dense(gq, math_mode, st, c_qkv))) return rc;
     if ((rc = attention(math_mode, qkv, vt, round4(L), lens, B, L, C, heads, ctx, st, c_att))) return rc;
-    // x = LN(x + linear_out(ctx)) (attention.py:74, encoder.py:60-62)
+    // x = LN(x + linear_out(ctx)) (attention.py:74, encoder.py:60-62); FS2_MATH_F16: also the fp16 copy for the conv-FFN
     TapGemm go = make_gemm(k.out, ctx, C, B, L, ACT_NONE, x, C, y, C);
     go.ln_gamma = k.ln1.g; go.ln_beta = k.ln1.b; go.ln_eps = k.ln1.eps;
-    if (math_mode == FS2_MATH_TF32 && gemm_ln_tf32_supported(go)) {   // fused: result in y, swap roles
+    const bool fuse_ln = math_mode == FS2_MATH_TF32 && gemm_ln_tf32_supported(go) && (!xh || (f16_parts & 2));
+    if (fuse_ln) {   // fused: result in y, swap roles
+      go.out_h = xh; go.ldo_h = C;
       if ((rc = dense(go, math_mode, st, c_out))) return rc;
       float* t = x; x = y; y = t;
     } else {
       go.ln_gamma = nullptr;
       if ((rc = dense(go, math_mode, st, c_out))) return rc;
-      if ((rc = norm_rows(make_norm(k.ln1, y, C, rows, C, x, C), st))) return rc;
+      RowNorm r1 = make_norm(k.ln1, y, C, rows, C, x, C);
+      r1.out_h = xh; r1.ldo_h = C;
+      if ((rc = norm_rows(r1, st))) return rc;
     }
     // conv-FFN: hid = relu(conv_k(x)); x = LN(x + conv_1(hid))  (modules.py:247-248, encoder.py:64-69)
-    if ((rc = dense(make_gemm(k.w1, x, C, B, L, ACT_RELU, nullptr, 0, hid, k.w1.N), math_mode, st, c_w1))) return rc;
+    TapGemm g1 = make_gemm(k.w1, x, C, B, L, ACT_RELU, nullptr, 0, hid, k.w1.N);
     TapGemm g2 = make_gemm(k.w2, hid, k.w1.N, B, L, ACT_NONE, x, C, y, C);
+    if (xh) {   // fp16 operands: the hidden activations only ever exist as fp16 (in the same workspace slot)
+      __half* hid_h = reinterpret_cast<__half*>(hid);
+      g1.x_h = xh; g1.ldx_h = C; g1.out = nullptr; g1.ldo = 0; g1.out_h = hid_h; g1.ldo_h = k.w1.N;
+      g2.x_h = hid_h; g2.ldx_h = k.w1.N;
+    }
+    if ((rc = dense(g1, math_mode, st, c_w1))) return rc;
     g2.ln_gamma = k.ln2.g; g2.ln_beta = k.ln2.b; g2.ln_eps = k.ln2.eps;
-    if (math_mode == FS2_MATH_TF32 && gemm_ln_tf32_supported(g2)) {
+    if (math_mode == FS2_MATH_TF32 && gemm_ln_tf32_supported(g2) && (!xh || (f16_parts & 2))) {
+      g2.out_h = xh; g2.ldo_h = C;             // fp16 copy of the block output: A operand of the next q|k|v / mel projection
       if ((rc = dense(g2, math_mode, st, c_w2))) return rc;
       float* t = x; x = y; y = t;
     } else {
       g2.ln_gamma = nullptr;
       if ((rc = dense(g2, math_mode, st, c_w2))) return rc;
-      if ((rc = norm_rows(make_norm(k.ln2, y, C, rows, C, x, C), st))) return rc;
+      RowNorm r2 = make_norm(k.ln2, y, C, rows, C, x, C);
+      r2.out_h = xh; r2.ldo_h = C;
+      if ((rc = norm_rows(r2, st))) return rc;
     }
   }
   *result = x;
@@ -243,6 +270,14 @@ struct Packer {
     d->w_hi = hi; d->w_lo = lo;
     return FS2_OK;
   }
+  // fp16 copy for the f16 family (gemm_tc.cu, HALF)
+  int half(Dense* d) {
+    const size_t n = (size_t)d->N * d->K * d->taps;
+    __half* hw = (__half*)bump.bytes(n * sizeof(__half));
+    if (!counting) { int rc = to_half(d->w, hw, (long)n, st); if (rc) return rc; }
+    d->w_h = hw;
+    return FS2_OK;
+  }
   int norm(const std::string& prefix, int C, float eps, Norm* out) {
     int rc;
     if ((rc = copy(prefix + "weight", C, &out->g))) return rc;
@@ -250,7 +285,7 @@ struct Packer {
     out->eps = eps;
     return FS2_OK;
   }
-  int blocks(const std::string& prefix, int n, int C, int H, int kffn, bool precise, std::vector<Block>* out) {
+  int blocks(const std::string& prefix, int n, int C, int H, int kffn, bool precise, bool f16_ffn, std::vector<Block>* out) {
     out->assign(n, Block());
     for (int i = 0; i < n; ++i) {
       std::string p = prefix + ".encoders_." + std::to_string(i) + ".";
@@ -273,6 +308,7 @@ struct Packer {
       if ((rc = dense(p + "feed_forward.w_1.weight", p + "feed_forward.w_1.bias", H, C, kffn, &b.w1))) return rc;
       if ((rc = dense(p + "feed_forward.w_2.weight", p + "feed_forward.w_2.bias", C, H, 1, &b.w2))) return rc;
       if (precise) for (Dense* d : {&b.qkv, &b.out, &b.w1, &b.w2}) if ((rc = split(d))) return rc;
+      if (f16_ffn) for (Dense* d : {&b.qkv, &b.w1, &b.w2}) if ((rc = half(d))) return rc;
       if ((rc = norm(p + "norm1.", C, 1e-5f, &b.ln1))) return rc;   // encoder.py:37-38
       if ((rc = norm(p + "norm2.", C, 1e-5f, &b.ln2))) return rc;
     }
@@ -300,7 +336,7 @@ struct Packer {
     if ((rc = copy("encoder.embed.0.weight", (int64_t)c.idim * c.adim, &h->emb))) return rc;
     if ((rc = copy("encoder.embed.1.alpha", 1, &h->enc_alpha))) return rc;
     if ((rc = copy("encoder.embed.1.pe", (int64_t)c.pe_len * c.adim, &h->enc_pe))) return rc;
-    if ((rc = blocks("encoder", c.elayers, c.adim, c.eunits, c.ffn_kernel, true, &h->enc))) return rc;
+    if ((rc = blocks("encoder", c.elayers, c.adim, c.eunits, c.ffn_kernel, true, false, &h->enc))) return rc;
     if ((rc = predictor("duration_predictor.", &h->dur))) return rc;
     if ((rc = predictor("energy_predictor.predictor.", &h->energy))) return rc;
     if ((rc = predictor("pitch_predictor.predictor.", &h->pitch))) return rc;
@@ -326,9 +362,10 @@ struct Packer {
     if ((rc = norm("decoder.embed.1.", c.ddim, 1e-5f, &h->dec_in_ln))) return rc;
     if ((rc = copy("decoder.embed.4.alpha", 1, &h->dec_alpha))) return rc;
     if ((rc = copy("decoder.embed.4.pe", (int64_t)c.pe_len * c.ddim, &h->dec_pe))) return rc;
-    if ((rc = blocks("decoder", c.dlayers, c.ddim, c.dunits, c.ffn_kernel, true, &h->dec))) return rc;
+    if ((rc = blocks("decoder", c.dlayers, c.ddim, c.dunits, c.ffn_kernel, true, true, &h->dec))) return rc;
     if ((rc = dense("feat_out.weight", "feat_out.bias", c.odim, c.ddim, 1, &h->feat_out))) return rc;
     if ((rc = split(&h->feat_out))) return rc;
+    if ((rc = half(&h->feat_out))) return rc;
     // Postnet: Conv1d(no bias) + BatchNorm1d(eval) folded into weight scale + bias (modules.py:283-348)
     h->postnet.assign(c.postnet_layers, Dense());
     for (int i = 0; i < c.postnet_layers; ++i) {
@@ -342,6 +379,7 @@ struct Packer {
                                             (const float*)var->data, 1e-5f, cout, scale, shift, st))) return rc;
       if ((rc = dense(p + "0.weight", "", cout, cin, c.postnet_filts, &h->postnet[i], scale, shift))) return rc;
       if ((rc = split(&h->postnet[i]))) return rc;
+      if ((rc = half(&h->postnet[i]))) return rc;
     }
     return FS2_OK;
   }
@@ -355,7 +393,7 @@ EncodePlan plan_encode(const fs2_config& c, Bump& b, int64_t rows) {
   p.t1 = b.floats(rows * c.pred_chans); p.t2 = b.floats(rows * c.pred_chans);
   return p;
 }
-struct DecodePlan { float *hm2, *x, *y, *qkv, *vt, *ctx, *hid, *t1, *t2, *q1, *q2; };
+struct DecodePlan { float *hm2, *x, *y, *qkv, *vt, *ctx, *hid, *t1, *t2, *q1, *q2; __half *xh, *before_h; };
 DecodePlan plan_decode(const fs2_config& c, Bump& b, int64_t rows, int B, int L) {
   DecodePlan p;
   p.hm2 = b.floats(rows * c.adim);
@@ -364,6 +402,8 @@ DecodePlan plan_decode(const fs2_config& c, Bump& b, int64_t rows, int B, int L)
   p.ctx = b.floats(rows * c.ddim); p.hid = b.floats(rows * c.dunits);
   p.t1 = b.floats(rows * c.pred_chans); p.t2 = b.floats(rows * c.pred_chans);
   p.q1 = b.floats(rows * c.postnet_chans); p.q2 = b.floats(rows * c.postnet_chans);
+  p.xh = (__half*)b.bytes((size_t)rows * c.ddim * sizeof(__half));   // FS2_MATH_F16: fp16 copy of the current block input / conv-FFN input
+  p.before_h = (__half*)b.bytes((size_t)rows * c.odim * sizeof(__half));   // FS2_MATH_F16: fp16 copy of before_outs for the Postnet
   return p;
 }
 
@@ -389,7 +429,7 @@ int fs2_create(fs2_handle** out, const fs2_config* cfg, int device) {
   FS2_REQUIRE((cfg->ffn_kernel & 1) && (cfg->pred_kernel & 1) && (cfg->postnet_filts & 1), "fs2_create: kernel sizes must be odd");
   FS2_REQUIRE(cfg->postnet_layers >= 1, "fs2_create: postnet_layers == 0 is not supported");
   FS2_REQUIRE(cfg->n_bins % 4 == 0, "fs2_create: n_bins must be a multiple of 4");
-  FS2_REQUIRE(cfg->math_mode >= FS2_MATH_FP32 && cfg->math_mode <= FS2_MATH_3XTF32, "fs2_create: bad math_mode");
+  FS2_REQUIRE(cfg->math_mode >= FS2_MATH_FP32 && cfg->math_mode <= FS2_MATH_F16, "fs2_create: bad math_mode");
   FS2_CUDA_CHECK(cudaSetDevice(device));
   fs2_handle* h = new fs2_handle();
   h->cfg = *cfg;
@@ -427,7 +467,7 @@ int fs2_profile_read(fs2_handle* h, double* ms, int64_t* launches, double* flop,
 
 int fs2_set_math_mode(fs2_handle* h, int math_mode) {
   FS2_REQUIRE(h, "fs2_set_math_mode: null handle");
-  FS2_REQUIRE(math_mode >= FS2_MATH_FP32 && math_mode <= FS2_MATH_3XTF32, "fs2_set_math_mode: bad mode %d", math_mode);
+  FS2_REQUIRE(math_mode >= FS2_MATH_FP32 && math_mode <= FS2_MATH_F16, "fs2_set_math_mode: bad mode %d", math_mode);
   h->cfg.math_mode = math_mode;
   return FS2_OK;
 }
@@ -521,7 +561,8 @@ int fs2_decode(fs2_handle* h, const float* hm, const int64_t* olens, const float
   Bump b(ws, ws_bytes);
   DecodePlan p = plan_decode(c, b, rows, B, L);
   if (!b.ok()) { set_error("fs2_decode: workspace too small (%zu < %zu)", ws_bytes, b.off); return FS2_ERR_WORKSPACE; }
-  const int mode = c.math_mode;
+  const bool f16_ffn = c.math_mode == FS2_MATH_F16;                     // tf32 everywhere except the conv-FFN
+  const int mode = f16_ffn ? FS2_MATH_TF32 : c.math_mode;
   const int precise = mode == FS2_MATH_FP32 ? FS2_MATH_FP32 : MATH_3XTF32;
   int rc;
   // energy / pitch predictors on the length-regulated states (fastspeech.py:195-196,214-216); fp32
@@ -536,20 +577,33 @@ int fs2_decode(fs2_handle* h, const float* hm, const int64_t* olens, const float
   {
     RowNorm r = make_norm(h->dec_in_ln, p.y, c.ddim, rows, c.ddim, p.x, c.ddim);
     r.relu_after = 1; r.pe = h->dec_pe; r.alpha = h->dec_alpha; r.L = L;
+    if (f16_ffn) { r.out_h = p.xh; r.ldo_h = c.ddim; }    // first block's q|k|v reads the fp16 copy
     if ((rc = norm_rows(r, st))) return rc;
   }
   float* dec_out = nullptr;
-  if ((rc = run_blocks(h->dec, p.x, p.y, p.qkv, p.vt, p.ctx, p.hid, olens, B, L, c.ddim, c.aheads, mode, true, st, &dec_out))) return rc;
-  // mel linear (fastspeech.py:228-230)
-  if ((rc = dense(make_gemm(h->feat_out, dec_out, c.ddim, B, L, ACT_NONE, nullptr, 0, before, c.odim), mode, st, P_FEAT_OUT))) return rc;
+  if ((rc = run_blocks(h->dec, p.x, p.y, p.qkv, p.vt, p.ctx, p.hid, olens, B, L, c.ddim, c.aheads, mode, true, st, &dec_out, f16_ffn ? p.xh : nullptr))) return rc;
+  // mel linear (fastspeech.py:228-230); FS2_MATH_F16: from the fp16 copy of the last block's output, and the Postnet
+  // chain stays in fp16 until the final residual layer
+  const bool f16_post = f16_ffn && (f16_parts_mask() & 4) && c.odim % 16 == 0;
+  {
+    TapGemm g = make_gemm(h->feat_out, dec_out, c.ddim, B, L, ACT_NONE, nullptr, 0, before, c.odim);
+    if (f16_post) { g.x_h = p.xh; g.ldx_h = c.ddim; g.out_h = p.before_h; g.ldo_h = c.odim; }
+    if ((rc = dense(g, mode, st, P_FEAT_OUT))) return rc;
+  }
   // Postnet + residual (fastspeech.py:236-238, modules.py:350-359)
   const float* cur = before; int curC = c.odim;
+  const __half* cur_h = p.before_h;
   float* pp[2] = {p.q1, p.q2};
   for (int i = 0; i < c.postnet_layers; ++i) {
     bool last = i == c.postnet_layers - 1;
     float* dst = last ? after : pp[i & 1];
     TapGemm g = make_gemm(h->postnet[i], cur, curC, B, L, last ? ACT_NONE : ACT_TANH, last ? before : nullptr, c.odim, dst,
                           h->postnet[i].N);
+    if (f16_post) {
+      g.x_h = cur_h; g.ldx_h = curC;
+      if (!last) { g.out = nullptr; g.ldo = 0; g.out_h = reinterpret_cast<__half*>(dst); g.ldo_h = h->postnet[i].N; }
+      cur_h = reinterpret_cast<const __half*>(dst);
+    }
     if ((rc = dense(g, mode, st, P_POSTNET))) return rc;
     cur = dst; curC = h->postnet[i].N;
   }
@@ -579,6 +633,19 @@ int fs2_op_tap_gemm(int math_mode, const float* x, int B, int L, int K, const fl
   FS2_REQUIRE(x && w && out, "fs2_op_tap_gemm: null argument");
   Dense d; d.w = w; d.bias = bias; d.N = N; d.K = K; d.taps = taps;
   cudaStream_t st = (cudaStream_t)stream;
+  if (math_mode == FS2_MATH_F16) {   // single-operator entry for the f16 family (tests): fp16 copies made on the fly
+    const size_t nx = (size_t)B * L * K, nw = (size_t)N * K * taps;
+    __half* tmp = nullptr;
+    FS2_CUDA_CHECK(cudaMallocAsync(&tmp, (nx + nw + 16) * sizeof(__half), st));
+    __half* wh = tmp + ((nx + 7) & ~(size_t)7);
+    int rc = to_half(x, tmp, (long)nx, st);
+    if (!rc) rc = to_half(w, wh, (long)nw, st);
+    TapGemm g = make_gemm(d, x, K, B, L, act, resid, N, out, N);
+    g.x_h = tmp; g.ldx_h = K; g.w_h = wh;
+    if (!rc) rc = dense(g, FS2_MATH_TF32, st, P_DEC_W1);
+    cudaFreeAsync(tmp, st);
+    return rc;
+  }
   if (math_mode != MATH_3XTF32) return dense(make_gemm(d, x, K, B, L, act, resid, N, out, N), math_mode, st, P_DEC_W1);
   // single-operator entry for the 3xTF32 family (tests): split the weights on the fly
   const size_t n = (size_t)N * K * taps;

@@ -1,5 +1,6 @@
 // Shared declarations of libfs2b200.so (internal; the public ABI is include/fs2_b200.h).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -56,6 +57,9 @@ struct TapGemm {
   const float* ln_gamma = nullptr; const float* ln_beta = nullptr; float ln_eps = 0.f;
   // tf32 family only: store output columns >= vt_col0 transposed into vt_out (see gemm_tc.cu)
   float* vt_out = nullptr; int vt_col0 = 0, vt_dk = 0, vt_heads = 0, vt_lpad = 0;
+  // f16 family (tap_gemm_f16): fp16 copies of the activations (row stride ldx_h halfs) and of w; the result goes to
+  // out (fp32, with the optional residual) and / or out_h (fp16, row stride ldo_h halfs, for the next f16 GEMM)
+  const __half* x_h = nullptr; int ldx_h = 0; const __half* w_h = nullptr; __half* out_h = nullptr; int ldo_h = 0;
 };
 int tap_gemm_fp32(const TapGemm& g, cudaStream_t st);
 int tap_gemm_tf32(const TapGemm& g, cudaStream_t st);   // tcgen05 + TMA (gemm_tc.cu)
@@ -63,6 +67,8 @@ bool gemm_ln_tf32_supported(const TapGemm& g);         // row-complete GEMM + re
 int gemm_ln_tf32(const TapGemm& g, cudaStream_t st);
 int tap_gemm_3xtf32(const TapGemm& g, cudaStream_t st); // same kernel, error-compensated split operands
 int split_tf32(const float* src, float* hi, float* lo, long n, cudaStream_t st);
+int tap_gemm_f16(const TapGemm& g, cudaStream_t st);    // same kernel, kind::f16 on x_h / w_h, fp32 accumulation
+int to_half(const float* src, __half* dst, long n, cudaStream_t st);   // round to nearest, clamped to +-65504
 constexpr int MATH_3XTF32 = FS2_MATH_3XTF32;            // also what FS2_MATH_TF32 uses for the encoder + predictors
 
 // Row LayerNorm with the fusions the path needs.
@@ -77,6 +83,7 @@ struct RowNorm {
   // optional scalar head (predictors): s = y . head_w + head_b, 0 where t >= lens[b]
   const float* head_w; const float* head_b; float* head_out; int64_t* dur_out;
   const int64_t* lens;            // optional mask for the head outputs
+  __half* out_h; int ldo_h;       // optional fp16 copy of y (A operand of an f16 GEMM)
 };
 int row_norm(const RowNorm& r, cudaStream_t st);
 

@@ -16,6 +16,8 @@
 //   pass B  partial sums of (y - mean)^2        (two-pass variance like nn.LayerNorm)
 //   pass C  (y - mean) * rstd * gamma + beta -> four 256-bit global stores per thread and chunk
 // Row statistics are exchanged between the two threads of a row through shared memory.
+// H16 = true: fp16 operands (kind::f16, 64 K-elements per 128-byte swizzle row) for FS2_MATH_F16's w_2 projection;
+// either variant can also emit the normalised rows as fp16 (out_h) for the f16 GEMM that consumes them next.
 #include "tc_common.cuh"
 
 namespace fs2 {
@@ -26,15 +28,16 @@ constexpr int BM = 128, BK = 32, UMMA_K = 8;
 constexpr int A_BYTES = BM * BK * 4;
 constexpr int LN_THREADS = 320;
 
-template <int C>
+template <int C, bool H16>
 struct LCfg {
   static constexpr int HALF = C / 2;                      // one MMA / one TMA box of weight rows
+  static constexpr int BKE = H16 ? 2 * BK : BK;            // K elements per pipeline step
   static constexpr int B_BYTES = C * BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGING_BYTES = 2 * BM * 4;         // row-statistic exchange between the two threads of a row
   static constexpr int STAGES = (227 * 1024 - STAGING_BYTES - 1024 - 512) / STAGE_BYTES;
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
-  static constexpr uint32_t IDESC = idesc_tf32(BM, HALF);
+  static constexpr uint32_t IDESC = H16 ? idesc_f16(BM, HALF) : idesc_tf32(BM, HALF);
   static constexpr int TMEM_COLS = 512;
   static constexpr int CHUNKS_PER_GROUP = C / 64;
   static_assert(C % 64 == 0 && HALF % 16 == 0 && HALF <= 256 && C <= 512, "row width");
@@ -46,12 +49,13 @@ struct LnParams {
   const float* bias; const float* resid; int ldr;
   const float* gamma; const float* beta; float eps;
   float* out; int ldo;
+  __half* out_h; int ldo_h;     // optional fp16 copy of the result
 };
 
-template <int C>
+template <int C, bool H16>
 __global__ void __launch_bounds__(LN_THREADS, 1)
 gemm_ln_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, LnParams p) {
-  using L = LCfg<C>;
+  using L = LCfg<C, H16>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (no generic LD/ST)
   uint8_t* staging = tiles + (size_t)L::STAGES * L::STAGE_BYTES;
@@ -62,7 +66,7 @@ gemm_ln_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int steps = (p.K + BK - 1) / BK;
+  const int steps = (p.K + L::BKE - 1) / L::BKE;
   const int tiles_total = (p.M + BM - 1) / BM;
 
   if (threadIdx.x == 0) {
@@ -86,9 +90,9 @@ gemm_ln_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           mbar_wait(&empty_bar[slot], ((n / L::STAGES) & 1) ^ 1);
           uint8_t* st = tiles + (size_t)slot * L::STAGE_BYTES;
           mbar_expect_tx(&full_bar[slot], L::STAGE_BYTES);
-          tma_load_3d(st, &tmap_a, &full_bar[slot], s * BK, r0, 0);
-          tma_load_3d(st + A_BYTES, &tmap_b, &full_bar[slot], s * BK, 0, 0);
-          tma_load_3d(st + A_BYTES + L::HALF * BK * 4, &tmap_b, &full_bar[slot], s * BK, L::HALF, 0);
+          tma_load_3d(st, &tmap_a, &full_bar[slot], s * L::BKE, r0, 0);
+          tma_load_3d(st + A_BYTES, &tmap_b, &full_bar[slot], s * L::BKE, 0, 0);
+          tma_load_3d(st + A_BYTES + L::HALF * BK * 4, &tmap_b, &full_bar[slot], s * L::BKE, L::HALF, 0);
         }
       }
     }
@@ -107,8 +111,13 @@ gemm_ln_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const uint64_t b0 = make_sw128_kmajor_desc(base + A_BYTES), b1 = make_sw128_kmajor_desc(base + A_BYTES + L::HALF * BK * 4);
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
-          umma_tf32(tmem_base, a + 2 * k, b0 + 2 * k, L::IDESC, (s | k) != 0);
-          umma_tf32(tmem_base + L::HALF, a + 2 * k, b1 + 2 * k, L::IDESC, (s | k) != 0);
+          if (H16) {
+            umma_f16(tmem_base, a + 2 * k, b0 + 2 * k, L::IDESC, (s | k) != 0);
+            umma_f16(tmem_base + L::HALF, a + 2 * k, b1 + 2 * k, L::IDESC, (s | k) != 0);
+          } else {
+            umma_tf32(tmem_base, a + 2 * k, b0 + 2 * k, L::IDESC, (s | k) != 0);
+            umma_tf32(tmem_base + L::HALF, a + 2 * k, b1 + 2 * k, L::IDESC, (s | k) != 0);
+          }
         }
         tcgen05_commit(&empty_bar[slot]);
       }
@@ -195,6 +204,16 @@ gemm_ln_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           float* dst = p.out + m * p.ldo + c0;
 #pragma unroll
           for (int q = 0; q < 4; ++q) st_global_v8(dst + q * 8, v + q * 8);
+          if (p.out_h != nullptr) {
+            uint32_t h[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const __half2 t = __floats2half2_rn(fminf(fmaxf(v[2 * j], -65504.f), 65504.f), fminf(fmaxf(v[2 * j + 1], -65504.f), 65504.f));
+              h[j] = *reinterpret_cast<const uint32_t*>(&t);
+            }
+            __half* dh = p.out_h + m * p.ldo_h + c0;
+            st_global_v8_b32(dh, h); st_global_v8_b32(dh + 16, h + 8);
+          }
         }
       }
       tcgen05_fence_before();
@@ -224,32 +243,49 @@ int sm_count_ln() {
 
 bool gemm_ln_tf32_supported(const TapGemm& g) { return g.taps == 1 && g.N == 384 && g.K % 4 == 0 && g.ln_gamma && !g.vt_out && g.act == ACT_NONE; }
 
-int gemm_ln_tf32(const TapGemm& g, cudaStream_t st) {
-  FS2_REQUIRE(gemm_ln_tf32_supported(g), "gemm_ln_tf32: unsupported shape (N=%d taps=%d)", g.N, g.taps);
-  FS2_REQUIRE(g.ldx % 4 == 0 && g.ldo % 8 == 0 && (!g.resid || g.ldr % 4 == 0) && (reinterpret_cast<uintptr_t>(g.out) & 31) == 0,
-              "gemm_ln_tf32: row strides / output alignment");
+namespace {
+template <bool H16>
+int launch_ln(const TapGemm& g, cudaStream_t st) {
   constexpr int C = 384;
-  using L = LCfg<C>;
+  using L = LCfg<C, H16>;
   const uint64_t M = (uint64_t)g.B * g.L;
-  if (M == 0) return FS2_OK;
   static bool configured = false;
   if (!configured) {
-    FS2_CUDA_CHECK(cudaFuncSetAttribute(gemm_ln_tf32_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
+    FS2_CUDA_CHECK(cudaFuncSetAttribute(gemm_ln_tf32_kernel<C, H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
     configured = true;
   }
   CUtensorMap ma, mb;
   int rc;
-  const uint64_t arow = (uint64_t)g.ldx * 4;
-  if ((rc = make_map(&ma, g.x, g.K, M, 1, arow, arow * M, BM))) return rc;
-  if ((rc = make_map(&mb, g.w, g.K, C, 1, (uint64_t)g.K * 4, (uint64_t)g.K * 4 * C, L::HALF))) return rc;
+  const int esz = H16 ? 2 : 4;
+  const uint64_t arow = H16 ? (uint64_t)g.ldx_h * 2 : (uint64_t)g.ldx * 4;
+  if ((rc = make_map(&ma, H16 ? (const void*)g.x_h : (const void*)g.x, g.K, M, 1, arow, arow * M, BM, H16))) return rc;
+  if ((rc = make_map(&mb, H16 ? (const void*)g.w_h : (const void*)g.w, g.K, C, 1, (uint64_t)g.K * esz, (uint64_t)g.K * esz * C, L::HALF, H16))) return rc;
   LnParams p;
   p.M = (int)M; p.K = g.K; p.bias = g.bias; p.resid = g.resid; p.ldr = g.ldr;
   p.gamma = g.ln_gamma; p.beta = g.ln_beta; p.eps = g.ln_eps; p.out = g.out; p.ldo = g.ldo;
+  p.out_h = g.out_h; p.ldo_h = g.ldo_h;
   const int tiles = (int)((M + BM - 1) / BM);
   const int grid = tiles < sm_count_ln() ? tiles : sm_count_ln();
-  gemm_ln_tf32_kernel<C><<<grid, LN_THREADS, L::SMEM, st>>>(ma, mb, p);
+  gemm_ln_tf32_kernel<C, H16><<<grid, LN_THREADS, L::SMEM, st>>>(ma, mb, p);
   FS2_LAUNCH_CHECK();
   return FS2_OK;
+}
+}  // namespace
+
+// g.x_h set: fp16 operands (x_h, w_h); g.out_h set: also emit the result as fp16
+int gemm_ln_tf32(const TapGemm& g, cudaStream_t st) {
+  FS2_REQUIRE(gemm_ln_tf32_supported(g), "gemm_ln_tf32: unsupported shape (N=%d taps=%d)", g.N, g.taps);
+  FS2_REQUIRE(g.ldo % 8 == 0 && (!g.resid || g.ldr % 4 == 0) && g.out && (reinterpret_cast<uintptr_t>(g.out) & 31) == 0,
+              "gemm_ln_tf32: row strides / output alignment");
+  FS2_REQUIRE(!g.out_h || (g.ldo_h % 16 == 0 && (reinterpret_cast<uintptr_t>(g.out_h) & 31) == 0), "gemm_ln_tf32: fp16 output rows must be 32-byte aligned");
+  if ((uint64_t)g.B * g.L == 0) return FS2_OK;
+  if (g.x_h) {
+    FS2_REQUIRE(g.w_h && g.K % 8 == 0 && g.ldx_h % 8 == 0 && (reinterpret_cast<uintptr_t>(g.x_h) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.w_h) & 15) == 0,
+                "gemm_ln_tf32: fp16 operands must be 16-byte aligned with K a multiple of 8");
+    return launch_ln<true>(g, st);
+  }
+  FS2_REQUIRE(g.ldx % 4 == 0, "gemm_ln_tf32: row strides / output alignment");
+  return launch_ln<false>(g, st);
 }
 
 }  // namespace fs2

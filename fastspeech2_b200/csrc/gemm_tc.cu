@@ -37,6 +37,11 @@
 // separate small TMA boxes) of several utterances packed into shared tiles, so no tensor-core rows are
 // spent on padding (at L = 800 that was 12 %).  Plain GEMMs (taps == 1) tile the flat [B*L, K] matrix.
 // Every mbarrier wait is bounded: a pipeline bug traps instead of hanging the GPU.
+//
+// HALF = true (FS2_MATH_F16, the decoder's conv-FFN): the same pipeline on fp16 copies of the activations and weights
+// with kind::f16 -- a 128-byte swizzle row then holds 64 K-elements and one MMA covers K = 16, so a pipeline step moves
+// the same bytes and issues the same four MMAs but does twice the work; the epilogue can emit the result as fp16 for
+// the next f16 GEMM (conv k=9 -> ReLU -> conv k=1).  fp16 has tf32's 10-bit mantissa; accumulation stays fp32.
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -46,8 +51,8 @@ namespace {
 using namespace tc;
 
 constexpr int BM = 128;
-constexpr int BK = 32;                 // fp32 elements per pipeline step = one 128-byte swizzle row
-constexpr int UMMA_K = 8;              // tf32
+constexpr int BK = 32;                 // fp32 elements per pipeline step = one 128-byte swizzle row (64 when the operands are fp16)
+constexpr int UMMA_K = 8;              // tf32 (16 for f16: 32 bytes of K per instruction either way)
 constexpr int A_BYTES = BM * BK * 4;   // 16 KB
 constexpr int STAGING_BYTES = 8 * 1024;          // bias[N] (N <= 2048) staged once per CTA; outputs go straight from registers
 constexpr int RING_BUDGET = 227 * 1024 - STAGING_BYTES - 1024 /*align slack*/ - 512 /*barriers*/;
@@ -61,6 +66,7 @@ struct TcParams {
   int K, taps, pad;
   const float* bias; const float* resid; int ldr; int act;
   float* out; int ldo;
+  __half* out_h; int ldo_h;      // HALF only: fp16 copy of the result (out may then be null)
   // optional: columns >= vt_col0 are the V third of a q|k|v projection and are stored transposed,
   // vt[(b*heads + h)*dk + d][t] with row pitch vt_lpad, for the attention kernel's K-major P.V operand
   float* vt_out; int vt_col0, vt_dk, vt_heads, vt_lpad, vt_L;
@@ -69,7 +75,7 @@ struct TcParams {
 
 constexpr int pow2_at_least(int x) { return x <= 32 ? 32 : x <= 64 ? 64 : x <= 128 ? 128 : 256; }
 
-template <int BN, bool PRECISE>
+template <int BN, bool PRECISE, bool HALF = false>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = (PRECISE ? 2 : 1) * (A_BYTES + B_BYTES);   // [A(hi)][A lo][B hi][B lo]
@@ -80,7 +86,9 @@ struct Cfg {
   static constexpr int GROUPS = 2;       // epilogue warp groups (4 warps each), alternate 32-column chunks
   static constexpr int THREADS = 64 + GROUPS * 128 + (PRECISE ? 128 : 0);
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
-  static constexpr uint32_t IDESC = idesc_tf32(BM, BN);
+  static constexpr uint32_t IDESC = HALF ? idesc_f16(BM, BN) : idesc_tf32(BM, BN);
+  static constexpr int BKE = HALF ? 2 * BK : BK;           // K elements per pipeline step
+  static_assert(!(HALF && PRECISE), "the f16 family has no split-operand variant");
   static constexpr int A_LO = A_BYTES;                                  // offsets inside a stage
   static constexpr int B_HI = PRECISE ? 2 * A_BYTES : A_BYTES;
   static constexpr int B_LO = B_HI + B_BYTES;
@@ -94,11 +102,11 @@ struct Cfg {
 // is itself read as tf32 by the tensor core (relative error 2^-10 of lo = 2^-21 of x)
 __device__ __forceinline__ float hi_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
-template <int BN, bool PRECISE>
-__global__ void __launch_bounds__(Cfg<BN, PRECISE>::THREADS, 1)
+template <int BN, bool PRECISE, bool HALF>
+__global__ void __launch_bounds__(Cfg<BN, PRECISE, HALF>::THREADS, 1)
 tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ CUtensorMap tmap_b_lo, const __grid_constant__ CUtensorMap tmap_a16, TcParams p) {
-  using C = Cfg<BN, PRECISE>;
+  using C = Cfg<BN, PRECISE, HALF>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (no generic LD/ST)
   uint8_t* staging = tiles + (size_t)C::STAGES * C::STAGE_BYTES;
@@ -110,7 +118,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kchunks = (p.K + BK - 1) / BK;
+  const int kchunks = (p.K + C::BKE - 1) / C::BKE;
   const int steps = p.taps * kchunks;
   const int total_tiles = p.m_tiles * p.n_tiles;
 
@@ -150,7 +158,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         for (int s = 0; s < steps; ++s, ++n) {
           const int slot = n % C::STAGES, round = n / C::STAGES;
           mbar_wait(&empty_bar[slot], (round & 1) ^ 1);
-          const int j = s / kchunks, k0 = (s - j * kchunks) * BK;
+          const int j = s / kchunks, k0 = (s - j * kchunks) * C::BKE;
           uint8_t* st = tiles + (size_t)slot * C::STAGE_BYTES;
           mbar_expect_tx(&full_bar[slot], C::TX_BYTES);
           if (packed < 0) {
@@ -189,6 +197,8 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
               umma_tf32(d, a_lo + 2 * k, b_hi + 2 * k, C::IDESC, (s | k) != 0);   // small terms first
               umma_tf32(d, a_hi + 2 * k, b_lo + 2 * k, C::IDESC, 1);
               umma_tf32(d, a_hi + 2 * k, b_hi + 2 * k, C::IDESC, 1);
+            } else if (HALF) {
+              umma_f16(d, a_hi + 2 * k, b_hi + 2 * k, C::IDESC, (s | k) != 0);
             } else {
               umma_tf32(d, a_hi + 2 * k, b_hi + 2 * k, C::IDESC, (s | k) != 0);
             }
@@ -275,8 +285,21 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             for (int q = 0; q < 8; ++q)
               if (full || c0 + q * 4 < BN) { v[q * 4] += rv[q].x; v[q * 4 + 1] += rv[q].y; v[q * 4 + 2] += rv[q].z; v[q * 4 + 3] += rv[q].w; }
           }
+          if (HALF && p.out_h != nullptr) {              // fp16 copy for the next f16 GEMM: two 32-byte stores
+            uint32_t h[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const __half2 t = __floats2half2_rn(fminf(fmaxf(v[2 * i], -65504.f), 65504.f), fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f));
+              h[i] = *reinterpret_cast<const uint32_t*>(&t);
+            }
+            __half* dh = p.out_h + m * p.ldo_h + n0 + c0;
+            if (full || c0 + 16 <= BN) st_global_v8_b32(dh, h);
+            if (full) st_global_v8_b32(dh + 16, h + 8);
+          }
           float* dst = out + m * ldo + n0 + c0;          // this thread's row: four sector-complete 32-byte stores
-          if (full) {
+          if (HALF && out == nullptr) {
+            // fp16-only result (the hidden activations of the conv-FFN)
+          } else if (full) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) st_global_v8(dst + q * 8, v + q * 8);
           } else {
@@ -342,28 +365,31 @@ int sm_count() {
   return n;
 }
 
-template <int BN, bool PRECISE>
+template <int BN, bool PRECISE, bool HALF = false>
 int launch(const TapGemm& g, cudaStream_t st) {
-  using C = Cfg<BN, PRECISE>;
+  using C = Cfg<BN, PRECISE, HALF>;
   static bool configured = false;
   if (!configured) {
-    FS2_CUDA_CHECK(cudaFuncSetAttribute(tap_gemm_tf32_kernel<BN, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    FS2_CUDA_CHECK(cudaFuncSetAttribute(tap_gemm_tf32_kernel<BN, PRECISE, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     configured = true;
   }
   TcParams p;
   p.K = g.K; p.taps = g.taps; p.pad = (g.taps - 1) / 2;
   p.bias = g.bias; p.resid = g.resid; p.ldr = g.ldr; p.act = g.act; p.out = g.out; p.ldo = g.ldo;
+  p.out_h = HALF ? g.out_h : nullptr; p.ldo_h = g.ldo_h;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FS2_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
   p.vt_out = g.vt_out; p.vt_col0 = g.vt_col0; p.vt_dk = g.vt_dk; p.vt_heads = g.vt_heads; p.vt_lpad = g.vt_lpad; p.vt_L = g.L;
   CUtensorMap ma, mb, mb_lo, ma16;
   int rc;
-  const uint64_t row_bytes = (uint64_t)g.ldx * 4;
+  const int esz = HALF ? 2 : 4;
+  const void* xa = HALF ? (const void*)g.x_h : (const void*)g.x;
+  const uint64_t row_bytes = HALF ? (uint64_t)g.ldx_h * 2 : (uint64_t)g.ldx * 4;
   if (g.taps == 1) {  // flat [B*L, K]
     const uint64_t M = (uint64_t)g.B * g.L;
     p.L = (int)M; p.tiles_per_utt = 0;
     p.m_tiles = (int)((M + BM - 1) / BM);
     p.B = 1; p.full = 0; p.gn = 1; p.upt = 1; p.full_tiles = 0;
-    if ((rc = make_map(&ma, g.x, g.K, M, 1, row_bytes, row_bytes * M, BM))) return rc;
+    if ((rc = make_map(&ma, xa, g.K, M, 1, row_bytes, row_bytes * M, BM, HALF))) return rc;
     ma16 = ma;
   } else {            // per-utterance tiles: shifted boxes zero-fill outside [0, L)
     p.L = g.L; p.tiles_per_utt = (g.L + BM - 1) / BM;
@@ -374,29 +400,33 @@ int launch(const TapGemm& g, cudaStream_t st) {
     if (tail && p.upt == 1) { p.full += 1; tail = 0; p.gn = 1; }   // tail > 64 rows: nothing to share, keep one ordinary (partly empty) tile
     p.full_tiles = p.full * g.B;
     p.m_tiles = p.full_tiles + (tail ? (g.B + p.upt - 1) / p.upt : 0);
-    if ((rc = make_map(&ma, g.x, g.K, g.L, g.B, row_bytes, row_bytes * g.L, BM))) return rc;
-    if ((rc = make_map(&ma16, g.x, g.K, g.L, g.B, row_bytes, row_bytes * g.L, 16))) return rc;
+    if ((rc = make_map(&ma, xa, g.K, g.L, g.B, row_bytes, row_bytes * g.L, BM, HALF))) return rc;
+    if ((rc = make_map(&ma16, xa, g.K, g.L, g.B, row_bytes, row_bytes * g.L, 16, HALF))) return rc;
   }
   p.n_tiles = g.N / BN;
-  const float* w_hi = PRECISE ? g.w_hi : g.w;
-  if ((rc = make_map(&mb, w_hi, g.K, g.N, g.taps, (uint64_t)g.K * 4, (uint64_t)g.K * 4 * g.N, BN))) return rc;
-  if ((rc = make_map(&mb_lo, PRECISE ? g.w_lo : w_hi, g.K, g.N, g.taps, (uint64_t)g.K * 4, (uint64_t)g.K * 4 * g.N, BN))) return rc;
+  const void* w_hi = HALF ? (const void*)g.w_h : PRECISE ? (const void*)g.w_hi : (const void*)g.w;
+  if ((rc = make_map(&mb, w_hi, g.K, g.N, g.taps, (uint64_t)g.K * esz, (uint64_t)g.K * esz * g.N, BN, HALF))) return rc;
+  if ((rc = make_map(&mb_lo, PRECISE ? (const void*)g.w_lo : w_hi, g.K, g.N, g.taps, (uint64_t)g.K * esz, (uint64_t)g.K * esz * g.N, BN, HALF))) return rc;
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < sm_count() ? total : sm_count();
-  tap_gemm_tf32_kernel<BN, PRECISE><<<grid, C::THREADS, C::SMEM, st>>>(ma, mb, mb_lo, ma16, p);
+  tap_gemm_tf32_kernel<BN, PRECISE, HALF><<<grid, C::THREADS, C::SMEM, st>>>(ma, mb, mb_lo, ma16, p);
   FS2_LAUNCH_CHECK();
   return FS2_OK;
 }
 
-int check_common(const TapGemm& g, const char* who) {
-  FS2_REQUIRE(g.K % 4 == 0 && g.N % 16 == 0, "%s: K (%d) must be a multiple of 4 and N (%d) of 16", who, g.K, g.N);
-  FS2_REQUIRE(g.ldx % 4 == 0 && g.ldo % 4 == 0 && (!g.resid || g.ldr % 4 == 0), "%s: row strides must be 16-byte multiples", who);
-  FS2_REQUIRE((reinterpret_cast<uintptr_t>(g.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.w) & 15) == 0 &&
-              (reinterpret_cast<uintptr_t>(g.out) & 15) == 0, "%s: operands must be 16-byte aligned", who);
+int check_output(const TapGemm& g, const char* who) {
   FS2_REQUIRE((g.taps & 1) == 1, "%s: taps must be odd", who);
-  FS2_REQUIRE(g.N <= 2048, "%s: N (%d) exceeds the staged bias vector (2048)", who, g.N);
+  FS2_REQUIRE(g.N % 16 == 0 && g.N <= 2048, "%s: N (%d) must be a multiple of 16 and fit the staged bias vector (2048)", who, g.N);
+  FS2_REQUIRE(!g.resid || g.ldr % 4 == 0, "%s: row strides must be 16-byte multiples", who);
   FS2_REQUIRE(g.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(g.out) & 31) == 0, "%s: output rows must be 32-byte aligned (256-bit stores)", who);
   return FS2_OK;
+}
+int check_common(const TapGemm& g, const char* who) {
+  FS2_REQUIRE(g.K % 4 == 0, "%s: K (%d) must be a multiple of 4", who, g.K);
+  FS2_REQUIRE(g.ldx % 4 == 0, "%s: row strides must be 16-byte multiples", who);
+  FS2_REQUIRE((reinterpret_cast<uintptr_t>(g.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.w) & 15) == 0 && g.out != nullptr,
+              "%s: operands must be 16-byte aligned", who);
+  return check_output(g, who);
 }
 
 }  // namespace
@@ -432,6 +462,24 @@ int tap_gemm_3xtf32(const TapGemm& g, cudaStream_t st) {
   if (g.N % 80 == 0) return launch<80, true>(g, st);
   if (g.N % 64 == 0) return launch<64, true>(g, st);
   set_error("tap_gemm_3xtf32: N=%d has no supported tile width", g.N);
+  return FS2_ERR_INVALID;
+}
+
+int tap_gemm_f16(const TapGemm& g, cudaStream_t st) {
+  const char* who = "tap_gemm_f16";
+  FS2_REQUIRE(g.x_h && g.w_h && (g.out || g.out_h), "%s: fp16 operands / an output missing", who);
+  FS2_REQUIRE(g.K % 8 == 0 && g.ldx_h % 8 == 0, "%s: K (%d) and the fp16 row stride must be multiples of 8", who, g.K);
+  FS2_REQUIRE((reinterpret_cast<uintptr_t>(g.x_h) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.w_h) & 15) == 0, "%s: operands must be 16-byte aligned", who);
+  FS2_REQUIRE(!g.out_h || (g.ldo_h % 16 == 0 && (reinterpret_cast<uintptr_t>(g.out_h) & 31) == 0), "%s: fp16 output rows must be 32-byte aligned", who);
+  FS2_REQUIRE(!g.ln_gamma, "%s: the LayerNorm epilogue lives in gemm_ln_tc.cu", who);
+  int rc = check_output(g, who);
+  if (rc) return rc;
+  if ((long)g.B * g.L == 0) return FS2_OK;
+  if (g.N % 256 == 0) return launch<256, false, true>(g, st);
+  if (g.N % 192 == 0) return launch<192, false, true>(g, st);
+  if (g.N % 128 == 0) return launch<128, false, true>(g, st);
+  if (g.N % 80 == 0) return launch<80, false, true>(g, st);
+  set_error("%s: N=%d has no supported tile width (multiples of 80, 128 or 192)", who, g.N);
   return FS2_ERR_INVALID;
 }
 

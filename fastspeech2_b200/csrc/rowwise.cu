@@ -86,6 +86,13 @@ __global__ void row_norm_kernel(RowNorm r) {
       dot += (y.x * w.x + y.y * w.y) + (y.z * w.z + y.w * w.w);
     }
     if (r.out) *reinterpret_cast<float4*>(r.out + row * r.ldo + c) = y;
+    if (r.out_h) {   // fp16 copy (A operand of the f16 conv-FFN), 8-byte store
+      const __half2 lo = __floats2half2_rn(fminf(fmaxf(y.x, -65504.f), 65504.f), fminf(fmaxf(y.y, -65504.f), 65504.f));
+      const __half2 hi = __floats2half2_rn(fminf(fmaxf(y.z, -65504.f), 65504.f), fminf(fmaxf(y.w, -65504.f), 65504.f));
+      uint2 u;
+      u.x = *reinterpret_cast<const uint32_t*>(&lo); u.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(r.out_h + row * r.ldo_h + c) = u;
+    }
   }
   if (r.head_w) {
     dot = warp_sum(dot) + __ldg(r.head_b);
@@ -269,13 +276,26 @@ int embed_posenc(const int64_t* xs, const float* table, int n_sym, const float* 
   return FS2_OK;
 }
 
+__global__ void to_half_kernel(const float* __restrict__ src, __half* __restrict__ dst, long n) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    dst[i] = __float2half_rn(fminf(fmaxf(src[i], -65504.f), 65504.f));
+}
+
 int row_norm(const RowNorm& r, cudaStream_t st) {
   if (r.rows == 0) return FS2_OK;
   FS2_REQUIRE(r.ldx % 4 == 0 && (!r.out || r.ldo % 4 == 0) && (!r.resid || r.ldr % 4 == 0), "row_norm: strides must be 16-byte multiples");
+  FS2_REQUIRE(!r.out_h || (r.ldo_h % 4 == 0 && (reinterpret_cast<uintptr_t>(r.out_h) & 7) == 0), "row_norm: fp16 output rows must be 8-byte aligned");
   int grid = (int)((r.rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
   if (r.C == 256) row_norm_kernel<2><<<grid, 256, 0, st>>>(r);
   else if (r.C == 384) row_norm_kernel<3><<<grid, 256, 0, st>>>(r);
   else { set_error("row_norm: C=%d unsupported (256 or 384)", r.C); return FS2_ERR_INVALID; }
+  FS2_LAUNCH_CHECK();
+  return FS2_OK;
+}
+
+int to_half(const float* src, __half* dst, long n, cudaStream_t st) {
+  if (n == 0) return FS2_OK;
+  to_half_kernel<<<grid_for(n, 256), 256, 0, st>>>(src, dst, n);
   FS2_LAUNCH_CHECK();
   return FS2_OK;
 }

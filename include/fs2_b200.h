@@ -51,10 +51,15 @@ extern "C" {
  *     fp32-class accuracy) because their outputs feed round() / bucketize().
  *   FS2_MATH_3XTF32: every dense contraction in 3xTF32 on the tensor cores (decoder side too); attention cores on
  *     the exact-fp32 kernel.  ~1e-4-class results at about a third of the fp32 mode's run time.
+ *   FS2_MATH_F16: FS2_MATH_TF32 with the decoder's conv-FFN (conv k=9 -> ReLU -> conv k=1, two thirds of the
+ *     model's flops) on kind::f16: fp16 copies of the activations and weights (the same 10-bit mantissa as tf32,
+ *     round-to-nearest instead of truncation, values clamped to +-65504), fp32 accumulation, twice the MMA rate.
+ *     Same stated tolerance as FS2_MATH_TF32; opt-in.
  * Normalisation, softmax statistics, gathers and every integer kernel are fp32 / exact in all modes. */
 #define FS2_MATH_FP32 0
 #define FS2_MATH_TF32 1
 #define FS2_MATH_3XTF32 2
+#define FS2_MATH_F16 3
 
 typedef struct fs2_handle fs2_handle;
 

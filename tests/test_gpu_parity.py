@@ -6,6 +6,7 @@ Tolerances (stated, per SURVEY.md section 7 "fp32 tolerance vs tensor cores"):
                   vs fp64 is 2.4e-6, long K=3456 fp32 reductions in a different order add ~1e-5)
   FS2_MATH_TF32 : max-abs <= 1e-2, mean-abs <= 1e-3 on mels (tf32 operands: 10-bit mantissa)
   FS2_MATH_3XTF32: max-abs <= 1e-3, mean-abs <= 1e-4 (operand rounding compensated; tensor-core accumulation rounds to zero)
+  FS2_MATH_F16  : as FS2_MATH_TF32 (the decoder conv-FFN reads fp16 copies: the same 10-bit mantissa, round-to-nearest)
   integer outputs (durations, bucket ids, LengthRegulator rows): bit-exact in both modes.
 """
 import numpy as np
@@ -19,8 +20,10 @@ from oracle import fs2_oracle as O
 
 pytestmark = pytest.mark.gpu
 T_ = torch.from_numpy
-TOL = {"fp32": dict(max=1e-4, mean=1e-5), "tf32": dict(max=1e-2, mean=1e-3), "3xtf32": dict(max=1e-3, mean=1e-4)}
-PRECISIONS = ["fp32", "tf32", "3xtf32"]
+TOL = {"fp32": dict(max=1e-4, mean=1e-5), "tf32": dict(max=1e-2, mean=1e-3), "3xtf32": dict(max=1e-3, mean=1e-4),
+       "f16": dict(max=1e-2, mean=1e-3)}
+PRECISIONS = ["fp32", "tf32", "3xtf32", "f16"]
+LOSS_REL = {"fp32": 1e-4, "tf32": 2e-3, "3xtf32": 3e-4, "f16": 2e-3}     # relative tolerance on the seven loss terms
 
 
 def close(got, want, tol, what=""):
@@ -121,7 +124,7 @@ def test_golden_forward_loss(models, golden, prec):
     import json, os
     from conftest import GOLDEN
     assert [list(r.keys())[0] for r in report] == json.load(open(os.path.join(GOLDEN, "report_keys.json")))
-    rel = {"fp32": 1e-4, "tf32": 2e-3, "3xtf32": 3e-4}[prec]
+    rel = LOSS_REL[prec]
     got = np.array([list(r.values())[0] for r in report])
     assert np.all(np.abs(got - gl["report"]) <= rel * np.maximum(1.0, np.abs(gl["report"]))), (got, gl["report"])
     assert abs(float(loss) - float(gl["loss"])) <= rel * max(1.0, abs(float(gl["loss"])))
@@ -136,7 +139,7 @@ def test_reference_unit_test_twin(models, golden, prec):
     y = torch.ones(2, 100, 80).cuda(); dur = torch.ones(2, 100).cuda(); e = torch.ones(2, 100).cuda(); p = torch.ones(2, 100).cuda()
     with torch.no_grad():
         loss, report = models[prec](x, il, y, il.clone(), dur, e, p)
-    rel = {"fp32": 1e-4, "tf32": 2e-3, "3xtf32": 3e-4}[prec]
+    rel = LOSS_REL[prec]
     got = np.array([list(r.values())[0] for r in report])
     assert np.all(np.abs(got - gl["report"]) <= rel * np.maximum(1.0, np.abs(gl["report"]))), (got, gl["report"])
 
@@ -280,6 +283,28 @@ def test_tap_gemm_3xtf32_is_fp32_class(shape):
     close(got3, y, dict(max=5e-4, mean=5e-5), str(shape))
 
 
+@pytest.mark.parametrize("shape", [(3, 70, 384, 1024, 9, 1), (2, 333, 1024, 384, 1, 0), (5, 41, 256, 256, 3, 1),
+                                   (1, 128, 64, 128, 1, 0), (4, 300, 384, 1024, 9, 1), (1, 7, 1024, 384, 1, 0)])
+def test_tap_gemm_f16_vs_torch(shape):
+    """kind::f16 family (decoder conv-FFN in FS2_MATH_F16): fp16 copies of x and w, fp32 accumulation.  Against
+    float64 on the *same fp16-rounded operands* only the accumulation order / rounding remains (max 5e-4, mean 5e-5,
+    as for 3xTF32), which pins descriptors, swizzle and the K stepping; against the unrounded operands the error is
+    the 10-bit-mantissa class of the tf32 family (max 1e-2, mean 1e-3)."""
+    B, L, K, N, taps, act = shape
+    g = torch.Generator().manual_seed(hash(shape) & 0xffff)
+    x = torch.randn(B, L, K, generator=g) * 2; w = torch.randn(N, K, taps, generator=g) / (K * taps) ** 0.5
+    bias = torch.randn(N, generator=g); resid = torch.randn(B, L, N, generator=g)
+
+    def ref(xx, ww):
+        y = torch.nn.functional.conv1d(xx.transpose(1, 2).double(), ww.double(), bias.double(), padding=(taps - 1) // 2).transpose(1, 2)
+        y = torch.relu(y) if act == 1 else y
+        return (y + resid.double()).float()
+    wp = w.permute(2, 0, 1).contiguous().cuda()
+    got = _tap_gemm(_lib.MATH_MODES["f16"], x.cuda(), wp, bias.cuda(), act, resid.cuda())
+    close(got, ref(x.half().float(), w.half().float()), dict(max=5e-4, mean=5e-5), f"{shape} vs fp16-rounded operands")
+    close(got, ref(x, w), dict(max=1e-2, mean=1e-3), f"{shape} vs exact operands")
+
+
 @pytest.mark.parametrize("prec", ["fp32", "tf32"])
 @pytest.mark.parametrize("C,L,masked", [(256, 100, True), (384, 333, True), (384, 800, False), (256, 37, False)])
 def test_attention_vs_torch(prec, C, L, masked):
@@ -418,7 +443,7 @@ def test_cuda_graph_replay_matches_eager(models, prec):
 
 
 def test_random_shapes_tf32_vs_fp32_paths(models):
-    """Shape stress: 24 random (B, T, L) with ragged lengths through both kernel families (the exact-fp32 CUDA-core
+    """Shape stress: 24 random (B, T, L) with ragged lengths through the kernel families (tf32 and f16 vs fp32) (the exact-fp32 CUDA-core
     path is already pinned to the oracle; the tensor-core path must agree with it within the tf32 tolerance).  Catches
     tile-boundary bugs: packed tail tiles, partial attention tiles, single-tile cases, odd L (transposed-V row pitch)."""
     g = torch.Generator().manual_seed(2024)
@@ -433,10 +458,11 @@ def test_random_shapes_tf32_vs_fp32_paths(models):
         args = [bt[k].cuda() for k in ("xs", "ilens", "olens", "ds", "es", "ps")]
         with torch.no_grad():
             ref = models["fp32"]._forward(*args, is_inference=False)
-            got = models["tf32"]._forward(*args, is_inference=False)
+            gots = {prec: models[prec]._forward(*args, is_inference=False) for prec in ("tf32", "f16")}
         valid = (torch.arange(L)[None] < bt["olens"][:, None]).cuda()
-        for name, r, o in (("before", ref[0], got[0]), ("after", ref[1], got[1])):
-            err = (r - o).abs()[valid]
-            assert torch.isfinite(o).all(), (case, name)
-            assert float(err.max()) <= 1e-2 and float(err.mean()) <= 1e-3, (case, B, T, L, name, float(err.max()), float(err.mean()))
-        assert float((ref[2] - got[2]).abs().max()) <= 2e-4, (case, "d_outs")
+        for prec, got in gots.items():
+            for name, r, o in (("before", ref[0], got[0]), ("after", ref[1], got[1])):
+                err = (r - o).abs()[valid]
+                assert torch.isfinite(o).all(), (case, prec, name)
+                assert float(err.max()) <= 1e-2 and float(err.mean()) <= 1e-3, (case, prec, B, T, L, name, float(err.max()), float(err.mean()))
+            assert float((ref[2] - got[2]).abs().max()) <= 2e-4, (case, prec, "d_outs")
