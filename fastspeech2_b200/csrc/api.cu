@@ -26,7 +26,9 @@ struct Dense {           // one Linear / Conv1d in kernel layout
   const float* w = nullptr;     // [taps][N][K]
   const float* w_hi = nullptr;  // 3xTF32 split of w (encoder / predictors only)
   const float* w_lo = nullptr;
-  const __half* w_h = nullptr;  // fp16 copy (decoder conv-FFN, FS2_MATH_F16)
+  const __half* w_h = nullptr;  // fp16 copy (decoder side, FS2_MATH_F16)
+  const __half* w_hi_h = nullptr;  // fp16 hi / lo split (3xF16, the default error-compensated family)
+  const __half* w_lo_h = nullptr;
   const float* bias = nullptr;  // [N] or nullptr
   int N = 0, K = 0, taps = 1;
 };
@@ -127,7 +129,7 @@ inline int round4(int x) { return (x + 3) & ~3; }
 TapGemm make_gemm(const Dense& d, const float* x, int ldx, int B, int L, int act, const float* resid, int ldr, float* out,
                   int ldo) {
   TapGemm g;
-  g.x = x; g.ldx = ldx; g.B = B; g.L = L; g.K = d.K; g.w = d.w; g.w_hi = d.w_hi; g.w_lo = d.w_lo; g.w_h = d.w_h; g.bias = d.bias; g.N = d.N; g.taps = d.taps;
+  g.x = x; g.ldx = ldx; g.B = B; g.L = L; g.K = d.K; g.w = d.w; g.w_hi = d.w_hi; g.w_lo = d.w_lo; g.w_h = d.w_h; g.w_hi_h = d.w_hi_h; g.w_lo_h = d.w_lo_h; g.bias = d.bias; g.N = d.N; g.taps = d.taps;
   g.act = act; g.resid = resid; g.ldr = ldr; g.out = out; g.ldo = ldo;
   return g;
 }
@@ -268,6 +270,10 @@ struct Packer {
     float* lo = bump.floats(n);
     if (!counting) { int rc = split_tf32(d->w, hi, lo, (long)n, st); if (rc) return rc; }
     d->w_hi = hi; d->w_lo = lo;
+    __half* hh = (__half*)bump.bytes(n * sizeof(__half));
+    __half* lh = (__half*)bump.bytes(n * sizeof(__half));
+    if (!counting) { int rc = split_f16(d->w, hh, lh, (long)n, st); if (rc) return rc; }
+    d->w_hi_h = hh; d->w_lo_h = lh;
     return FS2_OK;
   }
   // fp16 copy for the f16 family (gemm_tc.cu, HALF)
@@ -650,9 +656,13 @@ int fs2_op_tap_gemm(int math_mode, const float* x, int B, int L, int K, const fl
   // single-operator entry for the 3xTF32 family (tests): split the weights on the fly
   const size_t n = (size_t)N * K * taps;
   float* tmp = nullptr;
-  FS2_CUDA_CHECK(cudaMallocAsync(&tmp, 2 * n * sizeof(float), st));
+  FS2_CUDA_CHECK(cudaMallocAsync(&tmp, 3 * n * sizeof(float) + 64, st));
   int rc = split_tf32(w, tmp, tmp + n, (long)n, st);
   d.w_hi = tmp; d.w_lo = tmp + n;
+  __half* th = reinterpret_cast<__half*>(tmp + 2 * n);
+  __half* tl = th + ((n + 7) & ~(size_t)7);
+  if (!rc) rc = split_f16(w, th, tl, (long)n, st);
+  d.w_hi_h = th; d.w_lo_h = tl;
   if (!rc) rc = dense(make_gemm(d, x, K, B, L, act, resid, N, out, N), math_mode, st, P_DEC_W1);
   cudaFreeAsync(tmp, st);
   return rc;

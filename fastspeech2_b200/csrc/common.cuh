@@ -60,6 +60,8 @@ struct TapGemm {
   // f16 family (tap_gemm_f16): fp16 copies of the activations (row stride ldx_h halfs) and of w; the result goes to
   // out (fp32, with the optional residual) and / or out_h (fp16, row stride ldo_h halfs, for the next f16 GEMM)
   const __half* x_h = nullptr; int ldx_h = 0; const __half* w_h = nullptr; __half* out_h = nullptr; int ldo_h = 0;
+  // 3xF16 (the default error-compensated family): w split into fp16 hi = rn(w), lo = rn(w - hi)
+  const __half* w_hi_h = nullptr; const __half* w_lo_h = nullptr;
 };
 int tap_gemm_fp32(const TapGemm& g, cudaStream_t st);
 int tap_gemm_tf32(const TapGemm& g, cudaStream_t st);   // tcgen05 + TMA (gemm_tc.cu)
@@ -68,7 +70,8 @@ int gemm_ln_tf32(const TapGemm& g, cudaStream_t st);
 int tap_gemm_3xtf32(const TapGemm& g, cudaStream_t st); // same kernel, error-compensated split operands
 int split_tf32(const float* src, float* hi, float* lo, long n, cudaStream_t st);
 int tap_gemm_f16(const TapGemm& g, cudaStream_t st);    // same kernel, kind::f16 on x_h / w_h, fp32 accumulation
-int to_half(const float* src, __half* dst, long n, cudaStream_t st);   // round to nearest, clamped to +-65504
+int to_half(const float* src, __half* dst, long n, cudaStream_t st);
+int split_f16(const float* src, __half* hi, __half* lo, long n, cudaStream_t st);   // round to nearest, clamped to +-65504
 constexpr int MATH_3XTF32 = FS2_MATH_3XTF32;            // also what FS2_MATH_TF32 uses for the encoder + predictors
 
 // Row LayerNorm with the fusions the path needs.

@@ -38,7 +38,15 @@
 // spent on padding (at L = 800 that was 12 %).  Plain GEMMs (taps == 1) tile the flat [B*L, K] matrix.
 // Every mbarrier wait is bounded: a pipeline bug traps instead of hanging the GPU.
 //
-// HALF = true (FS2_MATH_F16, the decoder's conv-FFN): the same pipeline on fp16 copies of the activations and weights
+// PRECISE && HALF ("3xF16", the default error-compensated family): the activations still arrive as fp32 (two 32-float
+// TMA boxes per 64-element step), the split warps turn them into fp16 hi = rn(x) and lo = rn(x - hi) tiles in place
+// (read everything, barrier, write: the fp16 tiles alias the fp32 landing zone), the weights are split into fp16
+// hi / lo at load time, and the three products run on kind::f16.  hi + lo carries 22 mantissa bits like the tf32 split
+// (lo may be an fp16 subnormal: its absolute error, 3e-8, is below fp32 epsilon for O(1) activations and far below the
+// tensor core's accumulation error), but a pipeline step covers twice the K for the same 12 MMAs and the same shared-
+// memory traffic, which is what bounds this kernel at BN = 128.
+//
+// HALF = true, PRECISE = false (FS2_MATH_F16, the decoder's conv-FFN): the same pipeline on fp16 copies of the activations and weights
 // with kind::f16 -- a 128-byte swizzle row then holds 64 K-elements and one MMA covers K = 16, so a pipeline step moves
 // the same bytes and issues the same four MMAs but does twice the work; the epilogue can emit the result as fp16 for
 // the next f16 GEMM (conv k=9 -> ReLU -> conv k=1).  fp16 has tf32's 10-bit mantissa; accumulation stays fp32.
@@ -79,6 +87,7 @@ template <int BN, bool PRECISE, bool HALF = false>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = (PRECISE ? 2 : 1) * (A_BYTES + B_BYTES);   // [A(hi)][A lo][B hi][B lo]
+  static constexpr bool SPLIT16 = PRECISE && HALF;        // fp32 A boxes (k0.., k0+32..) land in [A][A lo] and are re-written as fp16 hi / lo
   static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
   static constexpr int ACC_STRIDE = pow2_at_least(BN);     // TMEM columns per accumulator buffer
   static constexpr int NACC = 512 / ACC_STRIDE > 4 ? 4 : 512 / ACC_STRIDE;   // accumulator buffers in flight (2 for BN > 128, else 4)
@@ -88,11 +97,11 @@ struct Cfg {
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
   static constexpr uint32_t IDESC = HALF ? idesc_f16(BM, BN) : idesc_tf32(BM, BN);
   static constexpr int BKE = HALF ? 2 * BK : BK;           // K elements per pipeline step
-  static_assert(!(HALF && PRECISE), "the f16 family has no split-operand variant");
+
   static constexpr int A_LO = A_BYTES;                                  // offsets inside a stage
   static constexpr int B_HI = PRECISE ? 2 * A_BYTES : A_BYTES;
   static constexpr int B_LO = B_HI + B_BYTES;
-  static constexpr uint32_t TX_BYTES = A_BYTES + (PRECISE ? 2 : 1) * B_BYTES;
+  static constexpr uint32_t TX_BYTES = (SPLIT16 ? 2 : 1) * A_BYTES + (PRECISE ? 2 : 1) * B_BYTES;
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128");
   static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment");
   static_assert(STAGES >= 2 && TMEM_COLS <= 512, "resources");
@@ -163,12 +172,14 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           mbar_expect_tx(&full_bar[slot], C::TX_BYTES);
           if (packed < 0) {
             tma_load_3d(st, &tmap_a, &full_bar[slot], k0, t0 + j - p.pad, b);
+            if (C::SPLIT16) tma_load_3d(st + C::A_LO, &tmap_a, &full_bar[slot], k0 + BK, t0 + j - p.pad, b);
           } else {
             // eight 16-row boxes: granule g belongs to utterance b + g / gn (zero-filled past the batch or past L)
             for (int g = 0; g < 8; ++g) {
               const int u = g / p.gn, gi = g - u * p.gn;
               const int bb = u < p.upt ? b + u : p.B;      // p.B is out of bounds in dim 2 -> the box is all zeros
               tma_load_3d(st + g * (16 * 128), &tmap_a16, &full_bar[slot], k0, t0 + gi * 16 + j - p.pad, bb);
+              if (C::SPLIT16) tma_load_3d(st + C::A_LO + g * (16 * 128), &tmap_a16, &full_bar[slot], k0 + BK, t0 + gi * 16 + j - p.pad, bb);
             }
           }
           tma_load_3d(st + C::B_HI, &tmap_b, &full_bar[slot], k0, n0, j);
@@ -194,9 +205,15 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           for (int k = 0; k < BK / UMMA_K; ++k) {  // +32 bytes along K inside the swizzle row = +2 in descriptor units
             if (PRECISE) {
               const uint64_t a_lo = make_sw128_kmajor_desc(base + C::A_LO), b_lo = make_sw128_kmajor_desc(base + C::B_LO);
-              umma_tf32(d, a_lo + 2 * k, b_hi + 2 * k, C::IDESC, (s | k) != 0);   // small terms first
-              umma_tf32(d, a_hi + 2 * k, b_lo + 2 * k, C::IDESC, 1);
-              umma_tf32(d, a_hi + 2 * k, b_hi + 2 * k, C::IDESC, 1);
+              if (HALF) {
+                umma_f16(d, a_lo + 2 * k, b_hi + 2 * k, C::IDESC, (s | k) != 0);  // small terms first
+                umma_f16(d, a_hi + 2 * k, b_lo + 2 * k, C::IDESC, 1);
+                umma_f16(d, a_hi + 2 * k, b_hi + 2 * k, C::IDESC, 1);
+              } else {
+                umma_tf32(d, a_lo + 2 * k, b_hi + 2 * k, C::IDESC, (s | k) != 0);
+                umma_tf32(d, a_hi + 2 * k, b_lo + 2 * k, C::IDESC, 1);
+                umma_tf32(d, a_hi + 2 * k, b_hi + 2 * k, C::IDESC, 1);
+              }
             } else if (HALF) {
               umma_f16(d, a_hi + 2 * k, b_hi + 2 * k, C::IDESC, (s | k) != 0);
             } else {
@@ -324,14 +341,42 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         mbar_wait(&full_bar[slot], round & 1);
         float4* a = reinterpret_cast<float4*>(tiles + (size_t)slot * C::STAGE_BYTES);
         float4* lo = reinterpret_cast<float4*>(tiles + (size_t)slot * C::STAGE_BYTES + C::A_LO);
+        if (C::SPLIT16) {
+          // thread == tile row.  Source: two fp32 tiles (k 0..31 at `a`, k 32..63 at `lo`), 128-byte rows, 16-byte chunk c
+          // of row r stored at chunk c ^ (r & 7).  Destination: fp16 hi tile over `a`, fp16 lo tile over `lo`, same
+          // swizzle, chunk cd = k / 8.  Everything is read before anything is overwritten (the tiles alias).
+          const int r = tid, sw = r & 7;
+          float4 x[16];
 #pragma unroll
-        for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
-          const int idx = tid + i * 128;
-          const float4 x = a[idx];
-          float4 h, l;
-          h.x = hi_tf32(x.x); h.y = hi_tf32(x.y); h.z = hi_tf32(x.z); h.w = hi_tf32(x.w);
-          l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
-          a[idx] = h; lo[idx] = l;
+          for (int c = 0; c < 8; ++c) { x[c] = a[r * 8 + (c ^ sw)]; x[8 + c] = lo[r * 8 + (c ^ sw)]; }
+          named_bar_sync(2, 128);
+          uint4* hi_t = reinterpret_cast<uint4*>(a);
+          uint4* lo_t = reinterpret_cast<uint4*>(lo);
+#pragma unroll
+          for (int cd = 0; cd < 8; ++cd) {
+            const float f[8] = {x[2 * cd].x, x[2 * cd].y, x[2 * cd].z, x[2 * cd].w, x[2 * cd + 1].x, x[2 * cd + 1].y, x[2 * cd + 1].z, x[2 * cd + 1].w};
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float f0 = fminf(fmaxf(f[2 * e], -65504.f), 65504.f), f1 = fminf(fmaxf(f[2 * e + 1], -65504.f), 65504.f);
+              const __half2 h2 = __floats2half2_rn(f0, f1);
+              const float2 hf = __half22float2(h2);
+              const __half2 l2 = __floats2half2_rn(f0 - hf.x, f1 - hf.y);
+              hw[e] = *reinterpret_cast<const uint32_t*>(&h2); lw[e] = *reinterpret_cast<const uint32_t*>(&l2);
+            }
+            hi_t[r * 8 + (cd ^ sw)] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            lo_t[r * 8 + (cd ^ sw)] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
+            const int idx = tid + i * 128;
+            const float4 x = a[idx];
+            float4 h, l;
+            h.x = hi_tf32(x.x); h.y = hi_tf32(x.y); h.z = hi_tf32(x.z); h.w = hi_tf32(x.w);
+            l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
+            a[idx] = h; lo[idx] = l;
+          }
         }
         fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core
         __syncwarp();
@@ -382,14 +427,15 @@ int launch(const TapGemm& g, cudaStream_t st) {
   CUtensorMap ma, mb, mb_lo, ma16;
   int rc;
   const int esz = HALF ? 2 : 4;
-  const void* xa = HALF ? (const void*)g.x_h : (const void*)g.x;
-  const uint64_t row_bytes = HALF ? (uint64_t)g.ldx_h * 2 : (uint64_t)g.ldx * 4;
+  constexpr bool AH = HALF && !PRECISE;                   // 3xF16 reads the fp32 activations and splits them in shared memory
+  const void* xa = AH ? (const void*)g.x_h : (const void*)g.x;
+  const uint64_t row_bytes = AH ? (uint64_t)g.ldx_h * 2 : (uint64_t)g.ldx * 4;
   if (g.taps == 1) {  // flat [B*L, K]
     const uint64_t M = (uint64_t)g.B * g.L;
     p.L = (int)M; p.tiles_per_utt = 0;
     p.m_tiles = (int)((M + BM - 1) / BM);
     p.B = 1; p.full = 0; p.gn = 1; p.upt = 1; p.full_tiles = 0;
-    if ((rc = make_map(&ma, xa, g.K, M, 1, row_bytes, row_bytes * M, BM, HALF))) return rc;
+    if ((rc = make_map(&ma, xa, g.K, M, 1, row_bytes, row_bytes * M, BM, AH))) return rc;
     ma16 = ma;
   } else {            // per-utterance tiles: shifted boxes zero-fill outside [0, L)
     p.L = g.L; p.tiles_per_utt = (g.L + BM - 1) / BM;
@@ -400,13 +446,13 @@ int launch(const TapGemm& g, cudaStream_t st) {
     if (tail && p.upt == 1) { p.full += 1; tail = 0; p.gn = 1; }   // tail > 64 rows: nothing to share, keep one ordinary (partly empty) tile
     p.full_tiles = p.full * g.B;
     p.m_tiles = p.full_tiles + (tail ? (g.B + p.upt - 1) / p.upt : 0);
-    if ((rc = make_map(&ma, xa, g.K, g.L, g.B, row_bytes, row_bytes * g.L, BM, HALF))) return rc;
-    if ((rc = make_map(&ma16, xa, g.K, g.L, g.B, row_bytes, row_bytes * g.L, 16, HALF))) return rc;
+    if ((rc = make_map(&ma, xa, g.K, g.L, g.B, row_bytes, row_bytes * g.L, BM, AH))) return rc;
+    if ((rc = make_map(&ma16, xa, g.K, g.L, g.B, row_bytes, row_bytes * g.L, 16, AH))) return rc;
   }
   p.n_tiles = g.N / BN;
-  const void* w_hi = HALF ? (const void*)g.w_h : PRECISE ? (const void*)g.w_hi : (const void*)g.w;
+  const void* w_hi = PRECISE ? (HALF ? (const void*)g.w_hi_h : (const void*)g.w_hi) : HALF ? (const void*)g.w_h : (const void*)g.w;
   if ((rc = make_map(&mb, w_hi, g.K, g.N, g.taps, (uint64_t)g.K * esz, (uint64_t)g.K * esz * g.N, BN, HALF))) return rc;
-  if ((rc = make_map(&mb_lo, PRECISE ? (const void*)g.w_lo : w_hi, g.K, g.N, g.taps, (uint64_t)g.K * esz, (uint64_t)g.K * esz * g.N, BN, HALF))) return rc;
+  if ((rc = make_map(&mb_lo, PRECISE ? (HALF ? (const void*)g.w_lo_h : (const void*)g.w_lo) : w_hi, g.K, g.N, g.taps, (uint64_t)g.K * esz, (uint64_t)g.K * esz * g.N, BN, HALF))) return rc;
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < sm_count() ? total : sm_count();
   tap_gemm_tf32_kernel<BN, PRECISE, HALF><<<grid, C::THREADS, C::SMEM, st>>>(ma, mb, mb_lo, ma16, p);
@@ -454,8 +500,16 @@ int tap_gemm_tf32(const TapGemm& g, cudaStream_t st) {
 int tap_gemm_3xtf32(const TapGemm& g, cudaStream_t st) {
   int rc = check_common(g, "tap_gemm_3xtf32");
   if (rc) return rc;
-  FS2_REQUIRE(g.w_hi && g.w_lo, "tap_gemm_3xtf32: split weights missing");
   if ((long)g.B * g.L == 0) return FS2_OK;
+  static int f16 = -1;    // FS2_PRECISE_F16=0 falls back to the tf32 split (kept for A/B measurements)
+  if (f16 < 0) { const char* e = getenv("FS2_PRECISE_F16"); f16 = e ? atoi(e) : 1; }
+  if (f16 && g.w_hi_h && g.w_lo_h && g.K % 8 == 0) {
+    if (g.N % 128 == 0) return launch<128, true, true>(g, st);
+    if (g.N % 96 == 0) return launch<96, true, true>(g, st);
+    if (g.N % 80 == 0) return launch<80, true, true>(g, st);
+    if (g.N % 64 == 0) return launch<64, true, true>(g, st);
+  }
+  FS2_REQUIRE(g.w_hi && g.w_lo, "tap_gemm_3xtf32: split weights missing");
   // narrower tiles than the plain kernel: the stage holds four operand tiles and the encoder's M is small
   if (g.N % 128 == 0) return launch<128, true>(g, st);
   if (g.N % 96 == 0) return launch<96, true>(g, st);
@@ -481,6 +535,24 @@ int tap_gemm_f16(const TapGemm& g, cudaStream_t st) {
   if (g.N % 80 == 0) return launch<80, false, true>(g, st);
   set_error("%s: N=%d has no supported tile width (multiples of 80, 128 or 192)", who, g.N);
   return FS2_ERR_INVALID;
+}
+
+namespace {
+__global__ void split_f16_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo, long n) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float x = fminf(fmaxf(src[i], -65504.f), 65504.f);
+    const __half h = __float2half_rn(x);
+    hi[i] = h; lo[i] = __float2half_rn(x - __half2float(h));
+  }
+}
+}  // namespace
+
+int split_f16(const float* src, __half* hi, __half* lo, long n, cudaStream_t st) {
+  if (n == 0) return FS2_OK;
+  long blocks = (n + 255) / 256;
+  split_f16_kernel<<<(int)(blocks > 1184 ? 1184 : blocks), 256, 0, st>>>(src, hi, lo, n);
+  FS2_LAUNCH_CHECK();
+  return FS2_OK;
 }
 
 int split_tf32(const float* src, float* hi, float* lo, long n, cudaStream_t st) {
