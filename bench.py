@@ -466,7 +466,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default=os.environ.get("FS2_PRECISION", "tf32"), choices=["fp32", "tf32", "3xtf32", "f16"])
+    ap.add_argument("--precision", default=os.environ.get("FS2_PRECISION", "f16"), choices=["fp32", "tf32", "3xtf32", "f16"])
     ap.add_argument("--cpu-sample-batch", type=int, default=8)
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (default), 0: eager launches")
     args = ap.parse_args()

@@ -51,6 +51,7 @@ struct Profiler {
   std::vector<ProfRec> recs;
 };
 static thread_local Profiler* t_prof = nullptr;
+static thread_local __half* t_split_ws = nullptr;   // scratch of the running stage for the 3xF16 activation planes
 struct ProfScope {
   ProfRec r; bool live; cudaStream_t st;
   ProfScope(int cls, double flop, double bytes, cudaStream_t s) : live(t_prof && t_prof->on), st(s) {
@@ -111,6 +112,7 @@ int dense(const TapGemm& g, int math_mode, cudaStream_t st, int cls) {
                4.0 * (M * g.K + (double)g.taps * g.N * g.K + M * g.N * (g.resid ? 2 : 1)), st);
   if (math_mode == FS2_MATH_TF32 && g.ln_gamma) return gemm_ln_tf32(g, st);   // fp16 operands / fp16 copy handled inside
   if (g.x_h) return tap_gemm_f16(g, st);
+  if (math_mode == MATH_3XTF32) { TapGemm gs = g; gs.split_ws = t_split_ws; return tap_gemm_3xtf32(gs, st); }
   return math_mode == MATH_3XTF32 ? tap_gemm_3xtf32(g, st) : math_mode == FS2_MATH_TF32 ? tap_gemm_tf32(g, st) : tap_gemm_fp32(g, st);
 }
 int norm_rows(const RowNorm& r, cudaStream_t st) {
@@ -391,15 +393,21 @@ struct Packer {
   }
 };
 
-struct EncodePlan { float *x, *y, *qkv, *ctx, *hid, *t1, *t2; };
+inline int64_t max_width(const fs2_config& c) {
+  int64_t w = c.adim;
+  for (int v : {c.ddim, c.eunits, c.dunits, c.pred_chans, c.postnet_chans, c.odim}) if (v > w) w = v;
+  return w;
+}
+struct EncodePlan { float *x, *y, *qkv, *ctx, *hid, *t1, *t2; __half* split; };
 EncodePlan plan_encode(const fs2_config& c, Bump& b, int64_t rows) {
   EncodePlan p;
   p.x = b.floats(rows * c.adim); p.y = b.floats(rows * c.adim); p.qkv = b.floats(rows * 3 * c.adim);
   p.ctx = b.floats(rows * c.adim); p.hid = b.floats(rows * c.eunits);
   p.t1 = b.floats(rows * c.pred_chans); p.t2 = b.floats(rows * c.pred_chans);
+  p.split = (__half*)b.floats(rows * max_width(c));     // 3xF16 activation planes (hi + lo = the bytes of the widest fp32 operand)
   return p;
 }
-struct DecodePlan { float *hm2, *x, *y, *qkv, *vt, *ctx, *hid, *t1, *t2, *q1, *q2; __half *xh, *before_h; };
+struct DecodePlan { float *hm2, *x, *y, *qkv, *vt, *ctx, *hid, *t1, *t2, *q1, *q2; __half *xh, *before_h, *split; };
 DecodePlan plan_decode(const fs2_config& c, Bump& b, int64_t rows, int B, int L) {
   DecodePlan p;
   p.hm2 = b.floats(rows * c.adim);
@@ -410,6 +418,7 @@ DecodePlan plan_decode(const fs2_config& c, Bump& b, int64_t rows, int B, int L)
   p.q1 = b.floats(rows * c.postnet_chans); p.q2 = b.floats(rows * c.postnet_chans);
   p.xh = (__half*)b.bytes((size_t)rows * c.ddim * sizeof(__half));   // FS2_MATH_F16: fp16 copy of the current block input / conv-FFN input
   p.before_h = (__half*)b.bytes((size_t)rows * c.odim * sizeof(__half));   // FS2_MATH_F16: fp16 copy of before_outs for the Postnet
+  p.split = (__half*)b.floats(rows * max_width(c));
   return p;
 }
 
@@ -527,6 +536,7 @@ int fs2_encode(fs2_handle* h, const int64_t* xs, const int64_t* ilens, int B, in
   Bump b(ws, ws_bytes);
   EncodePlan p = plan_encode(c, b, (int64_t)B * Tmax);
   if (!b.ok()) { set_error("fs2_encode: workspace too small (%zu < %zu)", ws_bytes, b.off); return FS2_ERR_WORKSPACE; }
+  t_split_ws = p.split;
   int rc;
   // the encoder's output feeds round() in the duration predictor: exact fp32 FMA in FS2_MATH_FP32,
   // error-compensated 3xTF32 on the tensor cores in FS2_MATH_TF32 (never plain tf32)
@@ -567,6 +577,7 @@ int fs2_decode(fs2_handle* h, const float* hm, const int64_t* olens, const float
   Bump b(ws, ws_bytes);
   DecodePlan p = plan_decode(c, b, rows, B, L);
   if (!b.ok()) { set_error("fs2_decode: workspace too small (%zu < %zu)", ws_bytes, b.off); return FS2_ERR_WORKSPACE; }
+  t_split_ws = p.split;
   const bool f16_ffn = c.math_mode == FS2_MATH_F16;                     // tf32 everywhere except the conv-FFN
   const int mode = f16_ffn ? FS2_MATH_TF32 : c.math_mode;
   const int precise = mode == FS2_MATH_FP32 ? FS2_MATH_FP32 : MATH_3XTF32;
@@ -656,13 +667,15 @@ int fs2_op_tap_gemm(int math_mode, const float* x, int B, int L, int K, const fl
   // single-operator entry for the 3xTF32 family (tests): split the weights on the fly
   const size_t n = (size_t)N * K * taps;
   float* tmp = nullptr;
-  FS2_CUDA_CHECK(cudaMallocAsync(&tmp, 3 * n * sizeof(float) + 64, st));
+  const size_t nx = (size_t)B * L * K;
+  FS2_CUDA_CHECK(cudaMallocAsync(&tmp, (3 * n + nx) * sizeof(float) + 256, st));
   int rc = split_tf32(w, tmp, tmp + n, (long)n, st);
   d.w_hi = tmp; d.w_lo = tmp + n;
   __half* th = reinterpret_cast<__half*>(tmp + 2 * n);
   __half* tl = th + ((n + 7) & ~(size_t)7);
   if (!rc) rc = split_f16(w, th, tl, (long)n, st);
   d.w_hi_h = th; d.w_lo_h = tl;
+  t_split_ws = reinterpret_cast<__half*>(tmp + 3 * n + 32);
   if (!rc) rc = dense(make_gemm(d, x, K, B, L, act, resid, N, out, N), math_mode, st, P_DEC_W1);
   cudaFreeAsync(tmp, st);
   return rc;

@@ -62,6 +62,7 @@ struct TapGemm {
   const __half* x_h = nullptr; int ldx_h = 0; const __half* w_h = nullptr; __half* out_h = nullptr; int ldo_h = 0;
   // 3xF16 (the default error-compensated family): w split into fp16 hi = rn(w), lo = rn(w - hi)
   const __half* w_hi_h = nullptr; const __half* w_lo_h = nullptr;
+  __half* split_ws = nullptr;   // scratch for the fp16 hi / lo planes of x: 2 * B*L * K halfs (= the bytes of x)
 };
 int tap_gemm_fp32(const TapGemm& g, cudaStream_t st);
 int tap_gemm_tf32(const TapGemm& g, cudaStream_t st);   // tcgen05 + TMA (gemm_tc.cu)

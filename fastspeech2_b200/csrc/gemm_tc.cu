@@ -38,13 +38,13 @@
 // spent on padding (at L = 800 that was 12 %).  Plain GEMMs (taps == 1) tile the flat [B*L, K] matrix.
 // Every mbarrier wait is bounded: a pipeline bug traps instead of hanging the GPU.
 //
-// PRECISE && HALF ("3xF16", the default error-compensated family): the activations still arrive as fp32 (two 32-float
-// TMA boxes per 64-element step), the split warps turn them into fp16 hi = rn(x) and lo = rn(x - hi) tiles in place
-// (read everything, barrier, write: the fp16 tiles alias the fp32 landing zone), the weights are split into fp16
-// hi / lo at load time, and the three products run on kind::f16.  hi + lo carries 22 mantissa bits like the tf32 split
-// (lo may be an fp16 subnormal: its absolute error, 3e-8, is below fp32 epsilon for O(1) activations and far below the
-// tensor core's accumulation error), but a pipeline step covers twice the K for the same 12 MMAs and the same shared-
-// memory traffic, which is what bounds this kernel at BN = 128.
+// PRECISE && HALF ("3xF16", the default error-compensated family): a small pre-pass (split_rows_f16_kernel) writes the
+// fp32 activations as two fp16 planes, hi = rn(x) and lo = rn(x - hi), the weights are split the same way at load
+// time, and the GEMM loads all four operand tiles by TMA and runs the three products on kind::f16 -- no split warps, no
+// shared-memory rewrite, and a pipeline step covers twice the K for the same 12 MMAs.  hi + lo carries 22 mantissa
+// bits like the tf32 split (lo may be an fp16 subnormal: its absolute error, 3e-8, is below fp32 epsilon for O(1)
+// activations and far below the tensor core's accumulation error).  The lo plane is addressed through the same tensor
+// map: plane stride = B*L rows, i.e. utterance index b + B.
 //
 // HALF = true, PRECISE = false (FS2_MATH_F16, the decoder's conv-FFN): the same pipeline on fp16 copies of the activations and weights
 // with kind::f16 -- a 128-byte swizzle row then holds 64 K-elements and one MMA covers K = 16, so a pipeline step moves
@@ -87,13 +87,14 @@ template <int BN, bool PRECISE, bool HALF = false>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = (PRECISE ? 2 : 1) * (A_BYTES + B_BYTES);   // [A(hi)][A lo][B hi][B lo]
-  static constexpr bool SPLIT16 = PRECISE && HALF;        // fp32 A boxes (k0.., k0+32..) land in [A][A lo] and are re-written as fp16 hi / lo
+  static constexpr bool SPLIT16 = PRECISE && HALF;        // A hi / lo are fp16 planes in global memory, loaded like B hi / lo
+  static constexpr bool SPLIT_WARPS = PRECISE && !HALF;    // tf32 split: four extra warps split the landed fp32 A tile in place
   static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
   static constexpr int ACC_STRIDE = pow2_at_least(BN);     // TMEM columns per accumulator buffer
   static constexpr int NACC = 512 / ACC_STRIDE > 4 ? 4 : 512 / ACC_STRIDE;   // accumulator buffers in flight (2 for BN > 128, else 4)
   static constexpr int TMEM_COLS = NACC * ACC_STRIDE;
   static constexpr int GROUPS = 2;       // epilogue warp groups (4 warps each), alternate 32-column chunks
-  static constexpr int THREADS = 64 + GROUPS * 128 + (PRECISE ? 128 : 0);
+  static constexpr int THREADS = 64 + GROUPS * 128 + (PRECISE && !HALF ? 128 : 0);
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
   static constexpr uint32_t IDESC = HALF ? idesc_f16(BM, BN) : idesc_tf32(BM, BN);
   static constexpr int BKE = HALF ? 2 * BK : BK;           // K elements per pipeline step
@@ -172,14 +173,15 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           mbar_expect_tx(&full_bar[slot], C::TX_BYTES);
           if (packed < 0) {
             tma_load_3d(st, &tmap_a, &full_bar[slot], k0, t0 + j - p.pad, b);
-            if (C::SPLIT16) tma_load_3d(st + C::A_LO, &tmap_a, &full_bar[slot], k0 + BK, t0 + j - p.pad, b);
+            if (C::SPLIT16) tma_load_3d(st + C::A_LO, &tmap_a, &full_bar[slot], k0, t0 + j - p.pad, b + p.B);
           } else {
             // eight 16-row boxes: granule g belongs to utterance b + g / gn (zero-filled past the batch or past L)
             for (int g = 0; g < 8; ++g) {
               const int u = g / p.gn, gi = g - u * p.gn;
-              const int bb = u < p.upt ? b + u : p.B;      // p.B is out of bounds in dim 2 -> the box is all zeros
-              tma_load_3d(st + g * (16 * 128), &tmap_a16, &full_bar[slot], k0, t0 + gi * 16 + j - p.pad, bb);
-              if (C::SPLIT16) tma_load_3d(st + C::A_LO + g * (16 * 128), &tmap_a16, &full_bar[slot], k0 + BK, t0 + gi * 16 + j - p.pad, bb);
+              const bool real = u < p.upt && b + u < p.B;
+              const int oob = C::SPLIT16 ? 2 * p.B : p.B;  // out of bounds in dim 2 -> the box is all zeros
+              tma_load_3d(st + g * (16 * 128), &tmap_a16, &full_bar[slot], k0, t0 + gi * 16 + j - p.pad, real ? b + u : oob);
+              if (C::SPLIT16) tma_load_3d(st + C::A_LO + g * (16 * 128), &tmap_a16, &full_bar[slot], k0, t0 + gi * 16 + j - p.pad, real ? b + u + p.B : oob);
             }
           }
           tma_load_3d(st + C::B_HI, &tmap_b, &full_bar[slot], k0, n0, j);
@@ -197,7 +199,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         const uint32_t d = tmem_base + (uint32_t)(acc * C::ACC_STRIDE);
         for (int s = 0; s < steps; ++s, ++n) {
           const int slot = n % C::STAGES, round = n / C::STAGES;
-          mbar_wait(PRECISE ? &split_bar[slot] : &full_bar[slot], round & 1);
+          mbar_wait(C::SPLIT_WARPS ? &split_bar[slot] : &full_bar[slot], round & 1);
           tcgen05_fence_after();
           const uint32_t base = smem_u32(tiles + (size_t)slot * C::STAGE_BYTES);
           const uint64_t a_hi = make_sw128_kmajor_desc(base), b_hi = make_sw128_kmajor_desc(base + C::B_HI);
@@ -331,7 +333,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
     }
-  } else if (PRECISE) {
+  } else if (C::SPLIT_WARPS) {
     // ---- operand split (the last 4 warps): A tile -> hi (in place) and lo (second buffer), same swizzled positions ----
     const int tid = threadIdx.x - (64 + 128 * C::GROUPS);      // 0..127
     int n = 0;
@@ -341,33 +343,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         mbar_wait(&full_bar[slot], round & 1);
         float4* a = reinterpret_cast<float4*>(tiles + (size_t)slot * C::STAGE_BYTES);
         float4* lo = reinterpret_cast<float4*>(tiles + (size_t)slot * C::STAGE_BYTES + C::A_LO);
-        if (C::SPLIT16) {
-          // thread == tile row.  Source: two fp32 tiles (k 0..31 at `a`, k 32..63 at `lo`), 128-byte rows, 16-byte chunk c
-          // of row r stored at chunk c ^ (r & 7).  Destination: fp16 hi tile over `a`, fp16 lo tile over `lo`, same
-          // swizzle, chunk cd = k / 8.  Everything is read before anything is overwritten (the tiles alias).
-          const int r = tid, sw = r & 7;
-          float4 x[16];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) { x[c] = a[r * 8 + (c ^ sw)]; x[8 + c] = lo[r * 8 + (c ^ sw)]; }
-          named_bar_sync(2, 128);
-          uint4* hi_t = reinterpret_cast<uint4*>(a);
-          uint4* lo_t = reinterpret_cast<uint4*>(lo);
-#pragma unroll
-          for (int cd = 0; cd < 8; ++cd) {
-            const float f[8] = {x[2 * cd].x, x[2 * cd].y, x[2 * cd].z, x[2 * cd].w, x[2 * cd + 1].x, x[2 * cd + 1].y, x[2 * cd + 1].z, x[2 * cd + 1].w};
-            uint32_t hw[4], lw[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float f0 = fminf(fmaxf(f[2 * e], -65504.f), 65504.f), f1 = fminf(fmaxf(f[2 * e + 1], -65504.f), 65504.f);
-              const __half2 h2 = __floats2half2_rn(f0, f1);
-              const float2 hf = __half22float2(h2);
-              const __half2 l2 = __floats2half2_rn(f0 - hf.x, f1 - hf.y);
-              hw[e] = *reinterpret_cast<const uint32_t*>(&h2); lw[e] = *reinterpret_cast<const uint32_t*>(&l2);
-            }
-            hi_t[r * 8 + (cd ^ sw)] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            lo_t[r * 8 + (cd ^ sw)] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-          }
-        } else {
+        {
 #pragma unroll
           for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
             const int idx = tid + i * 128;
@@ -389,6 +365,29 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// 3xF16 pre-pass: x [rows][ldx] fp32 -> S[0] = hi plane, S[1] = lo plane, each [rows][K] fp16;
+// hi = rn(clamp(x)), lo = rn(x - hi).  One float4 per thread and step, 8-byte stores.
+__global__ void split_rows_f16_kernel(const float* __restrict__ x, int ldx, long rows, int K, __half* __restrict__ S) {
+  const int kq = K >> 2;
+  const long quads = rows * kq;
+  __half* __restrict__ lo_plane = S + rows * K;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < quads; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / kq;
+    const int c = (int)(i - r * kq) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+    const float f0 = fminf(fmaxf(v.x, -65504.f), 65504.f), f1 = fminf(fmaxf(v.y, -65504.f), 65504.f);
+    const float f2 = fminf(fmaxf(v.z, -65504.f), 65504.f), f3 = fminf(fmaxf(v.w, -65504.f), 65504.f);
+    const __half2 h01 = __floats2half2_rn(f0, f1), h23 = __floats2half2_rn(f2, f3);
+    const float2 g01 = __half22float2(h01), g23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn(f0 - g01.x, f1 - g01.y), l23 = __floats2half2_rn(f2 - g23.x, f3 - g23.y);
+    uint2 hv, lv;
+    hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+    lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+    *reinterpret_cast<uint2*>(S + r * K + c) = hv;
+    *reinterpret_cast<uint2*>(lo_plane + r * K + c) = lv;
   }
 }
 
@@ -427,15 +426,16 @@ int launch(const TapGemm& g, cudaStream_t st) {
   CUtensorMap ma, mb, mb_lo, ma16;
   int rc;
   const int esz = HALF ? 2 : 4;
-  constexpr bool AH = HALF && !PRECISE;                   // 3xF16 reads the fp32 activations and splits them in shared memory
-  const void* xa = AH ? (const void*)g.x_h : (const void*)g.x;
-  const uint64_t row_bytes = AH ? (uint64_t)g.ldx_h * 2 : (uint64_t)g.ldx * 4;
+  constexpr bool AH = HALF;
+  constexpr int planes = HALF && PRECISE ? 2 : 1;          // 3xF16: [hi plane][lo plane], each [B*L][K] fp16 (split_rows_f16)
+  const void* xa = HALF ? (PRECISE ? (const void*)g.split_ws : (const void*)g.x_h) : (const void*)g.x;
+  const uint64_t row_bytes = HALF ? (PRECISE ? (uint64_t)g.K * 2 : (uint64_t)g.ldx_h * 2) : (uint64_t)g.ldx * 4;
   if (g.taps == 1) {  // flat [B*L, K]
     const uint64_t M = (uint64_t)g.B * g.L;
     p.L = (int)M; p.tiles_per_utt = 0;
     p.m_tiles = (int)((M + BM - 1) / BM);
     p.B = 1; p.full = 0; p.gn = 1; p.upt = 1; p.full_tiles = 0;
-    if ((rc = make_map(&ma, xa, g.K, M, 1, row_bytes, row_bytes * M, BM, AH))) return rc;
+    if ((rc = make_map(&ma, xa, g.K, M, planes, row_bytes, row_bytes * M, BM, AH))) return rc;
     ma16 = ma;
   } else {            // per-utterance tiles: shifted boxes zero-fill outside [0, L)
     p.L = g.L; p.tiles_per_utt = (g.L + BM - 1) / BM;
@@ -446,8 +446,8 @@ int launch(const TapGemm& g, cudaStream_t st) {
     if (tail && p.upt == 1) { p.full += 1; tail = 0; p.gn = 1; }   // tail > 64 rows: nothing to share, keep one ordinary (partly empty) tile
     p.full_tiles = p.full * g.B;
     p.m_tiles = p.full_tiles + (tail ? (g.B + p.upt - 1) / p.upt : 0);
-    if ((rc = make_map(&ma, xa, g.K, g.L, g.B, row_bytes, row_bytes * g.L, BM, AH))) return rc;
-    if ((rc = make_map(&ma16, xa, g.K, g.L, g.B, row_bytes, row_bytes * g.L, 16, AH))) return rc;
+    if ((rc = make_map(&ma, xa, g.K, g.L, (uint64_t)g.B * planes, row_bytes, row_bytes * g.L, BM, AH))) return rc;
+    if ((rc = make_map(&ma16, xa, g.K, g.L, (uint64_t)g.B * planes, row_bytes, row_bytes * g.L, 16, AH))) return rc;
   }
   p.n_tiles = g.N / BN;
   const void* w_hi = PRECISE ? (HALF ? (const void*)g.w_hi_h : (const void*)g.w_hi) : HALF ? (const void*)g.w_h : (const void*)g.w;
@@ -503,7 +503,13 @@ int tap_gemm_3xtf32(const TapGemm& g, cudaStream_t st) {
   if ((long)g.B * g.L == 0) return FS2_OK;
   static int f16 = -1;    // FS2_PRECISE_F16=0 falls back to the tf32 split (kept for A/B measurements)
   if (f16 < 0) { const char* e = getenv("FS2_PRECISE_F16"); f16 = e ? atoi(e) : 1; }
-  if (f16 && g.w_hi_h && g.w_lo_h && g.K % 8 == 0) {
+  if (f16 && g.w_hi_h && g.w_lo_h && g.split_ws && g.K % 8 == 0) {
+    // pre-pass: fp32 activations -> fp16 hi / lo planes (rows of K contiguous halfs)
+    const long rows = (long)g.B * g.L;
+    const long quads = rows * (g.K / 4);
+    long blocks = (quads + 255) / 256;
+    split_rows_f16_kernel<<<(int)(blocks > 148 * 16 ? 148 * 16 : blocks), 256, 0, st>>>(g.x, g.ldx, rows, g.K, g.split_ws);
+    FS2_LAUNCH_CHECK();
     if (g.N % 128 == 0) return launch<128, true, true>(g, st);
     if (g.N % 96 == 0) return launch<96, true, true>(g, st);
     if (g.N % 80 == 0) return launch<80, true, true>(g, st);

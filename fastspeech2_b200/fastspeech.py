@@ -29,7 +29,7 @@ from . import _lib
 from . import length_regulator as _lr
 from .weights import ModelDims, positional_table, variance_bins
 
-DEFAULT_PRECISION = os.environ.get("FS2_PRECISION", "tf32")
+DEFAULT_PRECISION = os.environ.get("FS2_PRECISION", "f16")
 
 
 def _get(node: Any, key: str, default: Any = None) -> Any:
