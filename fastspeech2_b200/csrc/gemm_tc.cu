@@ -1,17 +1,19 @@
-// Tensor-core "tap GEMM" for sm_100a: tcgen05.mma kind::tf32 with TMEM accumulators, operands
-// staged in shared memory by TMA (cp.async.bulk.tensor, 128-byte swizzle), mbarrier pipelines,
-// persistent CTAs.
+// Tensor-core "tap GEMM" for sm_100a: tcgen05.mma (kind::tf32 or kind::f16) with TMEM accumulators,
+// operands staged in shared memory by TMA (cp.async.bulk.tensor, 128-byte swizzle), mbarrier
+// pipelines, persistent CTAs.
 //
 //   out[b,t,n] = act( sum_{j<taps} sum_{k<K} x[b, t+j-pad, k] * w[j][n][k] + bias[n] ) (+ resid[b,t,n])
 //
-// Same contract as gemm_fp32.cu (the CUDA-core family).  In FS2_MATH_TF32 this kernel serves
-//   * the decoder side in plain tf32 (one MMA per product): decoder input Linear, q|k|v and output
-//     projections, conv-FFN (k=9 and k=1), mel Linear, Postnet convolutions;
-//   * the encoder and the three predictors in *3xTF32* (PRECISE = true): every operand is split
-//     into hi = top 19 bits of x and lo = x - hi and the product is accumulated as
-//     hi*hi + lo*hi + hi*lo in the fp32 TMEM accumulator (the dropped lo*lo term is ~2^-22
-//     relative), which gives near-fp32 results on the tensor pipe.  Their outputs feed round() /
-//     bucketize(), where plain tf32 noise (~1e-3) would flip integers.
+// Same contract as gemm_fp32.cu (the CUDA-core family).  Three instantiation families:
+//   <BN, false, false>  plain tf32 (one MMA per product) on the fp32 activations themselves: the decoder side in
+//                       FS2_MATH_TF32, and the GEMMs whose A operand has no fp16 copy in FS2_MATH_F16;
+//   <BN, false, true>   kind::f16 on fp16 copies of activations and weights (FS2_MATH_F16: q|k|v, conv-FFN, mel
+//                       projection, Postnet); see "HALF" below;
+//   <BN, true,  true>   error-compensated "3xF16" (encoder and predictors in every tensor-core mode, everything in
+//                       FS2_MATH_3XTF32): their outputs feed round() / bucketize(), where 10-bit-mantissa noise
+//                       (~1e-3) would flip integers; see "PRECISE && HALF" below;
+//   <BN, true,  false>  the earlier error-compensated form, 3 x tf32 with hi = top 19 bits of x, lo = x - hi split in
+//                       shared memory by four extra warps (kept behind FS2_PRECISE_F16=0 for A/B measurements).
 //
 // Why no im2col: activations are [B, time, channel] fp32 with channels innermost, which *is* the
 // K-major A operand of a GEMM.  Tap j of a 1-D convolution is the same matrix shifted by
@@ -19,7 +21,8 @@
 // 3-D tensor map {channel, time, utterance}; rows outside [0, L) of the utterance are
 // zero-filled by the TMA unit (that is exactly Conv1d's "same" padding), and fp32 data in shared
 // memory is consumed directly by kind::tf32, so there is no conversion pass either.
-// K loop = taps x ceil(K / 32) pipeline steps of 4 (12 when PRECISE) MMAs with K = 8 each.
+// K loop = taps x ceil(K / 32) pipeline steps of 4 (12 when PRECISE) MMAs with K = 8 each (tf32; f16: ceil(K / 64)
+// steps of the same MMA count with K = 16 each).
 //
 // One persistent CTA per SM walks the 128 x BN output tiles (n fastest, so concurrently running
 // CTAs share weight tiles in L2).  Three pipelines:
@@ -29,7 +32,7 @@
 //                 32-column chunks: tcgen05.ld -> bias / ReLU / tanh / residual in registers -> four
 //                 256-bit global stores per thread (sector-complete, no shared-memory transpose, no
 //                 barriers; rows past the utterance end are predicated off)
-//   PRECISE only: warps 10-13 split each landed A tile in place into hi / lo (element-wise, so the
+//   <BN, true, false> only: warps 10-13 split each landed A tile in place into hi / lo (element-wise, so the
 //                 swizzled layout is untouched) and hand the slot to the MMA warp through a third
 //                 mbarrier; the weight hi / lo arrays are split once at load time.
 // Convolutions tile each utterance separately so the shifted boxes never cross an utterance boundary:

@@ -47,14 +47,15 @@ extern "C" {
  *   FS2_MATH_FP32: fp32 FMA on CUDA cores everywhere.
  *   FS2_MATH_TF32: tcgen05 tensor-core tiles fed by TMA with fp32 (TMEM) accumulation:
  *     decoder side (decoder embed, decoder FFT blocks incl. attention, mel linear, Postnet) in
- *     plain kind::tf32; encoder GEMMs and the three predictors in 3xTF32 (hi/lo operand split,
- *     fp32-class accuracy) because their outputs feed round() / bucketize().
- *   FS2_MATH_3XTF32: every dense contraction in 3xTF32 on the tensor cores (decoder side too); attention cores on
+ *     plain kind::tf32; encoder GEMMs and the three predictors error-compensated (every operand split into fp16
+ *     hi + lo, three kind::f16 products per term, fp32-class accuracy; "3xF16") because their outputs feed
+ *     round() / bucketize().
+ *   FS2_MATH_3XTF32: every dense contraction error-compensated on the tensor cores (decoder side too); attention cores on
  *     the exact-fp32 kernel.  ~1e-4-class results at about a third of the fp32 mode's run time.
- *   FS2_MATH_F16: FS2_MATH_TF32 with the decoder's conv-FFN (conv k=9 -> ReLU -> conv k=1, two thirds of the
- *     model's flops) on kind::f16: fp16 copies of the activations and weights (the same 10-bit mantissa as tf32,
- *     round-to-nearest instead of truncation, values clamped to +-65504), fp32 accumulation, twice the MMA rate.
- *     Same stated tolerance as FS2_MATH_TF32; opt-in.
+ *   FS2_MATH_F16 (the Python class's default): FS2_MATH_TF32 with the decoder's q|k|v projection, conv-FFN (conv k=9
+ *     -> ReLU -> conv k=1, two thirds of the model's flops), mel projection and Postnet on kind::f16: fp16 copies of
+ *     the activations and weights (the same 10-bit mantissa as tf32, round-to-nearest instead of truncation, values
+ *     clamped to +-65504), fp32 accumulation, twice the MMA rate.  Same stated tolerance as FS2_MATH_TF32.
  * Normalisation, softmax statistics, gathers and every integer kernel are fp32 / exact in all modes. */
 #define FS2_MATH_FP32 0
 #define FS2_MATH_TF32 1
@@ -171,8 +172,9 @@ int fs2_bucketize(const float* vals, const float* bins, int n_edges, int64_t n, 
 /* F.one_hot(ids, n_bins).float(): the 4th/5th return value of _forward(is_inference=True) */
 int fs2_one_hot(const int64_t* ids, int64_t n, int n_bins, float* out, void* stream);
 /* out[b,t,:] = act(sum_j x[b,t+j-pad,:] . W[j] + bias) (+ resid); W [taps][N][K].
- * math_mode selects the kernel family: FS2_MATH_FP32, FS2_MATH_TF32, or 2 = 3xTF32 (the
- * error-compensated tensor-core family FS2_MATH_TF32 uses for the encoder and the predictors).
+ * math_mode selects the kernel family: FS2_MATH_FP32 (CUDA cores), FS2_MATH_TF32 (kind::tf32), FS2_MATH_3XTF32 (the
+ * error-compensated tensor-core family every tensor-core mode uses for the encoder and the predictors) or
+ * FS2_MATH_F16 (kind::f16 on fp16 copies of x and w made on the fly).
  * act: 0 none, 1 relu, 2 tanh */
 int fs2_op_tap_gemm(int math_mode, const float* x, int B, int L, int K, const float* w, const float* bias, int N, int taps,
                     int act, const float* resid, float* out, void* stream);
