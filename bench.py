@@ -122,6 +122,29 @@ def ncu_traffic(kernel: str, precision: str = "tf32"):
         return None
 
 
+FMA_PEAK = 2 * 148 * 128 * 1.965e9 / 1e12      # fp32 FMA pipe: 148 SM x 128 lanes x 2 flop x 1.965 GHz (nominal)
+F16_CLASSES = ("dec.qkv_proj", "dec.ffn_w1_conv9", "dec.ffn_w2", "feat_out", "postnet.conv5")
+ATTN_CLASSES = ("enc.attention", "dec.attention")
+
+
+def class_peak(precision: str, cls: str, tf_sus: float):
+    """Tensor / FMA peak (TFLOP/s) that bounds profiler class `cls` in `precision` mode, and how it was derived
+    (which instruction kind each class runs on)."""
+    fma = (FMA_PEAK, "fp32 FMA pipe = 148 SM x 128 lanes x 2 x 1.965 GHz (nominal)")
+    f16 = (tf_sus, "kind::f16 dense = the measured sustained bf16 rate")
+    tf32 = (tf_sus / 2.0, "kind::tf32 dense = 1/2 of the measured sustained bf16 rate")
+    x3 = (tf_sus / 3.0, "3xF16 (three kind::f16 products per term) = 1/3 of the measured sustained bf16 rate")
+    if precision == "fp32" or cls == "enc.attention":
+        return fma
+    if cls.startswith("enc.") or cls.startswith("predictor."):
+        return x3
+    if precision == "3xtf32":
+        return fma if cls in ATTN_CLASSES else x3
+    if precision == "f16" and cls in F16_CLASSES:
+        return f16
+    return tf32
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -410,19 +433,14 @@ def run_b200(args):
     if prof:
         tot = sum(v["ms"] for v in prof.values())
         top = max(prof, key=lambda k: prof[k]["ms"])
-        f16_kernel = args.precision == "f16" and top in ("dec.ffn_w1_conv9", "dec.ffn_w2")   # the only kind::f16 classes
-        tensor_peak = (tf_sus if f16_kernel else (tf_sus / 2.0) if args.precision in ("tf32", "f16") else (tf_sus / 6.0)
-                       if args.precision == "3xtf32" else 2 * 148 * 128 * 1.965e9 / 1e12)
+        tensor_peak, peak_note = class_peak(args.precision, top, tf_sus)
         pk = prof[top]
         achieved = pk["flop"] / (pk["ms"] * 1e-3) / 1e12 if pk["ms"] > 0 else 0.0
         roof = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                 "frac": achieved / tensor_peak, "traffic": ncu_traffic(top, args.precision),
                 "algorithmic_bytes_per_launch": pk["bytes"] / pk["launches"], "algorithmic_flop_per_launch": pk["flop"] / pk["launches"],
                 "avg_launch_ms": pk["ms"] / pk["launches"], "share_of_step": pk["ms"] / tot,
-                "peak_source": peak_src + ("; fp16 dense = the measured sustained bf16 rate" if f16_kernel else
-                                           "; tf32 dense = 1/2 of the measured sustained bf16 rate" if args.precision in ("tf32", "f16")
-                                           else "; 3xTF32 = 1/6 of the measured sustained bf16 rate" if args.precision == "3xtf32"
-                                           else "; fp32 FMA pipe = 148 SM x 128 lanes x 2 x 1.965 GHz (nominal)"),
+                "peak_source": peak_src + "; " + peak_note,
                 "classes": {k: {"ms_per_step": v["ms"] / 3, "launches_per_step": v["launches"] // 3,
                                 "tflops": (v["flop"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 else None,
                                 "gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else None} for k, v in prof.items()}}

@@ -16,7 +16,8 @@ LIB_PATH = os.path.join(_HERE, "libfs2b200.so")
 
 FS2_DUR_I64, FS2_DUR_F32, FS2_DUR_I32 = 0, 1, 2
 MATH_FP32, MATH_TF32, MATH_3XTF32, MATH_F16 = 0, 1, 2, 3
-MATH_MODES = {"fp32": MATH_FP32, "tf32": MATH_TF32, "3xtf32": MATH_3XTF32, "f16": MATH_F16}
+# "3xtf32" is the historical name of the error-compensated mode (now three kind::f16 products per term); "3xf16" is an alias
+MATH_MODES = {"fp32": MATH_FP32, "tf32": MATH_TF32, "3xtf32": MATH_3XTF32, "3xf16": MATH_3XTF32, "f16": MATH_F16}
 
 
 class Fs2Error(RuntimeError):

@@ -24,10 +24,8 @@ void set_error(const char* fmt, ...) {
 
 struct Dense {           // one Linear / Conv1d in kernel layout
   const float* w = nullptr;     // [taps][N][K]
-  const float* w_hi = nullptr;  // 3xTF32 split of w (encoder / predictors only)
-  const float* w_lo = nullptr;
   const __half* w_h = nullptr;  // fp16 copy (decoder side, FS2_MATH_F16)
-  const __half* w_hi_h = nullptr;  // fp16 hi / lo split (3xF16, the default error-compensated family)
+  const __half* w_hi_h = nullptr;  // fp16 hi / lo split (3xF16, the error-compensated family)
   const __half* w_lo_h = nullptr;
   const float* bias = nullptr;  // [N] or nullptr
   int N = 0, K = 0, taps = 1;
@@ -113,7 +111,7 @@ int dense(const TapGemm& g, int math_mode, cudaStream_t st, int cls) {
   if (math_mode == FS2_MATH_TF32 && g.ln_gamma) return gemm_ln_tf32(g, st);   // fp16 operands / fp16 copy handled inside
   if (g.x_h) return tap_gemm_f16(g, st);
   if (math_mode == MATH_3XTF32) { TapGemm gs = g; gs.split_ws = t_split_ws; return tap_gemm_3xtf32(gs, st); }
-  return math_mode == MATH_3XTF32 ? tap_gemm_3xtf32(g, st) : math_mode == FS2_MATH_TF32 ? tap_gemm_tf32(g, st) : tap_gemm_fp32(g, st);
+  return math_mode == FS2_MATH_TF32 ? tap_gemm_tf32(g, st) : tap_gemm_fp32(g, st);
 }
 int norm_rows(const RowNorm& r, cudaStream_t st) {
   ProfScope prof_scope(P_ROWNORM, 8.0 * r.rows * r.C, 4.0 * r.rows * r.C * (1 + (r.resid ? 1 : 0) + (r.out ? 1 : 0)), st);
@@ -131,7 +129,7 @@ inline int round4(int x) { return (x + 3) & ~3; }
 TapGemm make_gemm(const Dense& d, const float* x, int ldx, int B, int L, int act, const float* resid, int ldr, float* out,
                   int ldo) {
   TapGemm g;
-  g.x = x; g.ldx = ldx; g.B = B; g.L = L; g.K = d.K; g.w = d.w; g.w_hi = d.w_hi; g.w_lo = d.w_lo; g.w_h = d.w_h; g.w_hi_h = d.w_hi_h; g.w_lo_h = d.w_lo_h; g.bias = d.bias; g.N = d.N; g.taps = d.taps;
+  g.x = x; g.ldx = ldx; g.B = B; g.L = L; g.K = d.K; g.w = d.w; g.w_h = d.w_h; g.w_hi_h = d.w_hi_h; g.w_lo_h = d.w_lo_h; g.bias = d.bias; g.N = d.N; g.taps = d.taps;
   g.act = act; g.resid = resid; g.ldr = ldr; g.out = out; g.ldo = ldo;
   return g;
 }
@@ -211,7 +209,7 @@ int run_blocks(const std::vector<Block>& blocks, float* xin, float* yin, float* 
   return FS2_OK;
 }
 
-// conv stack + scalar head (duration_predictor.py:64-86 / variance_predictor.py:39-60); always fp32
+// conv stack + scalar head (duration_predictor.py:64-86 / variance_predictor.py:39-60); exact fp32 or error-compensated
 int run_predictor(const Predictor& p, const float* x, int C, int B, int L, float* t1, float* t2, const int64_t* lens,
                   float* head_out, int64_t* dur_out, int math_mode, cudaStream_t st) {
   const int64_t rows = (int64_t)B * L;
@@ -265,13 +263,9 @@ struct Packer {
     if (!bkey.empty()) { int rc = copy(bkey, N, &out->bias); if (rc) return rc; }
     return FS2_OK;
   }
-  // hi / lo copies for the 3xTF32 kernel (gemm_tc.cu)
+  // fp16 hi / lo planes for the error-compensated kernels (gemm_tc.cu, 3xF16)
   int split(Dense* d) {
     const size_t n = (size_t)d->N * d->K * d->taps;
-    float* hi = bump.floats(n);
-    float* lo = bump.floats(n);
-    if (!counting) { int rc = split_tf32(d->w, hi, lo, (long)n, st); if (rc) return rc; }
-    d->w_hi = hi; d->w_lo = lo;
     __half* hh = (__half*)bump.bytes(n * sizeof(__half));
     __half* lh = (__half*)bump.bytes(n * sizeof(__half));
     if (!counting) { int rc = split_f16(d->w, hh, lh, (long)n, st); if (rc) return rc; }
@@ -539,7 +533,7 @@ int fs2_encode(fs2_handle* h, const int64_t* xs, const int64_t* ilens, int B, in
   t_split_ws = p.split;
   int rc;
   // the encoder's output feeds round() in the duration predictor: exact fp32 FMA in FS2_MATH_FP32,
-  // error-compensated 3xTF32 on the tensor cores in FS2_MATH_TF32 (never plain tf32)
+  // error-compensated 3xF16 on the tensor cores in every other mode (never a plain 10-bit-mantissa product)
   const int precise = c.math_mode == FS2_MATH_FP32 ? FS2_MATH_FP32 : MATH_3XTF32;
   { ProfScope prof_scope(P_EMBED, 0, 8.0 * B * Tmax * c.adim, st);
     if ((rc = embed_posenc(xs, h->emb, c.idim, h->enc_pe, h->enc_alpha, B, Tmax, c.adim, p.x, st))) return rc; }
@@ -582,7 +576,7 @@ int fs2_decode(fs2_handle* h, const float* hm, const int64_t* olens, const float
   const int mode = f16_ffn ? FS2_MATH_TF32 : c.math_mode;
   const int precise = mode == FS2_MATH_FP32 ? FS2_MATH_FP32 : MATH_3XTF32;
   int rc;
-  // energy / pitch predictors on the length-regulated states (fastspeech.py:195-196,214-216); fp32
+  // energy / pitch predictors on the length-regulated states (fastspeech.py:195-196,214-216); fp32-class
   if ((rc = run_predictor(h->energy, hm, c.adim, B, L, p.t1, p.t2, olens, e_out, nullptr, precise, st))) return rc;
   if ((rc = run_predictor(h->pitch, hm, c.adim, B, L, p.t1, p.t2, olens, p_out, nullptr, precise, st))) return rc;
   // hs + pitch_embed(one_hot) + energy_embed(one_hot) (fastspeech.py:218-219)
@@ -664,18 +658,14 @@ int fs2_op_tap_gemm(int math_mode, const float* x, int B, int L, int K, const fl
     return rc;
   }
   if (math_mode != MATH_3XTF32) return dense(make_gemm(d, x, K, B, L, act, resid, N, out, N), math_mode, st, P_DEC_W1);
-  // single-operator entry for the 3xTF32 family (tests): split the weights on the fly
-  const size_t n = (size_t)N * K * taps;
-  float* tmp = nullptr;
-  const size_t nx = (size_t)B * L * K;
-  FS2_CUDA_CHECK(cudaMallocAsync(&tmp, (3 * n + nx) * sizeof(float) + 256, st));
-  int rc = split_tf32(w, tmp, tmp + n, (long)n, st);
-  d.w_hi = tmp; d.w_lo = tmp + n;
-  __half* th = reinterpret_cast<__half*>(tmp + 2 * n);
-  __half* tl = th + ((n + 7) & ~(size_t)7);
-  if (!rc) rc = split_f16(w, th, tl, (long)n, st);
-  d.w_hi_h = th; d.w_lo_h = tl;
-  t_split_ws = reinterpret_cast<__half*>(tmp + 3 * n + 32);
+  // single-operator entry for the error-compensated family (tests): split the weights on the fly
+  const size_t n = (size_t)N * K * taps, nx = (size_t)B * L * K;
+  __half* tmp = nullptr;
+  const size_t n8 = (n + 7) & ~(size_t)7;
+  FS2_CUDA_CHECK(cudaMallocAsync(&tmp, (2 * n8 + 2 * nx + 16) * sizeof(__half), st));
+  int rc = split_f16(w, tmp, tmp + n8, (long)n, st);
+  d.w_hi_h = tmp; d.w_lo_h = tmp + n8;
+  t_split_ws = tmp + 2 * n8;
   if (!rc) rc = dense(make_gemm(d, x, K, B, L, act, resid, N, out, N), math_mode, st, P_DEC_W1);
   cudaFreeAsync(tmp, st);
   return rc;

@@ -51,16 +51,14 @@ struct TapGemm {
   int act;
   const float* resid; int ldr;  // nullptr => none
   float* out; int ldo;
-  // 3xTF32 only: w split into hi = rn_tf32(w), lo = rn_tf32(w - hi), same [taps][N][K] layout
-  const float* w_hi = nullptr; const float* w_lo = nullptr;
-  // tf32 family, N == 384, taps == 1: fuse LayerNorm over the full output row into the epilogue (gemm_ln_tc.cu)
+  // tensor-core families, N == 384, taps == 1: fuse LayerNorm over the full output row into the epilogue (gemm_ln_tc.cu)
   const float* ln_gamma = nullptr; const float* ln_beta = nullptr; float ln_eps = 0.f;
-  // tf32 family only: store output columns >= vt_col0 transposed into vt_out (see gemm_tc.cu)
+  // tensor-core families only: store output columns >= vt_col0 transposed into vt_out (see gemm_tc.cu)
   float* vt_out = nullptr; int vt_col0 = 0, vt_dk = 0, vt_heads = 0, vt_lpad = 0;
   // f16 family (tap_gemm_f16): fp16 copies of the activations (row stride ldx_h halfs) and of w; the result goes to
   // out (fp32, with the optional residual) and / or out_h (fp16, row stride ldo_h halfs, for the next f16 GEMM)
   const __half* x_h = nullptr; int ldx_h = 0; const __half* w_h = nullptr; __half* out_h = nullptr; int ldo_h = 0;
-  // 3xF16 (the default error-compensated family): w split into fp16 hi = rn(w), lo = rn(w - hi)
+  // 3xF16 (the error-compensated family): w split into fp16 hi = rn(w), lo = rn(w - hi), same [taps][N][K] layout
   const __half* w_hi_h = nullptr; const __half* w_lo_h = nullptr;
   __half* split_ws = nullptr;   // scratch for the fp16 hi / lo planes of x: 2 * B*L * K halfs (= the bytes of x)
 };
@@ -68,12 +66,11 @@ int tap_gemm_fp32(const TapGemm& g, cudaStream_t st);
 int tap_gemm_tf32(const TapGemm& g, cudaStream_t st);   // tcgen05 + TMA (gemm_tc.cu)
 bool gemm_ln_tf32_supported(const TapGemm& g);         // row-complete GEMM + residual + LayerNorm (gemm_ln_tc.cu)
 int gemm_ln_tf32(const TapGemm& g, cudaStream_t st);
-int tap_gemm_3xtf32(const TapGemm& g, cudaStream_t st); // same kernel, error-compensated split operands
-int split_tf32(const float* src, float* hi, float* lo, long n, cudaStream_t st);
+int tap_gemm_3xtf32(const TapGemm& g, cudaStream_t st); // same kernel, error-compensated split operands ("3xF16")
 int tap_gemm_f16(const TapGemm& g, cudaStream_t st);    // same kernel, kind::f16 on x_h / w_h, fp32 accumulation
 int to_half(const float* src, __half* dst, long n, cudaStream_t st);
 int split_f16(const float* src, __half* hi, __half* lo, long n, cudaStream_t st);   // round to nearest, clamped to +-65504
-constexpr int MATH_3XTF32 = FS2_MATH_3XTF32;            // also what FS2_MATH_TF32 uses for the encoder + predictors
+constexpr int MATH_3XTF32 = FS2_MATH_3XTF32;            // also what the other tensor-core modes use for the encoder + predictors
 
 // Row LayerNorm with the fusions the path needs.
 struct RowNorm {

@@ -12,8 +12,6 @@
 //   <BN, true,  true>   error-compensated "3xF16" (encoder and predictors in every tensor-core mode, everything in
 //                       FS2_MATH_3XTF32): their outputs feed round() / bucketize(), where 10-bit-mantissa noise
 //                       (~1e-3) would flip integers; see "PRECISE && HALF" below;
-//   <BN, true,  false>  the earlier error-compensated form, 3 x tf32 with hi = top 19 bits of x, lo = x - hi split in
-//                       shared memory by four extra warps (kept behind FS2_PRECISE_F16=0 for A/B measurements).
 //
 // Why no im2col: activations are [B, time, channel] fp32 with channels innermost, which *is* the
 // K-major A operand of a GEMM.  Tap j of a 1-D convolution is the same matrix shifted by
@@ -32,9 +30,6 @@
 //                 32-column chunks: tcgen05.ld -> bias / ReLU / tanh / residual in registers -> four
 //                 256-bit global stores per thread (sector-complete, no shared-memory transpose, no
 //                 barriers; rows past the utterance end are predicated off)
-//   <BN, true, false> only: warps 10-13 split each landed A tile in place into hi / lo (element-wise, so the
-//                 swizzled layout is untouched) and hand the slot to the MMA warp through a third
-//                 mbarrier; the weight hi / lo arrays are split once at load time.
 // Convolutions tile each utterance separately so the shifted boxes never cross an utterance boundary:
 // floor(L/128) full row tiles per utterance, and the tails (L % 128 rows, in 16-row granules loaded by
 // separate small TMA boxes) of several utterances packed into shared tiles, so no tensor-core rows are
@@ -90,14 +85,14 @@ template <int BN, bool PRECISE, bool HALF = false>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = (PRECISE ? 2 : 1) * (A_BYTES + B_BYTES);   // [A(hi)][A lo][B hi][B lo]
-  static constexpr bool SPLIT16 = PRECISE && HALF;        // A hi / lo are fp16 planes in global memory, loaded like B hi / lo
-  static constexpr bool SPLIT_WARPS = PRECISE && !HALF;    // tf32 split: four extra warps split the landed fp32 A tile in place
+  static constexpr bool SPLIT16 = PRECISE;                // A hi / lo are fp16 planes in global memory, loaded like B hi / lo
+  static_assert(!PRECISE || HALF, "the error-compensated family is 3xF16");
   static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
   static constexpr int ACC_STRIDE = pow2_at_least(BN);     // TMEM columns per accumulator buffer
   static constexpr int NACC = 512 / ACC_STRIDE > 4 ? 4 : 512 / ACC_STRIDE;   // accumulator buffers in flight (2 for BN > 128, else 4)
   static constexpr int TMEM_COLS = NACC * ACC_STRIDE;
   static constexpr int GROUPS = 2;       // epilogue warp groups (4 warps each), alternate 32-column chunks
-  static constexpr int THREADS = 64 + GROUPS * 128 + (PRECISE && !HALF ? 128 : 0);
+  static constexpr int THREADS = 64 + GROUPS * 128;
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
   static constexpr uint32_t IDESC = HALF ? idesc_f16(BM, BN) : idesc_tf32(BM, BN);
   static constexpr int BKE = HALF ? 2 * BK : BK;           // K elements per pipeline step
@@ -111,10 +106,6 @@ struct Cfg {
   static_assert(STAGES >= 2 && TMEM_COLS <= 512, "resources");
 };
 
-// tf32 split: hi keeps the top 19 bits (exactly what kind::tf32 reads), lo = x - hi is exact in fp32 and
-// is itself read as tf32 by the tensor core (relative error 2^-10 of lo = 2^-21 of x)
-__device__ __forceinline__ float hi_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
-
 template <int BN, bool PRECISE, bool HALF>
 __global__ void __launch_bounds__(Cfg<BN, PRECISE, HALF>::THREADS, 1)
 tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -125,8 +116,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   uint8_t* staging = tiles + (size_t)C::STAGES * C::STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
-  uint64_t* split_bar = empty_bar + C::STAGES;
-  uint64_t* acc_full = split_bar + C::STAGES;     // [NACC] MMA -> epilogue
+  uint64_t* acc_full = empty_bar + C::STAGES;     // [NACC] MMA -> epilogue
   uint64_t* acc_empty = acc_full + 4;             // [NACC] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 4);
 
@@ -136,7 +126,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   const int total_tiles = p.m_tiles * p.n_tiles;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], 4); }
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int i = 0; i < C::NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4 * C::GROUPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -202,7 +192,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         const uint32_t d = tmem_base + (uint32_t)(acc * C::ACC_STRIDE);
         for (int s = 0; s < steps; ++s, ++n) {
           const int slot = n % C::STAGES, round = n / C::STAGES;
-          mbar_wait(C::SPLIT_WARPS ? &split_bar[slot] : &full_bar[slot], round & 1);
+          mbar_wait(&full_bar[slot], round & 1);
           tcgen05_fence_after();
           const uint32_t base = smem_u32(tiles + (size_t)slot * C::STAGE_BYTES);
           const uint64_t a_hi = make_sw128_kmajor_desc(base), b_hi = make_sw128_kmajor_desc(base + C::B_HI);
@@ -210,15 +200,9 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           for (int k = 0; k < BK / UMMA_K; ++k) {  // +32 bytes along K inside the swizzle row = +2 in descriptor units
             if (PRECISE) {
               const uint64_t a_lo = make_sw128_kmajor_desc(base + C::A_LO), b_lo = make_sw128_kmajor_desc(base + C::B_LO);
-              if (HALF) {
-                umma_f16(d, a_lo + 2 * k, b_hi + 2 * k, C::IDESC, (s | k) != 0);  // small terms first
-                umma_f16(d, a_hi + 2 * k, b_lo + 2 * k, C::IDESC, 1);
-                umma_f16(d, a_hi + 2 * k, b_hi + 2 * k, C::IDESC, 1);
-              } else {
-                umma_tf32(d, a_lo + 2 * k, b_hi + 2 * k, C::IDESC, (s | k) != 0);
-                umma_tf32(d, a_hi + 2 * k, b_lo + 2 * k, C::IDESC, 1);
-                umma_tf32(d, a_hi + 2 * k, b_hi + 2 * k, C::IDESC, 1);
-              }
+              umma_f16(d, a_lo + 2 * k, b_hi + 2 * k, C::IDESC, (s | k) != 0);  // small terms first
+              umma_f16(d, a_hi + 2 * k, b_lo + 2 * k, C::IDESC, 1);
+              umma_f16(d, a_hi + 2 * k, b_hi + 2 * k, C::IDESC, 1);
             } else if (HALF) {
               umma_f16(d, a_hi + 2 * k, b_hi + 2 * k, C::IDESC, (s | k) != 0);
             } else {
@@ -336,32 +320,6 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
     }
-  } else if (C::SPLIT_WARPS) {
-    // ---- operand split (the last 4 warps): A tile -> hi (in place) and lo (second buffer), same swizzled positions ----
-    const int tid = threadIdx.x - (64 + 128 * C::GROUPS);      // 0..127
-    int n = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      for (int s = 0; s < steps; ++s, ++n) {
-        const int slot = n % C::STAGES, round = n / C::STAGES;
-        mbar_wait(&full_bar[slot], round & 1);
-        float4* a = reinterpret_cast<float4*>(tiles + (size_t)slot * C::STAGE_BYTES);
-        float4* lo = reinterpret_cast<float4*>(tiles + (size_t)slot * C::STAGE_BYTES + C::A_LO);
-        {
-#pragma unroll
-          for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
-            const int idx = tid + i * 128;
-            const float4 x = a[idx];
-            float4 h, l;
-            h.x = hi_tf32(x.x); h.y = hi_tf32(x.y); h.z = hi_tf32(x.z); h.w = hi_tf32(x.w);
-            l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
-            a[idx] = h; lo[idx] = l;
-          }
-        }
-        fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&split_bar[slot]);
-      }
-    }
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -391,13 +349,6 @@ __global__ void split_rows_f16_kernel(const float* __restrict__ x, int ldx, long
     lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
     *reinterpret_cast<uint2*>(S + r * K + c) = hv;
     *reinterpret_cast<uint2*>(lo_plane + r * K + c) = lv;
-  }
-}
-
-__global__ void split_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, long n) {
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    const float x = src[i], h = hi_tf32(x);
-    hi[i] = h; lo[i] = x - h;
   }
 }
 
@@ -453,9 +404,9 @@ int launch(const TapGemm& g, cudaStream_t st) {
     if ((rc = make_map(&ma16, xa, g.K, g.L, (uint64_t)g.B * planes, row_bytes, row_bytes * g.L, 16, AH))) return rc;
   }
   p.n_tiles = g.N / BN;
-  const void* w_hi = PRECISE ? (HALF ? (const void*)g.w_hi_h : (const void*)g.w_hi) : HALF ? (const void*)g.w_h : (const void*)g.w;
+  const void* w_hi = PRECISE ? (const void*)g.w_hi_h : HALF ? (const void*)g.w_h : (const void*)g.w;
   if ((rc = make_map(&mb, w_hi, g.K, g.N, g.taps, (uint64_t)g.K * esz, (uint64_t)g.K * esz * g.N, BN, HALF))) return rc;
-  if ((rc = make_map(&mb_lo, PRECISE ? (HALF ? (const void*)g.w_lo_h : (const void*)g.w_lo) : w_hi, g.K, g.N, g.taps, (uint64_t)g.K * esz, (uint64_t)g.K * esz * g.N, BN, HALF))) return rc;
+  if ((rc = make_map(&mb_lo, PRECISE ? (const void*)g.w_lo_h : w_hi, g.K, g.N, g.taps, (uint64_t)g.K * esz, (uint64_t)g.K * esz * g.N, BN, HALF))) return rc;
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < sm_count() ? total : sm_count();
   tap_gemm_tf32_kernel<BN, PRECISE, HALF><<<grid, C::THREADS, C::SMEM, st>>>(ma, mb, mb_lo, ma16, p);
@@ -504,26 +455,21 @@ int tap_gemm_3xtf32(const TapGemm& g, cudaStream_t st) {
   int rc = check_common(g, "tap_gemm_3xtf32");
   if (rc) return rc;
   if ((long)g.B * g.L == 0) return FS2_OK;
-  static int f16 = -1;    // FS2_PRECISE_F16=0 falls back to the tf32 split (kept for A/B measurements)
-  if (f16 < 0) { const char* e = getenv("FS2_PRECISE_F16"); f16 = e ? atoi(e) : 1; }
-  if (f16 && g.w_hi_h && g.w_lo_h && g.split_ws && g.K % 8 == 0) {
+  FS2_REQUIRE(g.w_hi_h && g.w_lo_h && g.split_ws, "tap_gemm_3xtf32: split weights / activation scratch missing");
+  FS2_REQUIRE(g.K % 8 == 0, "tap_gemm_3xtf32: K (%d) must be a multiple of 8", g.K);
+  {
     // pre-pass: fp32 activations -> fp16 hi / lo planes (rows of K contiguous halfs)
     const long rows = (long)g.B * g.L;
     const long quads = rows * (g.K / 4);
     long blocks = (quads + 255) / 256;
     split_rows_f16_kernel<<<(int)(blocks > 148 * 16 ? 148 * 16 : blocks), 256, 0, st>>>(g.x, g.ldx, rows, g.K, g.split_ws);
     FS2_LAUNCH_CHECK();
-    if (g.N % 128 == 0) return launch<128, true, true>(g, st);
-    if (g.N % 96 == 0) return launch<96, true, true>(g, st);
-    if (g.N % 80 == 0) return launch<80, true, true>(g, st);
-    if (g.N % 64 == 0) return launch<64, true, true>(g, st);
   }
-  FS2_REQUIRE(g.w_hi && g.w_lo, "tap_gemm_3xtf32: split weights missing");
   // narrower tiles than the plain kernel: the stage holds four operand tiles and the encoder's M is small
-  if (g.N % 128 == 0) return launch<128, true>(g, st);
-  if (g.N % 96 == 0) return launch<96, true>(g, st);
-  if (g.N % 80 == 0) return launch<80, true>(g, st);
-  if (g.N % 64 == 0) return launch<64, true>(g, st);
+  if (g.N % 128 == 0) return launch<128, true, true>(g, st);
+  if (g.N % 96 == 0) return launch<96, true, true>(g, st);
+  if (g.N % 80 == 0) return launch<80, true, true>(g, st);
+  if (g.N % 64 == 0) return launch<64, true, true>(g, st);
   set_error("tap_gemm_3xtf32: N=%d has no supported tile width", g.N);
   return FS2_ERR_INVALID;
 }
@@ -560,14 +506,6 @@ int split_f16(const float* src, __half* hi, __half* lo, long n, cudaStream_t st)
   if (n == 0) return FS2_OK;
   long blocks = (n + 255) / 256;
   split_f16_kernel<<<(int)(blocks > 1184 ? 1184 : blocks), 256, 0, st>>>(src, hi, lo, n);
-  FS2_LAUNCH_CHECK();
-  return FS2_OK;
-}
-
-int split_tf32(const float* src, float* hi, float* lo, long n, cudaStream_t st) {
-  if (n == 0) return FS2_OK;
-  long blocks = (n + 255) / 256;
-  split_tf32_kernel<<<(int)(blocks > 1184 ? 1184 : blocks), 256, 0, st>>>(src, hi, lo, n);
   FS2_LAUNCH_CHECK();
   return FS2_OK;
 }
