@@ -50,6 +50,8 @@ struct Profiler {
 };
 static thread_local Profiler* t_prof = nullptr;
 static thread_local __half* t_split_ws = nullptr;   // scratch of the running stage for the 3xF16 activation planes
+static thread_local const float* t_split_of = nullptr;   // fp32 tensor whose planes t_split_ws currently holds (or null)
+static thread_local int64_t t_split_rows = 0; static thread_local int t_split_K = 0;
 struct ProfScope {
   ProfRec r; bool live; cudaStream_t st;
   ProfScope(int cls, double flop, double bytes, cudaStream_t s) : live(t_prof && t_prof->on), st(s) {
@@ -104,14 +106,39 @@ struct Bump {  // bump allocator over a caller-provided (or null = counting) buf
 
 using Map = std::unordered_map<std::string, const fs2_weight_desc*>;
 
+// FS2_FUSED_SPLIT=0 (debug / A-B): every 3xF16 GEMM runs its own pre-pass
+bool fused_split() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FS2_FUSED_SPLIT"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+int norm_rows(const RowNorm& r, cudaStream_t st);
+
 int dense(const TapGemm& g, int math_mode, cudaStream_t st, int cls) {
   const double M = (double)g.B * g.L;
   ProfScope prof_scope(cls, 2.0 * M * g.N * g.K * g.taps,
                4.0 * (M * g.K + (double)g.taps * g.N * g.K + M * g.N * (g.resid ? 2 : 1)), st);
   if (math_mode == FS2_MATH_TF32 && g.ln_gamma) return gemm_ln_tf32(g, st);   // fp16 operands / fp16 copy handled inside
   if (g.x_h) return tap_gemm_f16(g, st);
-  if (math_mode == MATH_3XTF32) { TapGemm gs = g; gs.split_ws = t_split_ws; return tap_gemm_3xtf32(gs, st); }
+  if (math_mode == MATH_3XTF32) {
+    // the planes of g.x may already be in the scratch: written by the LayerNorm that produced x, or by the previous
+    // GEMM's pre-pass over the same x (energy / pitch predictors share their input)
+    TapGemm gs = g;
+    gs.split_ws = t_split_ws;
+    gs.split_ready = fused_split() && t_split_of == g.x && t_split_rows == (int64_t)g.B * g.L && t_split_K == g.K && g.ldx == g.K;
+    t_split_of = g.x; t_split_rows = (int64_t)g.B * g.L; t_split_K = g.K;
+    if (!fused_split() || g.ldx != g.K) t_split_of = nullptr;
+    return tap_gemm_3xtf32(gs, st);
+  }
   return math_mode == FS2_MATH_TF32 ? tap_gemm_tf32(g, st) : tap_gemm_fp32(g, st);
+}
+// LayerNorm whose output feeds a 3xF16 GEMM next: write the operand planes from the same kernel
+int norm_rows_split(RowNorm r, cudaStream_t st) {
+  if (fused_split() && r.out && r.ldo == r.C && t_split_ws) {
+    r.split_out = t_split_ws;
+    t_split_of = r.out; t_split_rows = r.rows; t_split_K = r.C;
+  }
+  return norm_rows(r, st);
 }
 int norm_rows(const RowNorm& r, cudaStream_t st) {
   ProfScope prof_scope(P_ROWNORM, 8.0 * r.rows * r.C, 4.0 * r.rows * r.C * (1 + (r.resid ? 1 : 0) + (r.out ? 1 : 0)), st);
@@ -181,7 +208,7 @@ int run_blocks(const std::vector<Block>& blocks, float* xin, float* yin, float* 
       if ((rc = dense(go, math_mode, st, c_out))) return rc;
       RowNorm r1 = make_norm(k.ln1, y, C, rows, C, x, C);
       r1.out_h = xh; r1.ldo_h = C;
-      if ((rc = norm_rows(r1, st))) return rc;
+      if ((rc = math_mode == MATH_3XTF32 ? norm_rows_split(r1, st) : norm_rows(r1, st))) return rc;   // feeds the conv-FFN
     }
     // conv-FFN: hid = relu(conv_k(x)); x = LN(x + conv_1(hid))  (modules.py:247-248, encoder.py:64-69)
     TapGemm g1 = make_gemm(k.w1, x, C, B, L, ACT_RELU, nullptr, 0, hid, k.w1.N);
@@ -202,7 +229,7 @@ int run_blocks(const std::vector<Block>& blocks, float* xin, float* yin, float* 
       if ((rc = dense(g2, math_mode, st, c_w2))) return rc;
       RowNorm r2 = make_norm(k.ln2, y, C, rows, C, x, C);
       r2.out_h = xh; r2.ldo_h = C;
-      if ((rc = norm_rows(r2, st))) return rc;
+      if ((rc = math_mode == MATH_3XTF32 ? norm_rows_split(r2, st) : norm_rows(r2, st))) return rc;   // feeds the next GEMM
     }
   }
   *result = x;
@@ -222,7 +249,7 @@ int run_predictor(const Predictor& p, const float* x, int C, int B, int L, float
       r.out = nullptr; r.head_w = p.head_w; r.head_b = p.head_b; r.head_out = head_out; r.dur_out = dur_out;
       r.lens = lens; r.L = L;
     }
-    if ((rc = norm_rows(r, st))) return rc;
+    if ((rc = math_mode == MATH_3XTF32 ? norm_rows_split(r, st) : norm_rows(r, st))) return rc;
     cur = t2; curC = p.conv[i].N;
   }
   return FS2_OK;
@@ -530,7 +557,7 @@ int fs2_encode(fs2_handle* h, const int64_t* xs, const int64_t* ilens, int B, in
   Bump b(ws, ws_bytes);
   EncodePlan p = plan_encode(c, b, (int64_t)B * Tmax);
   if (!b.ok()) { set_error("fs2_encode: workspace too small (%zu < %zu)", ws_bytes, b.off); return FS2_ERR_WORKSPACE; }
-  t_split_ws = p.split;
+  t_split_ws = p.split; t_split_of = nullptr;
   int rc;
   // the encoder's output feeds round() in the duration predictor: exact fp32 FMA in FS2_MATH_FP32,
   // error-compensated 3xF16 on the tensor cores in every other mode (never a plain 10-bit-mantissa product)
@@ -571,7 +598,7 @@ int fs2_decode(fs2_handle* h, const float* hm, const int64_t* olens, const float
   Bump b(ws, ws_bytes);
   DecodePlan p = plan_decode(c, b, rows, B, L);
   if (!b.ok()) { set_error("fs2_decode: workspace too small (%zu < %zu)", ws_bytes, b.off); return FS2_ERR_WORKSPACE; }
-  t_split_ws = p.split;
+  t_split_ws = p.split; t_split_of = nullptr;
   const bool f16_ffn = c.math_mode == FS2_MATH_F16;                     // tf32 everywhere except the conv-FFN
   const int mode = f16_ffn ? FS2_MATH_TF32 : c.math_mode;
   const int precise = mode == FS2_MATH_FP32 ? FS2_MATH_FP32 : MATH_3XTF32;
@@ -589,7 +616,7 @@ int fs2_decode(fs2_handle* h, const float* hm, const int64_t* olens, const float
     RowNorm r = make_norm(h->dec_in_ln, p.y, c.ddim, rows, c.ddim, p.x, c.ddim);
     r.relu_after = 1; r.pe = h->dec_pe; r.alpha = h->dec_alpha; r.L = L;
     if (f16_ffn) { r.out_h = p.xh; r.ldo_h = c.ddim; }    // first block's q|k|v reads the fp16 copy
-    if ((rc = norm_rows(r, st))) return rc;
+    if ((rc = mode == MATH_3XTF32 ? norm_rows_split(r, st) : norm_rows(r, st))) return rc;
   }
   float* dec_out = nullptr;
   if ((rc = run_blocks(h->dec, p.x, p.y, p.qkv, p.vt, p.ctx, p.hid, olens, B, L, c.ddim, c.aheads, mode, true, st, &dec_out, f16_ffn ? p.xh : nullptr))) return rc;
@@ -665,7 +692,7 @@ int fs2_op_tap_gemm(int math_mode, const float* x, int B, int L, int K, const fl
   FS2_CUDA_CHECK(cudaMallocAsync(&tmp, (2 * n8 + 2 * nx + 16) * sizeof(__half), st));
   int rc = split_f16(w, tmp, tmp + n8, (long)n, st);
   d.w_hi_h = tmp; d.w_lo_h = tmp + n8;
-  t_split_ws = tmp + 2 * n8;
+  t_split_ws = tmp + 2 * n8; t_split_of = nullptr;
   if (!rc) rc = dense(make_gemm(d, x, K, B, L, act, resid, N, out, N), math_mode, st, P_DEC_W1);
   cudaFreeAsync(tmp, st);
   return rc;

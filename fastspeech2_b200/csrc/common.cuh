@@ -61,6 +61,7 @@ struct TapGemm {
   // 3xF16 (the error-compensated family): w split into fp16 hi = rn(w), lo = rn(w - hi), same [taps][N][K] layout
   const __half* w_hi_h = nullptr; const __half* w_lo_h = nullptr;
   __half* split_ws = nullptr;   // scratch for the fp16 hi / lo planes of x: 2 * B*L * K halfs (= the bytes of x)
+  bool split_ready = false;     // the producer of x already wrote the planes (row_norm's split_out): skip the pre-pass
 };
 int tap_gemm_fp32(const TapGemm& g, cudaStream_t st);
 int tap_gemm_tf32(const TapGemm& g, cudaStream_t st);   // tcgen05 + TMA (gemm_tc.cu)
@@ -85,6 +86,7 @@ struct RowNorm {
   const float* head_w; const float* head_b; float* head_out; int64_t* dur_out;
   const int64_t* lens;            // optional mask for the head outputs
   __half* out_h; int ldo_h;       // optional fp16 copy of y (A operand of an f16 GEMM)
+  __half* split_out;              // optional 3xF16 planes of y: hi at [row][C], lo at [rows + row][C] (A operand of a 3xF16 GEMM)
 };
 int row_norm(const RowNorm& r, cudaStream_t st);
 

@@ -457,7 +457,7 @@ int tap_gemm_3xtf32(const TapGemm& g, cudaStream_t st) {
   if ((long)g.B * g.L == 0) return FS2_OK;
   FS2_REQUIRE(g.w_hi_h && g.w_lo_h && g.split_ws, "tap_gemm_3xtf32: split weights / activation scratch missing");
   FS2_REQUIRE(g.K % 8 == 0, "tap_gemm_3xtf32: K (%d) must be a multiple of 8", g.K);
-  {
+  if (!g.split_ready) {
     // pre-pass: fp32 activations -> fp16 hi / lo planes (rows of K contiguous halfs)
     const long rows = (long)g.B * g.L;
     const long quads = rows * (g.K / 4);

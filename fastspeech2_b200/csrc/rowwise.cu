@@ -86,6 +86,18 @@ __global__ void row_norm_kernel(RowNorm r) {
       dot += (y.x * w.x + y.y * w.y) + (y.z * w.z + y.w * w.w);
     }
     if (r.out) *reinterpret_cast<float4*>(r.out + row * r.ldo + c) = y;
+    if (r.split_out) {   // 3xF16 operand planes: hi = rn(y), lo = rn(y - hi), what split_rows_f16_kernel would write
+      const float f0 = fminf(fmaxf(y.x, -65504.f), 65504.f), f1 = fminf(fmaxf(y.y, -65504.f), 65504.f);
+      const float f2 = fminf(fmaxf(y.z, -65504.f), 65504.f), f3 = fminf(fmaxf(y.w, -65504.f), 65504.f);
+      const __half2 h01 = __floats2half2_rn(f0, f1), h23 = __floats2half2_rn(f2, f3);
+      const float2 g01 = __half22float2(h01), g23 = __half22float2(h23);
+      const __half2 l01 = __floats2half2_rn(f0 - g01.x, f1 - g01.y), l23 = __floats2half2_rn(f2 - g23.x, f3 - g23.y);
+      uint2 hv, lv;
+      hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+      lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+      *reinterpret_cast<uint2*>(r.split_out + row * C + c) = hv;
+      *reinterpret_cast<uint2*>(r.split_out + (r.rows + row) * C + c) = lv;
+    }
     if (r.out_h) {   // fp16 copy (A operand of the f16 conv-FFN), 8-byte store
       const __half2 lo = __floats2half2_rn(fminf(fmaxf(y.x, -65504.f), 65504.f), fminf(fmaxf(y.y, -65504.f), 65504.f));
       const __half2 hi = __floats2half2_rn(fminf(fmaxf(y.z, -65504.f), 65504.f), fminf(fmaxf(y.w, -65504.f), 65504.f));
