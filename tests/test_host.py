@@ -65,6 +65,19 @@ def test_unsupported_hp_is_rejected():
         FeedForwardTransformer(68, 80, hp)
 
 
+def test_precision_names(model):
+    """The extra `precision` keyword: default from FS2_PRECISION else "f16"; unknown names are rejected; the header's
+    FS2_MATH_* values and the ctypes table agree."""
+    assert model.precision == os.environ.get("FS2_PRECISION", "f16")
+    with pytest.raises(ValueError):
+        FeedForwardTransformer(68, 80, load_hp(), precision="bf16")
+    hdr = open(os.path.join(REPO, "include", "fs2_b200.h")).read()
+    macros = {k: int(v) for k, v in re.findall(r"#define FS2_MATH_(\w+) (\d+)", hdr)}
+    assert macros == {"FP32": _lib.MATH_MODES["fp32"], "TF32": _lib.MATH_MODES["tf32"], "3XTF32": _lib.MATH_MODES["3xtf32"],
+                      "F16": _lib.MATH_MODES["f16"]}
+    assert _lib.MATH_MODES["3xf16"] == _lib.MATH_MODES["3xtf32"]
+
+
 def test_library_exports_every_declared_symbol():
     header = open(os.path.join(REPO, "include", "fs2_b200.h")).read()
     declared = set(re.findall(r"\b(fs2_[a-z0-9_]+)\s*\(", header))
