@@ -196,6 +196,27 @@ def _init_like_reference(model: nn.Module, init_type: str) -> None:
 class FeedForwardTransformer(nn.Module):
     """Feed-forward Transformer TTS (FastSpeech2) on B200.  See module docstring."""
 
+    @classmethod
+    def from_checkpoint(cls, checkpoint, hp=None, precision: Optional[str] = None, device=None):
+        """Build the model from a reference checkpoint: a path or the loaded dict `{"model": state_dict, "optim": ..,
+        "step": .., "hp_str": .., "githash": ..}` that train_fastspeech.py:235-244 writes (or a bare state_dict, the
+        `--old_model` case of inference.py:161-163).  `hp` defaults to the checkpoint's own `hp_str` like
+        inference.py:148-152; idim is read off the embedding table instead of the text front-end's symbol list."""
+        from .hparams import load_hp_str
+        if isinstance(checkpoint, (str, bytes, os.PathLike)):
+            checkpoint = torch.load(checkpoint, map_location="cpu", weights_only=True)
+        sd = checkpoint["model"] if "model" in checkpoint else checkpoint
+        if hp is None:
+            if "hp_str" not in checkpoint:
+                raise ValueError("checkpoint carries no hp_str: pass hp=")
+            hp = load_hp_str(checkpoint["hp_str"])
+        idim = int(sd["encoder.embed.0.weight"].shape[0])
+        odim = int(_get(_get(hp, "audio"), "num_mels"))
+        model = cls(idim, odim, hp, precision=precision)
+        model.load_state_dict(sd, strict="model" in checkpoint)
+        model.eval()
+        return model.to(device) if device is not None else model
+
     def __init__(self, idim: int, odim: int, hp: Dict, precision: Optional[str] = None):
         super().__init__()
         dims = dims_from_hp(idim, odim, hp)

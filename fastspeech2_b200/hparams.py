@@ -31,3 +31,13 @@ class AttrDict(dict):
 def load_hp(path: str = DEFAULT_YAML) -> AttrDict:
     with open(path) as f:
         return AttrDict(yaml.safe_load(f))
+
+
+def load_hp_str(hp_str: str) -> AttrDict:
+    """The `hp_str` a reference checkpoint carries (train_fastspeech.py:235-244): the YAML text of the config, possibly
+    several documents, merged like utils/hparams.py:14-24 does."""
+    merged = {}
+    for doc in yaml.safe_load_all(hp_str):
+        if isinstance(doc, dict):
+            merged.update(doc)
+    return AttrDict(merged)

@@ -51,3 +51,22 @@ def test_bucket_sampler_partitions_and_cuts_padding():
     rand_waste = 1.0 - float(np.mean(lengths)) / float(np.mean([lengths[np.array(b)].max() for b in
                         np.array_split(rng.permutation(2000), 125)]))
     assert s.padding_waste() < 0.1 < rand_waste
+
+
+def test_vocoder_handoff_layout():
+    """fastspeech2_b200.handoff vs the reference's own tensor ops (inference.py:170-180: audio.T, cat(dim=1), unsqueeze(0))."""
+    from fastspeech2_b200.handoff import batch_to_vocoder, paragraph_mel, split_utterances
+    g = torch.Generator().manual_seed(3)
+    olens = torch.tensor([7, 3, 5])
+    mels = torch.randn(3, 7, 80, generator=g)
+    para_mel = []
+    for b in range(3):
+        audio = mels[b, :olens[b]]                 # what model.inference(text) returns: [L, 80]
+        para_mel.append(audio.T)
+    want = torch.cat(para_mel, dim=1).unsqueeze(0)  # inference.py:176,181
+    assert want.shape == (1, 80, 15)
+    assert torch.equal(batch_to_vocoder(mels, olens), want)
+    assert torch.equal(paragraph_mel([mels[b, :olens[b]] for b in range(3)]), want)
+    parts = split_utterances(mels, olens)
+    assert [tuple(p.shape) for p in parts] == [(1, 80, 7), (1, 80, 3), (1, 80, 5)]
+    assert torch.equal(torch.cat(parts, dim=2), want)

@@ -65,6 +65,24 @@ def test_unsupported_hp_is_rejected():
         FeedForwardTransformer(68, 80, hp)
 
 
+def test_from_reference_checkpoint(tmp_path, weights):
+    """The checkpoint layout train_fastspeech.py:235-244 writes, hp restored from its hp_str like inference.py:148-152."""
+    from fastspeech2_b200.hparams import DEFAULT_YAML
+    ck = {"model": weights, "optim": {"state": {}, "param_groups": []}, "step": 123000, "hp_str": open(DEFAULT_YAML).read(),
+          "githash": "abc1234"}
+    path = tmp_path / "fs2_abc1234_123k_steps.pyt"
+    torch.save(ck, path)
+    m = FeedForwardTransformer.from_checkpoint(str(path))
+    assert not m.training and m.idim == 68 and m.odim == 80
+    got = m.state_dict()
+    assert list(got.keys()) == list(weights.keys())
+    assert all(torch.equal(got[k], weights[k]) for k in weights)
+    old_style = FeedForwardTransformer.from_checkpoint(dict(weights), hp=load_hp())       # bare state_dict (--old_model)
+    assert torch.equal(old_style.state_dict()["feat_out.weight"], weights["feat_out.weight"])
+    with pytest.raises(ValueError):
+        FeedForwardTransformer.from_checkpoint(dict(weights))
+
+
 def test_precision_names(model):
     """The extra `precision` keyword: default from FS2_PRECISION else "f16"; unknown names are rejected; the header's
     FS2_MATH_* values and the ctypes table agree."""
