@@ -116,8 +116,11 @@ int norm_rows(const RowNorm& r, cudaStream_t st);
 
 int dense(const TapGemm& g, int math_mode, cudaStream_t st, int cls) {
   const double M = (double)g.B * g.L;
+  // algorithmic bytes: operands at the width this launch reads them (fp16 copies: 2 B; fp32, or fp16 hi + lo: 4 B),
+  // the result at the width(s) it is written, the residual as fp32
+  const double e_in = g.x_h ? 2.0 : 4.0, e_out = (g.out ? 4.0 : 0.0) + (g.out_h ? 2.0 : 0.0);
   ProfScope prof_scope(cls, 2.0 * M * g.N * g.K * g.taps,
-               4.0 * (M * g.K + (double)g.taps * g.N * g.K + M * g.N * (g.resid ? 2 : 1)), st);
+               e_in * (M * g.K + (double)g.taps * g.N * g.K) + M * g.N * (e_out + (g.resid ? 4.0 : 0.0)), st);
   if (math_mode == FS2_MATH_TF32 && g.ln_gamma) return gemm_ln_tf32(g, st);   // fp16 operands / fp16 copy handled inside
   if (g.x_h) return tap_gemm_f16(g, st);
   if (math_mode == MATH_3XTF32) {
