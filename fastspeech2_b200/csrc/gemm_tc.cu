@@ -40,8 +40,9 @@
 // fp32 activations as two fp16 planes, hi = rn(x) and lo = rn(x - hi), the weights are split the same way at load
 // time, and the GEMM loads all four operand tiles by TMA and runs the three products on kind::f16 -- no split warps, no
 // shared-memory rewrite, and a pipeline step covers twice the K for the same 12 MMAs.  hi + lo carries 22 mantissa
-// bits like the tf32 split (lo may be an fp16 subnormal: its absolute error, 3e-8, is below fp32 epsilon for O(1)
-// activations and far below the tensor core's accumulation error).  The lo plane is addressed through the same tensor
+// bits where lo is a normal fp16 (|x| >= 2^-3); smaller elements -- all weights of a trained layer -- keep an absolute
+// error of up to 2^-25 = 3e-8 (subnormal lo), an output error floor of ~sqrt(K) * rms(x) * 2e-8 that sits well below
+// the tensor core's own accumulation error for O(1) results (tests/test_numerics_model.py).  The lo plane is addressed through the same tensor
 // map: plane stride = B*L rows, i.e. utterance index b + B.
 //
 // HALF = true, PRECISE = false (FS2_MATH_F16, the decoder's conv-FFN): the same pipeline on fp16 copies of the activations and weights
