@@ -3,7 +3,7 @@ mounted (/root/reference: the build container, not the GPU box), in a subprocess
 `python -m fastspeech2_b200.dropin_run <script>` with cwd = the reference root, exactly how INTEGRATION.md tells a
 reference user to switch over (a plain PYTHONPATH entry is not enough: a script's own directory precedes it):
 
-  * the UNMODIFIED `inference.py` and `evaluation.py` import, and their `FeedForwardTransformer` is this repo's class;
+  * the UNMODIFIED `inference.py`, `evaluation.py` and `train_fastspeech.py` import, and their `FeedForwardTransformer` is this repo's class;
   * it is constructed from the reference's own `HParam("configs/default.yaml")` object;
   * checkpoints move both ways: the real reference class's `state_dict()` loads strictly into ours and ours into it.
 Third-party modules the scripts import at module scope but do not need for this are stubbed.  CPU only: no
@@ -39,6 +39,9 @@ SCRIPT = textwrap.dedent('''
 
     import torch
     import inference, evaluation                      # the unmodified reference scripts
+    import train_fastspeech                           # `import fastspeech` form (train_fastspeech.py:1,37)
+    assert train_fastspeech.fastspeech.FeedForwardTransformer is inference.FeedForwardTransformer
+    assert len(train_fastspeech.valid_symbols) == 68  # idim of the reference's phoneme set (train_fastspeech.py:35)
     from utils.hparams import HParam                  # the reference's own config object
     ours = inference.FeedForwardTransformer
     assert ours is evaluation.FeedForwardTransformer
