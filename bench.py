@@ -283,6 +283,7 @@ def run_b200(args):
     from fastspeech2_b200 import FeedForwardTransformer, _lib, synthetic_state_dict
     from fastspeech2_b200.hparams import load_hp
     from fastspeech2_b200.synthetic import make_batch
+    from fastspeech2_b200.sharded import gather_mels_to_root
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -318,7 +319,10 @@ def run_b200(args):
             else:
                 out = model._forward(inp["xs"], inp["ilens"], inp["olens"], inp["ds"], inp["es"], inp["ps"], is_inference=False)
         if world > 1:   # the single exchange step: gather the final mel batch over NVLink
-            dist.all_gather_into_tensor(gathered, out[1])
+            if args.collective == "gather":     # rank 0 receives everything, the others only send their shard
+                gather_mels_to_root(out[1], dst=0, out=gathered if rank == 0 else None)
+            else:
+                dist.all_gather_into_tensor(gathered, out[1])
         return out[1]
 
     def step_e2e():
@@ -452,7 +456,7 @@ def run_b200(args):
         "config": {"workload": args.workload, "B_per_gpu": B, "global_batch": B * world, "T": T, "L": L,
                    "mode": "teacher-forced _forward, eval, no_grad" + (", one CUDA graph per step" if args.graph else ", eager launches"),
                    "parallelism": f"dp{world}",
-                   "collective": "one NCCL all_gather of the [B,L,80] mel shard" if world > 1 else "none",
+                   "collective": (f"one NCCL {args.collective} of the [B,L,80] mel shard" if world > 1 else "none"),
                    "l2": "per-step working set ~0.9 GB of activations >> 126 MB L2; no flush needed",
                    "tolerance": "fp32 mode: max-abs 1e-4 vs CPU oracle; tf32 and f16 modes: max-abs 1e-2, mean-abs 1e-3 (tests/test_gpu_parity.py)"},
         "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -486,6 +490,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default=os.environ.get("FS2_PRECISION", "f16"), choices=["fp32", "tf32", "3xtf32", "f16"])
     ap.add_argument("--cpu-sample-batch", type=int, default=8)
+    ap.add_argument("--collective", default="all_gather", choices=["all_gather", "gather"],
+                    help="N>1: all ranks receive all mels (default, measured) or only rank 0 does (gather to root)")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (default), 0: eager launches")
     args = ap.parse_args()
     if args.impl == "reference":

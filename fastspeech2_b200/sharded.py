@@ -59,6 +59,25 @@ def gather_mels(mel: torch.Tensor, olens: torch.Tensor, group: Optional[dist.Pro
     return mels, lens
 
 
+def gather_mels_to_root(mel: torch.Tensor, dst: int = 0, group: Optional[dist.ProcessGroup] = None,
+                        out: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """Gather equal-shape `[B, L, odim]` mel shards on rank `dst` only (the other ranks just send their 1/N share):
+    the "gather of the final mel batch" of SURVEY section 8e without the N-fold fan-out of an all-gather.  Returns the
+    `[world*B, L, odim]` batch on `dst` (written into `out` when given) and None elsewhere."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return mel
+    B, L, D = mel.shape
+    rank = dist.get_rank(group)
+    if rank == dst:
+        if out is None:
+            out = torch.empty((world * B, L, D), dtype=mel.dtype, device=mel.device)
+        dist.gather(mel.contiguous(), list(out.view(world, B, L, D).unbind(0)), dst=dst, group=group)
+        return out
+    dist.gather(mel.contiguous(), None, dst=dst, group=group)
+    return None
+
+
 def synthesize_sharded(model, xs: torch.Tensor, ilens: torch.Tensor, group: Optional[dist.ProcessGroup] = None):
     """Batched `is_inference=True` synthesis of a global batch: every rank passes the same global
     `xs [B,T]` / `ilens [B]`, runs its shard and receives all mels.  Returns (mels, olens)."""

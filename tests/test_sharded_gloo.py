@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from fastspeech2_b200.sharded import gather_mels, shard_bounds
+from fastspeech2_b200.sharded import gather_mels, gather_mels_to_root, shard_bounds
 
 
 def test_shard_bounds_partition():
@@ -52,3 +52,22 @@ def test_gather_mels_world2_ragged():
 
 def test_gather_mels_world2_equal_single_collective():
     mp.spawn(_worker, args=(2, _free_port(), True), nprocs=2, join=True)
+
+
+def _root_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        full = torch.randn(8, 6, 5, generator=torch.Generator().manual_seed(1))
+        lo, hi = shard_bounds(8, rank, world)
+        got = gather_mels_to_root(full[lo:hi].contiguous(), dst=0)
+        if rank == 0:
+            assert torch.equal(got, full)
+        else:
+            assert got is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_mels_to_root_world2():
+    mp.spawn(_root_worker, args=(2, _free_port()), nprocs=2, join=True)
