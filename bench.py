@@ -13,14 +13,20 @@ linear, Postnet (teacher-forced durations so the frame count is fixed; SURVEY.md
 plus -- for N > 1 -- the single NCCL all-gather of the final mels.  Workload c2: B=64,
 T=100 phonemes, L=800 frames per utterance per GPU (weak scaling: every rank owns its shard).
 
+Precision: the default (and the headline `value` / `dtype`) is "3xf16" -- every contraction of the path, both attention
+products included, error-compensated on the tensor cores: fp32-class results (parity gate max-abs 1e-4 against the fp32
+reference, the reference's own precision).  The 10-bit-mantissa fast modes are measured beside it in `modes`.
+
 `value`  : whole-job frames/s with inputs resident in HBM, CUDA-event timed, max over ranks.
 `e2e`    : same through the public API with HOST (pinned) inputs: H2D of xs/ilens/olens/ds/es/ps
-           and D2H of the mel batch inside the timed region, every step.
+           and D2H of the mel batch inside the timed region, every step (mel copy on a side stream,
+           two captured graphs with their own output buffers alternate so the copy of step i overlaps step i+1).
 `roofline`: dominant kernel class (decoder conv-FFN w_1: k=9 conv 384->1024 as a tap-GEMM),
            algorithmic FLOPs per launch / its CUDA-event duration measured by the library's
            per-kernel-class event profiler on extra steps of this same workload.
-`cpu_baseline`: the CPU oracle port (same ATen calls as the reference, oracle/fs2_oracle.py) on a
-           bounded sample of the same workload, all host threads.
+`cpu_baseline`: the UNMODIFIED reference (`baseline/_ref`, staged by tools/make_baseline_ref.py) on a
+           bounded sample of the same workload on the host cores (kind "reference"); the oracle port if the
+           staged reference is absent (kind "port").
 """
 from __future__ import annotations
 
@@ -123,26 +129,20 @@ def ncu_traffic(kernel: str, precision: str = "tf32"):
 
 
 FMA_PEAK = 2 * 148 * 128 * 1.965e9 / 1e12      # fp32 FMA pipe: 148 SM x 128 lanes x 2 flop x 1.965 GHz (nominal)
-F16_CLASSES = ("dec.qkv_proj", "dec.ffn_w1_conv9", "dec.ffn_w2", "feat_out", "postnet.conv5")
-ATTN_CLASSES = ("enc.attention", "dec.attention")
 
 
-def class_peak(precision: str, cls: str, tf_sus: float):
+def class_peak(precision: str, cls: str, tf_peak: float):
     """Tensor / FMA peak (TFLOP/s) that bounds profiler class `cls` in `precision` mode, and how it was derived
-    (which instruction kind each class runs on)."""
+    (which instruction kind each class runs on).  `tf_peak` is the measured dense bf16 rate."""
     fma = (FMA_PEAK, "fp32 FMA pipe = 148 SM x 128 lanes x 2 x 1.965 GHz (nominal)")
-    f16 = (tf_sus, "kind::f16 dense = the measured sustained bf16 rate")
-    tf32 = (tf_sus / 2.0, "kind::tf32 dense = 1/2 of the measured sustained bf16 rate")
-    x3 = (tf_sus / 3.0, "3xF16 (three kind::f16 products per term) = 1/3 of the measured sustained bf16 rate")
-    if precision == "fp32" or cls == "enc.attention":
+    f16 = (tf_peak, "kind::f16 dense = the measured bf16 rate")
+    tf32 = (tf_peak / 2.0, "kind::tf32 dense = 1/2 of the measured bf16 rate")
+    x3 = (tf_peak / 3.0, "3xF16 (three kind::f16 products per term) = 1/3 of the measured bf16 rate")
+    if precision == "fp32":
         return fma
-    if cls.startswith("enc.") or cls.startswith("predictor."):
+    if cls.startswith("enc.") or cls.startswith("predictor.") or precision in ("3xtf32", "3xf16"):
         return x3
-    if precision == "3xtf32":
-        return fma if cls in ATTN_CLASSES else x3
-    if precision == "f16" and cls in F16_CLASSES:
-        return f16
-    return tf32
+    return f16 if precision == "f16" else tf32
 
 
 def peaks():
@@ -153,55 +153,61 @@ def peaks():
     return 6650.0, 1590.0, 1400.0, "fallback (B200_PROFILING.md)"
 
 
-def oracle_frames_per_s(B: int, T: int, L: int, steps: int, warmup: int):
-    """CPU oracle port on B utterances of the workload.  PyTorch's CPU kernels do not scale to every core of a
-    128-thread host on these shapes (oversubscription makes them slower), so the thread count is calibrated on a
-    2-utterance forward over {16, 32, 64, all} and the fastest is used and reported -- the reference at its best."""
+def cpu_frames_per_s(B: int, T: int, L: int, steps: int, warmup: int, threads: int = 32):
+    """The reference's own CPU path on B utterances of the workload: the UNMODIFIED `FeedForwardTransformer._forward` from
+    `baseline/_ref` (kind "reference"), or the oracle port when the staged reference is absent (kind "port").  PyTorch's
+    CPU kernels do not scale to every core of a 128-thread host on these shapes (oversubscription makes them slower;
+    measured in round 1: 16-32 threads is the optimum), so the thread count is fixed at min(32, cores) and reported."""
     from fastspeech2_b200 import synthetic_state_dict
     from fastspeech2_b200.synthetic import make_batch
-    from oracle import fs2_oracle as O
-    ncpu = os.cpu_count() or 1
-    sd = synthetic_state_dict(0)
-    cal = make_batch(2, T, L, seed=99)
-    best, cores = None, ncpu
-    for nt in sorted({min(ncpu, c) for c in (16, 32, 64, ncpu)}):
-        torch.set_num_threads(nt)
-        with torch.no_grad():
-            O.forward_path(sd, cal["xs"], cal["ilens"], cal["olens"], cal["ds"].clone(), cal["es"], cal["ps"], False)
-            t0 = time.perf_counter()
-            O.forward_path(sd, cal["xs"], cal["ilens"], cal["olens"], cal["ds"].clone(), cal["es"], cal["ps"], False)
-            dt = time.perf_counter() - t0
-        if best is None or dt < best:
-            best, cores = dt, nt
+    from oracle import ref_import
+    cores = min(threads, os.cpu_count() or 1)
     torch.set_num_threads(cores)
+    sd = synthetic_state_dict(0)
     bt = make_batch(B, T, L, seed=1234)
+    if ref_import.available():
+        cls, hp = ref_import.load_reference()
+        model = cls(68, 80, hp)
+        model.load_state_dict(sd, strict=True)
+        model.eval()
+        kind = "reference"
+
+        def fwd():
+            model._forward(bt["xs"], bt["ilens"], bt["olens"], bt["ds"].clone(), bt["es"], bt["ps"], is_inference=False)
+    else:
+        from oracle import fs2_oracle as O
+        kind = "port"
+
+        def fwd():
+            O.forward_path(sd, bt["xs"], bt["ilens"], bt["olens"], bt["ds"].clone(), bt["es"], bt["ps"], False)
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            O.forward_path(sd, bt["xs"], bt["ilens"], bt["olens"], bt["ds"].clone(), bt["es"], bt["ps"], False)
+            fwd()
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     dt = sum(times) / len(times)
-    return B * L / dt, dt, cores
+    return B * L / dt, dt, cores, kind
 
 
 def run_reference(args):
-    """Reference arm: the reference's own CPU implementation of the path = the oracle port (the
-    reference is pure Python over ATen; oracle/fs2_oracle.py issues the same ATen calls and is
-    pinned bit-exact to it by tests/golden).  Rank 0 only."""
+    """Reference arm: the reference's own CPU implementation of the path -- the unmodified reference class staged in
+    baseline/_ref (falls back to the oracle port, which issues the same ATen calls and is pinned bit-exact to it by
+    tests/golden).  Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     B, T, L = WORKLOADS[args.workload]
     Bs = min(B, args.cpu_sample_batch)
-    fps, dt, cores = oracle_frames_per_s(Bs, T, L, args.steps, args.warmup)
-    sample = f"{Bs} of the {B} utterances of workload {args.workload} (T={T}, L={L}) per step"
+    fps, dt, cores, kind = cpu_frames_per_s(Bs, T, L, args.steps, args.warmup, args.cpu_threads)
+    sample = f"{Bs} of the {B} utterances of workload {args.workload} (T={T}, L={L}) per step, {cores} threads"
     line = {
         "impl": "reference", "metric": "mel-frames/sec (batched inference)", "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "B_per_gpu": B, "T": T, "L": L, "mode": "teacher-forced _forward, eval, no_grad"},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": args.workload, "B_per_gpu": B, "T": T, "L": L, "mode": "teacher-forced _forward, eval, no_grad",
+                   "same_config": Bs == B},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "rtf": (1.0 / fps) / (HOP / SR),
     }
@@ -297,39 +303,20 @@ def run_b200(args):
     lib = _lib.load()
 
     B, T, L = WORKLOADS[args.workload]
-    model = FeedForwardTransformer(68, 80, load_hp(), precision=args.precision)
-    model.load_state_dict(synthetic_state_dict(0), strict=True)
-    model = model.to(dev).eval()
+    sd = synthetic_state_dict(0)
     bt = make_batch(B, T, L, seed=1234 + rank)          # rank r owns utterances [r*B, (r+1)*B)
     keys = ("xs", "ilens", "olens", "ds", "es", "ps")
     host = {k: bt[k].pin_memory() for k in keys}
     devin = {k: bt[k].to(dev) for k in keys}
     frames_rank = int(bt["olens"].sum())
     gathered = torch.empty((world * B, L, 80), dtype=torch.float32, device=dev) if world > 1 else None
-    mel_host = torch.empty((B, L, 80), dtype=torch.float32).pin_memory()
+    mel_host = [torch.empty((B, L, 80), dtype=torch.float32).pin_memory() for _ in range(2)]
+    copy_stream = torch.cuda.Stream(dev)
 
-    graphed = None
-    if args.graph:   # the whole step (all kernel launches of the library) as one CUDA graph (public API: model.graphed_forward)
-        graphed = model.graphed_forward(*[devin[k] for k in keys])
-
-    def step(inp):
-        with torch.no_grad():
-            if graphed is not None:
-                out = graphed(inp["xs"], inp["ilens"], inp["olens"], inp["ds"], inp["es"], inp["ps"])
-            else:
-                out = model._forward(inp["xs"], inp["ilens"], inp["olens"], inp["ds"], inp["es"], inp["ps"], is_inference=False)
-        if world > 1:   # the single exchange step: gather the final mel batch over NVLink
-            if args.collective == "gather":     # rank 0 receives everything, the others only send their shard
-                gather_mels_to_root(out[1], dst=0, out=gathered if rank == 0 else None)
-            else:
-                dist.all_gather_into_tensor(gathered, out[1])
-        return out[1]
-
-    def step_e2e():
-        inp = {k: host[k].to(dev, non_blocking=True) for k in keys}
-        mel = step(inp)
-        mel_host.copy_(mel, non_blocking=True)
-        return mel
+    def build(precision):
+        m = FeedForwardTransformer(68, 80, load_hp(), precision=precision)
+        m.load_state_dict(sd, strict=True)
+        return m.to(dev).eval()
 
     def barrier():
         if world > 1:
@@ -337,13 +324,13 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
+        for i in range(warmup):
+            fn(i)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            fn()
+        for i in range(steps):
+            fn(i)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -353,6 +340,58 @@ def run_b200(args):
             ms = float(t)
         return ms / steps
 
+    def make_steps(model):
+        """(device-resident step, end-to-end step, flush) for one model.  Graph mode: two captured graphs with their own
+        static inputs / outputs alternate, so the D2H copy of step i (side stream) overlaps step i+1; the length
+        validation is deferred (checked at the start of the next call), so replays queue back to back."""
+        graphs = [model.graphed_forward(*[devin[k] for k in keys]) for _ in range(2)] if args.graph else None
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def collective(mel):
+            if world > 1:   # the single exchange step: gather the final mel batch over NVLink
+                if args.collective == "gather":     # rank 0 receives everything, the others only send their shard
+                    gather_mels_to_root(mel, dst=0, out=gathered if rank == 0 else None)
+                else:
+                    dist.all_gather_into_tensor(gathered, mel)
+
+        def step(i):
+            with torch.no_grad():
+                if graphs is not None:
+                    out = graphs[i & 1].replay(validate="deferred")    # inputs already sit in the graph's static buffers
+                else:
+                    out = model._forward(*[devin[k] for k in keys], is_inference=False)
+            collective(out[1])
+            return out[1]
+
+        def step_e2e(i):
+            cur = torch.cuda.current_stream(dev)
+            with torch.no_grad():
+                if graphs is not None:
+                    g = graphs[i & 1]
+                    cur.wait_event(copied[i & 1])                       # its previous output has left for the host
+                    for dst, k in zip(g.inputs, keys):
+                        dst.copy_(host[k], non_blocking=True)           # H2D straight into the graph's static inputs
+                    out = g.replay(validate="deferred")
+                else:
+                    inp = [host[k].to(dev, non_blocking=True) for k in keys]
+                    out = model._forward(*inp, is_inference=False)
+            collective(out[1])
+            done = torch.cuda.Event()
+            done.record(cur)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done)
+                mel_host[i & 1].copy_(out[1], non_blocking=True)
+                copied[i & 1].record(copy_stream)
+            return out[1]
+
+        def flush():
+            if graphs is not None:
+                for g in graphs:
+                    g.flush()
+            copy_stream.synchronize()
+        return step, step_e2e, flush
+
+    model = build(args.precision)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -362,12 +401,15 @@ def run_b200(args):
         n0 = lib.fs2_kernel_launches()
         model._forward(*[devin[k] for k in keys], is_inference=False)
     launches_per_step = lib.fs2_kernel_launches() - n0
-    for _ in range(max(args.warmup, 3)):
-        step(devin)
+    step, step_e2e, flush = make_steps(model)
+    for i in range(max(args.warmup, 3)):
+        step(i)
     torch.cuda.synchronize()
     t_begin = time.time()
-    ms_step = timed(lambda: step(devin), args.steps, 0)
+    ms_step = timed(step, args.steps, 0)
+    flush()
     ms_e2e = timed(step_e2e, args.steps, 2)
+    flush()
     clocks = sampler.stop(t_begin, time.time()) if sampler else None
     if clocks is not None:
         clocks["window"] = "samples every 100 ms during the device-timed loop and the e2e loop"
@@ -421,6 +463,26 @@ def run_b200(args):
         lat = {"ms": lat_ms, "frames": int(mel1.shape[0]), "rtf": (lat_ms * 1e-3) / (mel1.shape[0] * HOP / SR),
                "note": "model.inference(x) for one 50-phoneme utterance, wall clock incl. the host read of Lmax"}
 
+    # the 10-bit-mantissa fast modes beside the headline (same workload, same timing rules; N = 1 only)
+    modes = None
+    if world == 1 and args.modes:
+        modes = {}
+        del step, step_e2e, flush
+        for prec in [p_ for p_ in args.modes.split(",") if p_ and p_ != args.precision]:
+            m2 = build(prec)
+            st2, st2_e2e, fl2 = make_steps(m2)
+            for i in range(3):
+                st2(i)
+            torch.cuda.synchronize()
+            ms2 = timed(st2, args.steps, 0); fl2()
+            ms2e = timed(st2_e2e, args.steps, 2); fl2()
+            modes[prec] = {"value": frames_rank / (ms2 * 1e-3), "unit": "frames/s", "ms_per_step": ms2,
+                           "e2e": frames_rank / (ms2e * 1e-3), "e2e_ms_per_step": ms2e,
+                           "tolerance": {"f16": "max-abs 5e-3, mean-abs 5e-4", "tf32": "max-abs 1e-2, mean-abs 1e-3",
+                                         "fp32": "max-abs 1e-4"}.get(prec, "max-abs 1e-4, mean-abs 1e-5") + " vs the fp32 reference"}
+            del m2, st2, st2_e2e, fl2
+            torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -431,24 +493,28 @@ def run_b200(args):
     value = frames / (ms_step * 1e-3)
     e2e = frames / (ms_e2e * 1e-3)
     h2d = sum(host[k].numel() * host[k].element_size() for k in keys)
-    d2h = mel_host.numel() * 4
+    d2h = mel_host[0].numel() * 4
     mf = mflop_per_frame(T, L)
     roof = None
+    gpu_busy = None
     if prof:
         tot = sum(v["ms"] for v in prof.values())
+        gpu_busy = tot / 3
         top = max(prof, key=lambda k: prof[k]["ms"])
-        tensor_peak, peak_note = class_peak(args.precision, top, tf_sus)
+        # a kernel class timed launch by launch with events at full clocks inside a ~10 ms step: the burst figure applies
+        tensor_peak, peak_note = class_peak(args.precision, top, tf_burst)
         pk = prof[top]
         achieved = pk["flop"] / (pk["ms"] * 1e-3) / 1e12 if pk["ms"] > 0 else 0.0
         roof = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                 "frac": achieved / tensor_peak, "traffic": ncu_traffic(top, args.precision),
                 "algorithmic_bytes_per_launch": pk["bytes"] / pk["launches"], "algorithmic_flop_per_launch": pk["flop"] / pk["launches"],
                 "avg_launch_ms": pk["ms"] / pk["launches"], "share_of_step": pk["ms"] / tot,
-                "peak_source": peak_src + "; " + peak_note,
+                "peak_source": peak_src + " burst bf16 figure (kernel timed alone by CUDA events); " + peak_note,
+                "whole_step_frac_of_burst": (value / world * mf / 1e6) / (tf_burst / (3.0 if args.precision in ("3xtf32", "3xf16") else 1.0)),
                 "classes": {k: {"ms_per_step": v["ms"] / 3, "launches_per_step": v["launches"] // 3,
                                 "tflops": (v["flop"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 else None,
                                 "gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else None} for k, v in prof.items()}}
-    cpu_fps, cpu_dt, cores = oracle_frames_per_s(min(B, args.cpu_sample_batch), T, L, 1, 1) if args.gpus == 1 else (None, None, None)
+    cpu = cpu_frames_per_s(min(B, args.cpu_sample_batch), T, L, 1, 1, args.cpu_threads) if args.gpus == 1 else None
     line = {
         "metric": "mel-frames/sec (batched inference)", "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -456,26 +522,37 @@ def run_b200(args):
         "config": {"workload": args.workload, "B_per_gpu": B, "global_batch": B * world, "T": T, "L": L,
                    "mode": "teacher-forced _forward, eval, no_grad" + (", one CUDA graph per step" if args.graph else ", eager launches"),
                    "parallelism": f"dp{world}",
+                   "precision": {"3xf16": "fp32-class: every contraction incl. attention error-compensated on tcgen05 (fp16 hi+lo operand planes, 3 products per term, fp32 accumulation)",
+                                 "3xtf32": "fp32-class: every contraction incl. attention error-compensated on tcgen05 (fp16 hi+lo operand planes, 3 products per term, fp32 accumulation)",
+                                 "f16": "decoder side on kind::f16 (10-bit mantissa operands), encoder + predictors error-compensated",
+                                 "tf32": "decoder side on kind::tf32, encoder + predictors error-compensated",
+                                 "fp32": "fp32 FMA on CUDA cores"}[args.precision],
                    "collective": (f"one NCCL {args.collective} of the [B,L,80] mel shard" if world > 1 else "none"),
                    "l2": "per-step working set ~0.9 GB of activations >> 126 MB L2; no flush needed",
-                   "tolerance": "fp32 mode: max-abs 1e-4 vs CPU oracle; tf32 and f16 modes: max-abs 1e-2, mean-abs 1e-3 (tests/test_gpu_parity.py)"},
+                   "tolerance": "3xf16 (default): max-abs 1e-4, mean-abs 1e-5 vs the CPU fp32 oracle on the mels, durations / bucket ids bit-exact; "
+                                "fp32: 1e-4; f16: 5e-3 / 5e-4; tf32: 1e-2 / 1e-3 (tests/test_gpu_parity.py)"},
         "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches_per_step * args.steps),
         "gpu_launches_per_step": int(launches_per_step),
+        "gpu_busy_ms_per_step": gpu_busy,
+        "gpu_busy_note": "sum of the per-kernel CUDA-event durations of one eager step (library profiler); value's ms_per_step is K graph replays queued back to back",
         "clocks": clocks,
         "rtf": (1.0 / value) / (HOP / SR),
         "model_tflops": value * mf / 1e6,
         "mflop_per_frame": mf,
     }
+    if modes:
+        line["modes"] = modes
     if inf:
         line["inference_mode"] = inf
     if lat:
         line["single_utterance_latency"] = lat
     if roof:
         line["roofline"] = roof
-    if cpu_fps:
-        line["cpu_baseline"] = {"value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                                "sample": f"{min(B, args.cpu_sample_batch)} of the {B} utterances of workload {args.workload}, 1 warm-up + 1 timed forward"}
+    if cpu:
+        cpu_fps, cpu_dt, cores, kind = cpu
+        line["cpu_baseline"] = {"value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": kind,
+                                "sample": f"{min(B, args.cpu_sample_batch)} of the {B} utterances of workload {args.workload}, 1 warm-up + 1 timed forward, {cores} threads"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -488,8 +565,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default=os.environ.get("FS2_PRECISION", "f16"), choices=["fp32", "tf32", "3xtf32", "f16"])
-    ap.add_argument("--cpu-sample-batch", type=int, default=8)
+    ap.add_argument("--precision", default=os.environ.get("FS2_PRECISION", "3xf16"), choices=["fp32", "tf32", "3xtf32", "3xf16", "f16"])
+    ap.add_argument("--modes", default="f16,tf32", help="N=1: other precision modes measured beside the headline ('' = none)")
+    ap.add_argument("--cpu-sample-batch", type=int, default=64, help="utterances per CPU-reference step (64 = the full c2 batch)")
+    ap.add_argument("--cpu-threads", type=int, default=32, help="host threads of the CPU reference (fixed; oversubscription is slower)")
     ap.add_argument("--collective", default="all_gather", choices=["all_gather", "gather"],
                     help="N>1: all ranks receive all mels (default, measured) or only rank 0 does (gather to root)")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (default), 0: eager launches")

@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -14,7 +15,7 @@
 namespace fs2 {
 
 static thread_local char g_err[512] = "";
-unsigned long long g_kernel_launches = 0;
+std::atomic<unsigned long long> g_kernel_launches{0};
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -23,10 +24,10 @@ void set_error(const char* fmt, ...) {
 }
 
 struct Dense {           // one Linear / Conv1d in kernel layout
-  const float* w = nullptr;     // [taps][N][K]
-  const __half* w_h = nullptr;  // fp16 copy (decoder side, FS2_MATH_F16)
-  const __half* w_hi_h = nullptr;  // fp16 hi / lo split (3xF16, the error-compensated family)
-  const __half* w_lo_h = nullptr;
+  const float* w = nullptr;     // [taps][N][K] fp32 (fp32 FMA and kind::tf32 families)
+  const __half* w_hi = nullptr; // fp16 hi / lo planes of (scale * w): kind::f16 reads hi, 3xF16 reads both
+  const __half* w_lo = nullptr;
+  const float* w_inv = nullptr; // device scalar 1 / scale (a power of two chosen per layer at load time)
   const float* bias = nullptr;  // [N] or nullptr
   int N = 0, K = 0, taps = 1;
 };
@@ -49,9 +50,6 @@ struct Profiler {
   std::vector<ProfRec> recs;
 };
 static thread_local Profiler* t_prof = nullptr;
-static thread_local __half* t_split_ws = nullptr;   // scratch of the running stage for the 3xF16 activation planes
-static thread_local const float* t_split_of = nullptr;   // fp32 tensor whose planes t_split_ws currently holds (or null)
-static thread_local int64_t t_split_rows = 0; static thread_local int t_split_K = 0;
 struct ProfScope {
   ProfRec r; bool live; cudaStream_t st;
   ProfScope(int cls, double flop, double bytes, cudaStream_t s) : live(t_prof && t_prof->on), st(s) {
@@ -71,6 +69,7 @@ struct ProfScope {
 
 struct fs2_handle {
   fs2::Profiler prof;
+  int enc_pe_len = 0, dec_pe_len = 0;
   fs2_config cfg;
   int device = 0;
   bool loaded = false;
@@ -106,63 +105,54 @@ struct Bump {  // bump allocator over a caller-provided (or null = counting) buf
 
 using Map = std::unordered_map<std::string, const fs2_weight_desc*>;
 
-// FS2_FUSED_SPLIT=0 (debug / A-B): every 3xF16 GEMM runs its own pre-pass
-bool fused_split() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("FS2_FUSED_SPLIT"); v = e ? atoi(e) : 1; }
-  return v != 0;
-}
-int norm_rows(const RowNorm& r, cudaStream_t st);
+// selects the handle's device for the duration of an ABI call and restores the caller's (torch's) current device
+struct DeviceGuard {
+  int prev = -1; bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define FS2_DEVICE_GUARD(h)                                                              \
+  DeviceGuard _guard((h)->device);                                                       \
+  if (!_guard.ok) { set_error("cannot select device %d", (h)->device); return FS2_ERR_CUDA; }
 
 int dense(const TapGemm& g, int math_mode, cudaStream_t st, int cls) {
   const double M = (double)g.B * g.L;
-  // algorithmic bytes: operands at the width this launch reads them (fp16 copies: 2 B; fp32, or fp16 hi + lo: 4 B),
+  // algorithmic bytes: operands at the width this launch reads them (hi plane: 2 B; fp32, or hi + lo planes: 4 B),
   // the result at the width(s) it is written, the residual as fp32
-  const double e_in = g.x_h ? 2.0 : 4.0, e_out = (g.out ? 4.0 : 0.0) + (g.out_h ? 2.0 : 0.0);
+  const double e_in = g.xp ? (g.precise ? 4.0 : 2.0) : 4.0;
+  const double e_out = (g.out ? 4.0 : 0.0) + ((g.outp || g.vtp) ? (g.outp_lo ? 4.0 : 2.0) : 0.0);
   ProfScope prof_scope(cls, 2.0 * M * g.N * g.K * g.taps,
                e_in * (M * g.K + (double)g.taps * g.N * g.K) + M * g.N * (e_out + (g.resid ? 4.0 : 0.0)), st);
-  if (math_mode == FS2_MATH_TF32 && g.ln_gamma) return gemm_ln_tf32(g, st);   // fp16 operands / fp16 copy handled inside
-  if (g.x_h) return tap_gemm_f16(g, st);
-  if (math_mode == MATH_3XTF32) {
-    // the planes of g.x may already be in the scratch: written by the LayerNorm that produced x, or by the previous
-    // GEMM's pre-pass over the same x (energy / pitch predictors share their input)
-    TapGemm gs = g;
-    gs.split_ws = t_split_ws;
-    gs.split_ready = fused_split() && t_split_of == g.x && t_split_rows == (int64_t)g.B * g.L && t_split_K == g.K && g.ldx == g.K;
-    t_split_of = g.x; t_split_rows = (int64_t)g.B * g.L; t_split_K = g.K;
-    if (!fused_split() || g.ldx != g.K) t_split_of = nullptr;
-    return tap_gemm_3xtf32(gs, st);
-  }
+  if (g.ln_gamma) return gemm_ln_tf32(g, st);       // fused residual + LayerNorm epilogue (tf32 on fp32 rows, or f16 on hi planes)
+  if (g.xp) return tap_gemm_planes(g, st);
   return math_mode == FS2_MATH_TF32 ? tap_gemm_tf32(g, st) : tap_gemm_fp32(g, st);
 }
-// LayerNorm whose output feeds a 3xF16 GEMM next: write the operand planes from the same kernel
-int norm_rows_split(RowNorm r, cudaStream_t st) {
-  if (fused_split() && r.out && r.ldo == r.C && t_split_ws) {
-    r.split_out = t_split_ws;
-    t_split_of = r.out; t_split_rows = r.rows; t_split_K = r.C;
-  }
-  return norm_rows(r, st);
-}
 int norm_rows(const RowNorm& r, cudaStream_t st) {
-  ProfScope prof_scope(P_ROWNORM, 8.0 * r.rows * r.C, 4.0 * r.rows * r.C * (1 + (r.resid ? 1 : 0) + (r.out ? 1 : 0)), st);
+  ProfScope prof_scope(P_ROWNORM, 8.0 * r.rows * r.C,
+                       4.0 * r.rows * r.C * (1 + (r.resid ? 1 : 0) + (r.out ? 1 : 0)) + (r.split_out ? (r.split_lo ? 4.0 : 2.0) * r.rows * r.C : 0.0), st);
   return row_norm(r, st);
 }
-int attention(int math_mode, const float* qkv, const float* vt, int lpad, const int64_t* lens, int B, int L, int C, int heads,
-              float* ctx, cudaStream_t st, int cls) {
-  ProfScope prof_scope(cls, 4.0 * B * (double)L * L * C, 4.0 * 4.0 * B * (double)L * C, st);
-  // the encoder (MATH_3XTF32) keeps the exact-fp32 attention core: 0.2 ms at c2, and its scores feed the durations
-  return math_mode == FS2_MATH_TF32 ? attention_tf32(qkv, vt, lpad, lens, B, L, C, heads, ctx, st)
-                                    : attention_fp32(qkv, lens, B, L, C, heads, ctx, st);
-}
 inline int round4(int x) { return (x + 3) & ~3; }
+inline int round8(int x) { return (x + 7) & ~7; }
 
 TapGemm make_gemm(const Dense& d, const float* x, int ldx, int B, int L, int act, const float* resid, int ldr, float* out,
                   int ldo) {
   TapGemm g;
-  g.x = x; g.ldx = ldx; g.B = B; g.L = L; g.K = d.K; g.w = d.w; g.w_h = d.w_h; g.w_hi_h = d.w_hi_h; g.w_lo_h = d.w_lo_h; g.bias = d.bias; g.N = d.N; g.taps = d.taps;
+  g.x = x; g.ldx = ldx; g.B = B; g.L = L; g.K = d.K; g.w = d.w; g.bias = d.bias; g.N = d.N; g.taps = d.taps;
   g.act = act; g.resid = resid; g.ldr = ldr; g.out = out; g.ldo = ldo;
   return g;
 }
+// contraction on operand planes written by this library (kPlaneScale): kind::f16 on the hi planes, or 3xF16 (x3)
+TapGemm make_gemm_p(const Dense& d, const __half* xp, int B, int L, bool x3, int act, const float* resid, int ldr, float* out,
+                    int ldo) {
+  TapGemm g = make_gemm(d, nullptr, d.K, B, L, act, resid, ldr, out, ldo);
+  g.xp = xp; g.w_hi = d.w_hi; g.w_lo = d.w_lo; g.w_inv = d.w_inv; g.a_inv = kPlaneInv; g.precise = x3;
+  return g;
+}
+void planes_out(TapGemm& g, __half* outp, int ldo_p, bool lo) { g.outp = outp; g.ldo_p = ldo_p; g.outp_lo = lo; }
 
 RowNorm make_norm(const Norm& n, const float* x, int ldx, int64_t rows, int C, float* out, int ldo) {
   RowNorm r;
@@ -171,89 +161,149 @@ RowNorm make_norm(const Norm& n, const float* x, int ldx, int64_t rows, int C, f
   return r;
 }
 
-// FS2_F16_PARTS (debug / bisecting): which pieces of FS2_MATH_F16 beyond the conv-FFN are on.  2 = LayerNorm-fused
-// projections (gemm_ln_tc.cu) with fp16 operands / fp16 copy, 4 = mel projection + Postnet in f16, 8 = q|k|v in f16.
-int f16_parts_mask() {
-  static int m = -1;
-  if (m < 0) { const char* e = getenv("FS2_F16_PARTS"); m = e ? atoi(e) : 14; }
-  return m;
+// FS2_FUSE_LN=0 (debug / A-B): FS2_MATH_F16 runs GEMM -> LayerNorm as two kernels instead of the fused epilogue
+bool fuse_ln_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FS2_FUSE_LN"); v = e ? atoi(e) : 1; }
+  return v != 0;
 }
 
-// FFT blocks on xin; the result lands in *result (one of the two ping-pong buffers xin / y)
-int run_blocks(const std::vector<Block>& blocks, float* xin, float* yin, float* qkv, float* vt, float* ctx, float* hid,
-               const int64_t* lens, int B, int L, int C, int heads, int math_mode, bool is_dec, cudaStream_t st, float** result,
-               __half* xh = nullptr) {
+struct BlockBufs {
+  float *x, *y;            // fp32 rows [rows, C]: block input / output ping-pong (the residual stream)
+  float *qkv, *vt, *ctx, *hid;   // fp32 families: q|k|v rows, transposed V, context, conv-FFN hidden
+  __half *xp, *qkp, *vtp, *ctxp, *hidp;   // plane families: the same tensors as operand planes (qkp..hidp alias the fp32 ones)
+};
+
+// FFT blocks of the fp32-FMA and kind::tf32 families (fp32 rows everywhere); the result lands in *result
+int run_blocks(const std::vector<Block>& blocks, const BlockBufs& w, const int64_t* lens, int B, int L, int C, int heads,
+               int math_mode, bool is_dec, cudaStream_t st, float** result) {
   const int64_t rows = (int64_t)B * L;
   const int c_qkv = is_dec ? P_DEC_QKV : P_ENC_QKV, c_att = is_dec ? P_DEC_ATTN : P_ENC_ATTN;
   const int c_out = is_dec ? P_DEC_OUT : P_ENC_OUT, c_w1 = is_dec ? P_DEC_W1 : P_ENC_W1, c_w2 = is_dec ? P_DEC_W2 : P_ENC_W2;
-  float *x = xin, *y = yin;
-  const int f16_parts = f16_parts_mask();
+  float *x = w.x, *y = w.y;
   for (const Block& k : blocks) {
     int rc;
     // q | k | v projection (attention.py:48-50), one GEMM with N = 3C
-    TapGemm gq = make_gemm(k.qkv, x, C, B, L, ACT_NONE, nullptr, 0, qkv, 3 * C);
+    TapGemm gq = make_gemm(k.qkv, x, C, B, L, ACT_NONE, nullptr, 0, w.qkv, 3 * C);
     if (math_mode == FS2_MATH_TF32) {  // V third stored transposed for the tensor-core attention (gemm_tc.cu epilogue)
-      gq.vt_out = vt; gq.vt_col0 = 2 * C; gq.vt_dk = C / heads; gq.vt_heads = heads; gq.vt_lpad = round4(L);
+      gq.vt_out = w.vt; gq.vt_col0 = 2 * C; gq.vt_dk = C / heads; gq.vt_heads = heads; gq.vt_lpad = round4(L);
     }
-    if (xh && (f16_parts & 8)) { gq.x_h = xh; gq.ldx_h = C; }   // xh holds the fp16 copy of x here (written by the LayerNorm before)
     if ((rc = dense(gq, math_mode, st, c_qkv))) return rc;
-    if ((rc = attention(math_mode, qkv, vt, round4(L), lens, B, L, C, heads, ctx, st, c_att))) return rc;
-    // x = LN(x + linear_out(ctx)) (attention.py:74, encoder.py:60-62); FS2_MATH_F16: also the fp16 copy for the conv-FFN
-    TapGemm go = make_gemm(k.out, ctx, C, B, L, ACT_NONE, x, C, y, C);
+    {
+      ProfScope prof_scope(c_att, 4.0 * B * (double)L * L * C, 4.0 * 4.0 * B * (double)L * C, st);
+      rc = math_mode == FS2_MATH_TF32 ? attention_tf32(w.qkv, w.vt, round4(L), lens, B, L, C, heads, w.ctx, st)
+                                      : attention_fp32(w.qkv, lens, B, L, C, heads, w.ctx, st);
+      if (rc) return rc;
+    }
+    // x = LN(x + linear_out(ctx)) (attention.py:74, encoder.py:60-62)
+    TapGemm go = make_gemm(k.out, w.ctx, C, B, L, ACT_NONE, x, C, y, C);
     go.ln_gamma = k.ln1.g; go.ln_beta = k.ln1.b; go.ln_eps = k.ln1.eps;
-    const bool fuse_ln = math_mode == FS2_MATH_TF32 && gemm_ln_tf32_supported(go) && (!xh || (f16_parts & 2));
-    if (fuse_ln) {   // fused: result in y, swap roles
-      go.out_h = xh; go.ldo_h = C;
+    if (math_mode == FS2_MATH_TF32 && gemm_ln_tf32_supported(go) && fuse_ln_enabled()) {   // fused: result in y, swap roles
       if ((rc = dense(go, math_mode, st, c_out))) return rc;
       float* t = x; x = y; y = t;
     } else {
       go.ln_gamma = nullptr;
       if ((rc = dense(go, math_mode, st, c_out))) return rc;
-      RowNorm r1 = make_norm(k.ln1, y, C, rows, C, x, C);
-      r1.out_h = xh; r1.ldo_h = C;
-      if ((rc = math_mode == MATH_3XTF32 ? norm_rows_split(r1, st) : norm_rows(r1, st))) return rc;   // feeds the conv-FFN
+      if ((rc = norm_rows(make_norm(k.ln1, y, C, rows, C, x, C), st))) return rc;
     }
     // conv-FFN: hid = relu(conv_k(x)); x = LN(x + conv_1(hid))  (modules.py:247-248, encoder.py:64-69)
-    TapGemm g1 = make_gemm(k.w1, x, C, B, L, ACT_RELU, nullptr, 0, hid, k.w1.N);
-    TapGemm g2 = make_gemm(k.w2, hid, k.w1.N, B, L, ACT_NONE, x, C, y, C);
-    if (xh) {   // fp16 operands: the hidden activations only ever exist as fp16 (in the same workspace slot)
-      __half* hid_h = reinterpret_cast<__half*>(hid);
-      g1.x_h = xh; g1.ldx_h = C; g1.out = nullptr; g1.ldo = 0; g1.out_h = hid_h; g1.ldo_h = k.w1.N;
-      g2.x_h = hid_h; g2.ldx_h = k.w1.N;
-    }
-    if ((rc = dense(g1, math_mode, st, c_w1))) return rc;
+    if ((rc = dense(make_gemm(k.w1, x, C, B, L, ACT_RELU, nullptr, 0, w.hid, k.w1.N), math_mode, st, c_w1))) return rc;
+    TapGemm g2 = make_gemm(k.w2, w.hid, k.w1.N, B, L, ACT_NONE, x, C, y, C);
     g2.ln_gamma = k.ln2.g; g2.ln_beta = k.ln2.b; g2.ln_eps = k.ln2.eps;
-    if (math_mode == FS2_MATH_TF32 && gemm_ln_tf32_supported(g2) && (!xh || (f16_parts & 2))) {
-      g2.out_h = xh; g2.ldo_h = C;             // fp16 copy of the block output: A operand of the next q|k|v / mel projection
+    if (math_mode == FS2_MATH_TF32 && gemm_ln_tf32_supported(g2) && fuse_ln_enabled()) {
       if ((rc = dense(g2, math_mode, st, c_w2))) return rc;
       float* t = x; x = y; y = t;
     } else {
       g2.ln_gamma = nullptr;
       if ((rc = dense(g2, math_mode, st, c_w2))) return rc;
-      RowNorm r2 = make_norm(k.ln2, y, C, rows, C, x, C);
-      r2.out_h = xh; r2.ldo_h = C;
-      if ((rc = math_mode == MATH_3XTF32 ? norm_rows_split(r2, st) : norm_rows(r2, st))) return rc;   // feeds the next GEMM
+      if ((rc = norm_rows(make_norm(k.ln2, y, C, rows, C, x, C), st))) return rc;
     }
   }
   *result = x;
   return FS2_OK;
 }
 
-// conv stack + scalar head (duration_predictor.py:64-86 / variance_predictor.py:39-60); exact fp32 or error-compensated
-int run_predictor(const Predictor& p, const float* x, int C, int B, int L, float* t1, float* t2, const int64_t* lens,
-                  float* head_out, int64_t* dur_out, int math_mode, cudaStream_t st) {
+// FFT blocks of the plane families: every contraction reads fp16 operand planes written by its producer and writes the
+// planes its consumer reads; fp32 rows exist only for the residual stream (x, y).  x3: error-compensated (hi + lo planes,
+// fp32-class); else kind::f16 on the hi planes with the residual + LayerNorm epilogue fused into the projections.
+// On entry w.xp holds the planes of w.x; on exit it holds the planes of *result.
+int run_blocks_planes(const std::vector<Block>& blocks, const BlockBufs& w, const int64_t* lens, int B, int L, int C, int heads,
+                      bool x3, bool is_dec, cudaStream_t st, float** result) {
   const int64_t rows = (int64_t)B * L;
-  const float* cur = x; int curC = C;
+  const int c_qkv = is_dec ? P_DEC_QKV : P_ENC_QKV, c_att = is_dec ? P_DEC_ATTN : P_ENC_ATTN;
+  const int c_out = is_dec ? P_DEC_OUT : P_ENC_OUT, c_w1 = is_dec ? P_DEC_W1 : P_ENC_W1, c_w2 = is_dec ? P_DEC_W2 : P_ENC_W2;
+  const int lpad = round8(L);
+  float *x = w.x, *y = w.y;
+  for (const Block& k : blocks) {
+    int rc;
+    // q | k | v projection (attention.py:48-50), one GEMM with N = 3C: q | k leave as planes [P][rows][2C], the V third
+    // as transposed planes [P][B*heads][dk][lpad]; no fp32 copy exists
+    TapGemm gq = make_gemm_p(k.qkv, w.xp, B, L, x3, ACT_NONE, nullptr, 0, nullptr, 0);
+    planes_out(gq, w.qkp, 2 * C, x3);
+    gq.vtp = w.vtp; gq.vt_col0 = 2 * C; gq.vt_dk = C / heads; gq.vt_heads = heads; gq.vt_lpad = lpad;
+    if ((rc = dense(gq, FS2_MATH_F16, st, c_qkv))) return rc;
+    {
+      ProfScope prof_scope(c_att, 4.0 * B * (double)L * L * C, (x3 ? 4.0 : 2.0) * 4.0 * B * (double)L * C, st);
+      if ((rc = attention_planes(w.qkp, w.vtp, lpad, lens, B, L, C, heads, x3, nullptr, w.ctxp, st))) return rc;
+    }
+    // x = LN(x + linear_out(ctx)) (attention.py:74, encoder.py:60-62); the LayerNorm also writes the conv-FFN's operand planes
+    TapGemm go = make_gemm_p(k.out, w.ctxp, B, L, x3, ACT_NONE, x, C, y, C);
+    go.ln_gamma = k.ln1.g; go.ln_beta = k.ln1.b; go.ln_eps = k.ln1.eps;
+    if (!x3 && gemm_ln_tf32_supported(go) && fuse_ln_enabled()) {   // fused: result in y, swap roles
+      planes_out(go, w.xp, C, false);
+      if ((rc = dense(go, FS2_MATH_F16, st, c_out))) return rc;
+      float* t = x; x = y; y = t;
+    } else {
+      go.ln_gamma = nullptr;
+      if ((rc = dense(go, FS2_MATH_F16, st, c_out))) return rc;
+      RowNorm r1 = make_norm(k.ln1, y, C, rows, C, x, C);
+      r1.split_out = w.xp; r1.split_lo = x3;
+      if ((rc = norm_rows(r1, st))) return rc;
+    }
+    // conv-FFN: hid = relu(conv_k(x)); x = LN(x + conv_1(hid))  (modules.py:247-248, encoder.py:64-69); the hidden
+    // activations exist only as planes
+    TapGemm g1 = make_gemm_p(k.w1, w.xp, B, L, x3, ACT_RELU, nullptr, 0, nullptr, 0);
+    planes_out(g1, w.hidp, k.w1.N, x3);
+    if ((rc = dense(g1, FS2_MATH_F16, st, c_w1))) return rc;
+    TapGemm g2 = make_gemm_p(k.w2, w.hidp, B, L, x3, ACT_NONE, x, C, y, C);
+    g2.ln_gamma = k.ln2.g; g2.ln_beta = k.ln2.b; g2.ln_eps = k.ln2.eps;
+    if (!x3 && gemm_ln_tf32_supported(g2) && fuse_ln_enabled()) {
+      planes_out(g2, w.xp, C, false);              // planes of the block output: A operand of the next q|k|v / mel projection
+      if ((rc = dense(g2, FS2_MATH_F16, st, c_w2))) return rc;
+      float* t = x; x = y; y = t;
+    } else {
+      g2.ln_gamma = nullptr;
+      if ((rc = dense(g2, FS2_MATH_F16, st, c_w2))) return rc;
+      RowNorm r2 = make_norm(k.ln2, y, C, rows, C, x, C);
+      r2.split_out = w.xp; r2.split_lo = x3;
+      if ((rc = norm_rows(r2, st))) return rc;
+    }
+  }
+  *result = x;
+  return FS2_OK;
+}
+
+// conv stack + scalar head (duration_predictor.py:64-86 / variance_predictor.py:39-60).  xp == nullptr: exact fp32 FMA on
+// the rows x; else error-compensated 3xF16 on the planes xp (the LayerNorms write the next layer's planes into t2p)
+int run_predictor(const Predictor& p, const float* x, const __half* xp, int C, int B, int L, float* t1, float* t2, __half* t2p,
+                  const int64_t* lens, float* head_out, int64_t* dur_out, cudaStream_t st) {
+  const int64_t rows = (int64_t)B * L;
+  const float* cur = x; const __half* cur_p = xp; int curC = C;
   for (int i = 0; i < p.layers; ++i) {
     int rc;
-    if ((rc = dense(make_gemm(p.conv[i], cur, curC, B, L, ACT_RELU, nullptr, 0, t1, p.conv[i].N), math_mode, st, P_PRED_GEMM))) return rc;
-    RowNorm r = make_norm(p.ln[i], t1, p.conv[i].N, rows, p.conv[i].N, t2, p.conv[i].N);
+    const int N = p.conv[i].N;
+    TapGemm g = xp ? make_gemm_p(p.conv[i], cur_p, B, L, true, ACT_RELU, nullptr, 0, t1, N)
+                   : make_gemm(p.conv[i], cur, curC, B, L, ACT_RELU, nullptr, 0, t1, N);
+    if ((rc = dense(g, FS2_MATH_FP32, st, P_PRED_GEMM))) return rc;
+    RowNorm r = make_norm(p.ln[i], t1, N, rows, N, xp ? nullptr : t2, N);
     if (i == p.layers - 1) {  // last layer: only the scalar head leaves the kernel
       r.out = nullptr; r.head_w = p.head_w; r.head_b = p.head_b; r.head_out = head_out; r.dur_out = dur_out;
       r.lens = lens; r.L = L;
+    } else if (xp) {
+      r.split_out = t2p; r.split_lo = 1;
     }
-    if ((rc = math_mode == MATH_3XTF32 ? norm_rows_split(r, st) : norm_rows(r, st))) return rc;
-    cur = t2; curC = p.conv[i].N;
+    if ((rc = norm_rows(r, st))) return rc;
+    cur = t2; cur_p = t2p; curC = N;
   }
   return FS2_OK;
 }
@@ -293,22 +343,28 @@ struct Packer {
     if (!bkey.empty()) { int rc = copy(bkey, N, &out->bias); if (rc) return rc; }
     return FS2_OK;
   }
-  // fp16 hi / lo planes for the error-compensated kernels (gemm_tc.cu, 3xF16)
+  // fp16 hi / lo planes of (s * w) with the layer's power-of-two scale s (gemm_tc.cu): kind::f16 reads the hi plane,
+  // 3xF16 reads both; the consuming epilogue multiplies by 1 / s (d->w_inv, a device scalar)
   int split(Dense* d) {
     const size_t n = (size_t)d->N * d->K * d->taps;
     __half* hh = (__half*)bump.bytes(n * sizeof(__half));
     __half* lh = (__half*)bump.bytes(n * sizeof(__half));
-    if (!counting) { int rc = split_f16(d->w, hh, lh, (long)n, st); if (rc) return rc; }
-    d->w_hi_h = hh; d->w_lo_h = lh;
+    float* sc = bump.floats(2);       // [scale, 1 / scale]
+    if (!counting) {
+      int rc = weight_scale(d->w, (long)n, sc, sc + 1, st); if (rc) return rc;
+      rc = split_f16(d->w, hh, lh, (long)n, sc, st); if (rc) return rc;
+    }
+    d->w_hi = hh; d->w_lo = lh; d->w_inv = sc + 1;
     return FS2_OK;
   }
-  // fp16 copy for the f16 family (gemm_tc.cu, HALF)
-  int half(Dense* d) {
-    const size_t n = (size_t)d->N * d->K * d->taps;
-    __half* hw = (__half*)bump.bytes(n * sizeof(__half));
-    if (!counting) { int rc = to_half(d->w, hw, (long)n, st); if (rc) return rc; }
-    d->w_h = hw;
-    return FS2_OK;
+  // positional table [1, rows, C]: as many rows as the checkpoint tensor holds (the reference regenerates a longer table
+  // on demand, core/embedding.py:48-66; the Python class does the same and the repack picks the new length up here)
+  int pos_table(const std::string& key, int C, const float** out, int* rows) {
+    NEED(d, key);
+    int64_t have = 1; for (int i = 0; i < d->ndim; ++i) have *= d->shape[i];
+    if (have <= 0 || have % C != 0) { set_error("fs2_load_weights: '%s' has %lld elements, not a multiple of %d", key.c_str(), (long long)have, C); return FS2_ERR_INVALID; }
+    *rows = (int)(have / C);
+    return copy(key, have, out);
   }
   int norm(const std::string& prefix, int C, float eps, Norm* out) {
     int rc;
@@ -317,7 +373,7 @@ struct Packer {
     out->eps = eps;
     return FS2_OK;
   }
-  int blocks(const std::string& prefix, int n, int C, int H, int kffn, bool precise, bool f16_ffn, std::vector<Block>* out) {
+  int blocks(const std::string& prefix, int n, int C, int H, int kffn, std::vector<Block>* out) {
     out->assign(n, Block());
     for (int i = 0; i < n; ++i) {
       std::string p = prefix + ".encoders_." + std::to_string(i) + ".";
@@ -339,8 +395,7 @@ struct Packer {
       if ((rc = dense(p + "self_attn.linear_out.weight", p + "self_attn.linear_out.bias", C, C, 1, &b.out))) return rc;
       if ((rc = dense(p + "feed_forward.w_1.weight", p + "feed_forward.w_1.bias", H, C, kffn, &b.w1))) return rc;
       if ((rc = dense(p + "feed_forward.w_2.weight", p + "feed_forward.w_2.bias", C, H, 1, &b.w2))) return rc;
-      if (precise) for (Dense* d : {&b.qkv, &b.out, &b.w1, &b.w2}) if ((rc = split(d))) return rc;
-      if (f16_ffn) for (Dense* d : {&b.qkv, &b.w1, &b.w2}) if ((rc = half(d))) return rc;
+      for (Dense* d : {&b.qkv, &b.out, &b.w1, &b.w2}) if ((rc = split(d))) return rc;
       if ((rc = norm(p + "norm1.", C, 1e-5f, &b.ln1))) return rc;   // encoder.py:37-38
       if ((rc = norm(p + "norm2.", C, 1e-5f, &b.ln2))) return rc;
     }
@@ -367,8 +422,8 @@ struct Packer {
     // encoder (fastspeech.py:65-84)
     if ((rc = copy("encoder.embed.0.weight", (int64_t)c.idim * c.adim, &h->emb))) return rc;
     if ((rc = copy("encoder.embed.1.alpha", 1, &h->enc_alpha))) return rc;
-    if ((rc = copy("encoder.embed.1.pe", (int64_t)c.pe_len * c.adim, &h->enc_pe))) return rc;
-    if ((rc = blocks("encoder", c.elayers, c.adim, c.eunits, c.ffn_kernel, true, false, &h->enc))) return rc;
+    if ((rc = pos_table("encoder.embed.1.pe", c.adim, &h->enc_pe, &h->enc_pe_len))) return rc;
+    if ((rc = blocks("encoder", c.elayers, c.adim, c.eunits, c.ffn_kernel, &h->enc))) return rc;
     if ((rc = predictor("duration_predictor.", &h->dur))) return rc;
     if ((rc = predictor("energy_predictor.predictor.", &h->energy))) return rc;
     if ((rc = predictor("pitch_predictor.predictor.", &h->pitch))) return rc;
@@ -393,11 +448,10 @@ struct Packer {
     if ((rc = split(&h->dec_in))) return rc;                                   // hi/lo copies serve FS2_MATH_3XTF32
     if ((rc = norm("decoder.embed.1.", c.ddim, 1e-5f, &h->dec_in_ln))) return rc;
     if ((rc = copy("decoder.embed.4.alpha", 1, &h->dec_alpha))) return rc;
-    if ((rc = copy("decoder.embed.4.pe", (int64_t)c.pe_len * c.ddim, &h->dec_pe))) return rc;
-    if ((rc = blocks("decoder", c.dlayers, c.ddim, c.dunits, c.ffn_kernel, true, true, &h->dec))) return rc;
+    if ((rc = pos_table("decoder.embed.4.pe", c.ddim, &h->dec_pe, &h->dec_pe_len))) return rc;
+    if ((rc = blocks("decoder", c.dlayers, c.ddim, c.dunits, c.ffn_kernel, &h->dec))) return rc;
     if ((rc = dense("feat_out.weight", "feat_out.bias", c.odim, c.ddim, 1, &h->feat_out))) return rc;
     if ((rc = split(&h->feat_out))) return rc;
-    if ((rc = half(&h->feat_out))) return rc;
     // Postnet: Conv1d(no bias) + BatchNorm1d(eval) folded into weight scale + bias (modules.py:283-348)
     h->postnet.assign(c.postnet_layers, Dense());
     for (int i = 0; i < c.postnet_layers; ++i) {
@@ -411,38 +465,41 @@ struct Packer {
                                             (const float*)var->data, 1e-5f, cout, scale, shift, st))) return rc;
       if ((rc = dense(p + "0.weight", "", cout, cin, c.postnet_filts, &h->postnet[i], scale, shift))) return rc;
       if ((rc = split(&h->postnet[i]))) return rc;
-      if ((rc = half(&h->postnet[i]))) return rc;
     }
     return FS2_OK;
   }
 };
 
-inline int64_t max_width(const fs2_config& c) {
-  int64_t w = c.adim;
-  for (int v : {c.ddim, c.eunits, c.dunits, c.pred_chans, c.postnet_chans, c.odim}) if (v > w) w = v;
-  return w;
-}
-struct EncodePlan { float *x, *y, *qkv, *ctx, *hid, *t1, *t2; __half* split; };
-EncodePlan plan_encode(const fs2_config& c, Bump& b, int64_t rows) {
+// Workspace layouts.  A tensor exists either as fp32 rows (fp32 / tf32 families) or as fp16 operand planes [2][rows][K]
+// (plane families) -- the same bytes, so the two views alias one allocation.
+struct EncodePlan { BlockBufs w; float *t1, *t2; __half* t2p; };
+EncodePlan plan_encode(const fs2_config& c, Bump& b, int B, int T) {
+  const int64_t rows = (int64_t)B * T;
   EncodePlan p;
-  p.x = b.floats(rows * c.adim); p.y = b.floats(rows * c.adim); p.qkv = b.floats(rows * 3 * c.adim);
-  p.ctx = b.floats(rows * c.adim); p.hid = b.floats(rows * c.eunits);
-  p.t1 = b.floats(rows * c.pred_chans); p.t2 = b.floats(rows * c.pred_chans);
-  p.split = (__half*)b.floats(rows * max_width(c));     // 3xF16 activation planes (hi + lo = the bytes of the widest fp32 operand)
+  p.w.x = b.floats(rows * c.adim); p.w.y = b.floats(rows * c.adim);
+  p.w.xp = (__half*)b.floats(rows * c.adim);
+  p.w.qkv = b.floats(rows * 3 * c.adim); p.w.qkp = (__half*)p.w.qkv;
+  p.w.vt = b.floats((int64_t)B * c.adim * round8(T)); p.w.vtp = (__half*)p.w.vt;
+  p.w.ctx = b.floats(rows * c.adim); p.w.ctxp = (__half*)p.w.ctx;
+  p.w.hid = b.floats(rows * c.eunits); p.w.hidp = (__half*)p.w.hid;
+  p.t1 = b.floats(rows * c.pred_chans); p.t2 = b.floats(rows * c.pred_chans); p.t2p = (__half*)p.t2;
   return p;
 }
-struct DecodePlan { float *hm2, *x, *y, *qkv, *vt, *ctx, *hid, *t1, *t2, *q1, *q2; __half *xh, *before_h, *split; };
-DecodePlan plan_decode(const fs2_config& c, Bump& b, int64_t rows, int B, int L) {
+struct DecodePlan { BlockBufs w; float *hm2, *t1, *t2, *q1, *q2; __half *hmp, *hm2p, *t2p, *beforep; };
+DecodePlan plan_decode(const fs2_config& c, Bump& b, int B, int L) {
+  const int64_t rows = (int64_t)B * L;
   DecodePlan p;
-  p.hm2 = b.floats(rows * c.adim);
-  p.x = b.floats(rows * c.ddim); p.y = b.floats(rows * c.ddim); p.qkv = b.floats(rows * 3 * c.ddim);
-  p.vt = b.floats((int64_t)B * c.ddim * round4(L));
-  p.ctx = b.floats(rows * c.ddim); p.hid = b.floats(rows * c.dunits);
-  p.t1 = b.floats(rows * c.pred_chans); p.t2 = b.floats(rows * c.pred_chans);
+  p.hmp = (__half*)b.floats(rows * c.adim);                          // planes of the length-regulated states (predictor input)
+  p.hm2 = b.floats(rows * c.adim); p.hm2p = (__half*)p.hm2;
+  p.w.x = b.floats(rows * c.ddim); p.w.y = b.floats(rows * c.ddim);
+  p.w.xp = (__half*)b.floats(rows * c.ddim);
+  p.w.qkv = b.floats(rows * 3 * c.ddim); p.w.qkp = (__half*)p.w.qkv;
+  p.w.vt = b.floats((int64_t)B * c.ddim * round8(L)); p.w.vtp = (__half*)p.w.vt;
+  p.w.ctx = b.floats(rows * c.ddim); p.w.ctxp = (__half*)p.w.ctx;
+  p.w.hid = b.floats(rows * c.dunits); p.w.hidp = (__half*)p.w.hid;
+  p.t1 = b.floats(rows * c.pred_chans); p.t2 = b.floats(rows * c.pred_chans); p.t2p = (__half*)p.t2;
   p.q1 = b.floats(rows * c.postnet_chans); p.q2 = b.floats(rows * c.postnet_chans);
-  p.xh = (__half*)b.bytes((size_t)rows * c.ddim * sizeof(__half));   // FS2_MATH_F16: fp16 copy of the current block input / conv-FFN input
-  p.before_h = (__half*)b.bytes((size_t)rows * c.odim * sizeof(__half));   // FS2_MATH_F16: fp16 copy of before_outs for the Postnet
-  p.split = (__half*)b.floats(rows * max_width(c));
+  p.beforep = (__half*)b.floats(rows * c.odim);
   return p;
 }
 
@@ -454,8 +511,8 @@ using namespace fs2;
 extern "C" {
 
 const char* fs2_last_error(void) { return g_err; }
-const char* fs2_version(void) { return "fs2-b200 0.1 sm_100a"; }
-unsigned long long fs2_kernel_launches(void) { return g_kernel_launches; }
+const char* fs2_version(void) { return "fs2-b200 0.2 sm_100a"; }
+unsigned long long fs2_kernel_launches(void) { return g_kernel_launches.load(); }
 
 int fs2_create(fs2_handle** out, const fs2_config* cfg, int device) {
   FS2_REQUIRE(out && cfg, "fs2_create: null argument");
@@ -469,7 +526,9 @@ int fs2_create(fs2_handle** out, const fs2_config* cfg, int device) {
   FS2_REQUIRE(cfg->postnet_layers >= 1, "fs2_create: postnet_layers == 0 is not supported");
   FS2_REQUIRE(cfg->n_bins % 4 == 0, "fs2_create: n_bins must be a multiple of 4");
   FS2_REQUIRE(cfg->math_mode >= FS2_MATH_FP32 && cfg->math_mode <= FS2_MATH_F16, "fs2_create: bad math_mode");
-  FS2_CUDA_CHECK(cudaSetDevice(device));
+  int n_dev = 0;
+  FS2_CUDA_CHECK(cudaGetDeviceCount(&n_dev));
+  FS2_REQUIRE(device >= 0 && device < n_dev, "fs2_create: device %d out of range (%d visible)", device, n_dev);
   fs2_handle* h = new fs2_handle();
   h->cfg = *cfg;
   h->device = device;
@@ -479,7 +538,10 @@ int fs2_create(fs2_handle** out, const fs2_config* cfg, int device) {
 
 void fs2_destroy(fs2_handle* h) {
   if (!h) return;
-  if (h->arena) cudaFree(h->arena);
+  {
+    DeviceGuard guard(h->device);
+    if (h->arena) cudaFree(h->arena);
+  }
   delete h;
 }
 
@@ -492,6 +554,7 @@ int fs2_profile_classes(void) { return P_COUNT; }
 const char* fs2_profile_label(int i) { return i >= 0 && i < P_COUNT ? kProfLabels[i] : ""; }
 int fs2_profile_read(fs2_handle* h, double* ms, int64_t* launches, double* flop, double* bytes) {
   FS2_REQUIRE(h && ms && launches && flop && bytes, "fs2_profile_read: null argument");
+  FS2_DEVICE_GUARD(h);
   for (int i = 0; i < P_COUNT; ++i) { ms[i] = 0; launches[i] = 0; flop[i] = 0; bytes[i] = 0; }
   for (ProfRec& r : h->prof.recs) {
     FS2_CUDA_CHECK(cudaEventSynchronize(r.b));
@@ -514,7 +577,7 @@ int fs2_set_math_mode(fs2_handle* h, int math_mode) {
 int fs2_load_weights(fs2_handle* h, const fs2_weight_desc* w, int n, void* stream) {
   FS2_REQUIRE(h && w && n > 0, "fs2_load_weights: null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  FS2_CUDA_CHECK(cudaSetDevice(h->device));
+  FS2_DEVICE_GUARD(h);
   Map m;
   for (int i = 0; i < n; ++i) {
     FS2_REQUIRE(w[i].name && w[i].data, "fs2_load_weights: entry %d has a null name/data", i);
@@ -543,8 +606,8 @@ int fs2_load_weights(fs2_handle* h, const fs2_weight_desc* w, int n, void* strea
 int fs2_workspace_bytes(fs2_handle* h, int B, int Tmax, int Lmax, size_t* out) {
   FS2_REQUIRE(h && out && B >= 0 && Tmax >= 0 && Lmax >= 0, "fs2_workspace_bytes: bad argument");
   Bump e(nullptr, 0), d(nullptr, 0);
-  plan_encode(h->cfg, e, (int64_t)B * Tmax);
-  plan_decode(h->cfg, d, (int64_t)B * Lmax, B, Lmax);
+  plan_encode(h->cfg, e, B, Tmax);
+  plan_decode(h->cfg, d, B, Lmax);
   *out = (e.off > d.off ? e.off : d.off) + 1024;
   return FS2_OK;
 }
@@ -553,25 +616,26 @@ int fs2_encode(fs2_handle* h, const int64_t* xs, const int64_t* ilens, int B, in
                int64_t* d_int, void* ws, size_t ws_bytes, void* stream) {
   FS2_REQUIRE(h && xs && ilens && hs && ws, "fs2_encode: null argument");
   if (!h->loaded) { set_error("fs2_encode: weights not loaded"); return FS2_ERR_NOT_LOADED; }
-  FS2_REQUIRE(Tmax <= h->cfg.pe_len, "fs2_encode: Tmax=%d exceeds the positional table (%d rows)", Tmax, h->cfg.pe_len);
+  FS2_REQUIRE(Tmax <= h->enc_pe_len, "fs2_encode: Tmax=%d exceeds the positional table (%d rows)", Tmax, h->enc_pe_len);
+  FS2_DEVICE_GUARD(h);
   cudaStream_t st = (cudaStream_t)stream;
   const fs2_config& c = h->cfg;
   t_prof = &h->prof;
   Bump b(ws, ws_bytes);
-  EncodePlan p = plan_encode(c, b, (int64_t)B * Tmax);
+  EncodePlan p = plan_encode(c, b, B, Tmax);
   if (!b.ok()) { set_error("fs2_encode: workspace too small (%zu < %zu)", ws_bytes, b.off); return FS2_ERR_WORKSPACE; }
-  t_split_ws = p.split; t_split_of = nullptr;
   int rc;
   // the encoder's output feeds round() in the duration predictor: exact fp32 FMA in FS2_MATH_FP32,
   // error-compensated 3xF16 on the tensor cores in every other mode (never a plain 10-bit-mantissa product)
-  const int precise = c.math_mode == FS2_MATH_FP32 ? FS2_MATH_FP32 : MATH_3XTF32;
-  { ProfScope prof_scope(P_EMBED, 0, 8.0 * B * Tmax * c.adim, st);
-    if ((rc = embed_posenc(xs, h->emb, c.idim, h->enc_pe, h->enc_alpha, B, Tmax, c.adim, p.x, st))) return rc; }
+  const bool planes = c.math_mode != FS2_MATH_FP32;
+  { ProfScope prof_scope(P_EMBED, 0, (planes ? 12.0 : 8.0) * B * Tmax * c.adim, st);
+    if ((rc = embed_posenc(xs, h->emb, c.idim, h->enc_pe, h->enc_alpha, B, Tmax, c.adim, p.w.x, planes ? p.w.xp : nullptr, st))) return rc; }
   float* enc_out = nullptr;
-  if ((rc = run_blocks(h->enc, p.x, p.y, p.qkv, nullptr, p.ctx, p.hid, ilens, B, Tmax, c.adim, c.aheads, precise, false, st, &enc_out))) return rc;
+  if (planes) { if ((rc = run_blocks_planes(h->enc, p.w, ilens, B, Tmax, c.adim, c.aheads, true, false, st, &enc_out))) return rc; }
+  else { if ((rc = run_blocks(h->enc, p.w, ilens, B, Tmax, c.adim, c.aheads, FS2_MATH_FP32, false, st, &enc_out))) return rc; }
   FS2_CUDA_CHECK(cudaMemcpyAsync(hs, enc_out, (size_t)B * Tmax * c.adim * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (d_log || d_int)
-    if ((rc = run_predictor(h->dur, enc_out, c.adim, B, Tmax, p.t1, p.t2, ilens, d_log, d_int, precise, st))) return rc;
+    if ((rc = run_predictor(h->dur, enc_out, planes ? p.w.xp : nullptr, c.adim, B, Tmax, p.t1, p.t2, p.t2p, ilens, d_log, d_int, st))) return rc;
   return FS2_OK;
 }
 
@@ -593,60 +657,68 @@ int fs2_decode(fs2_handle* h, const float* hm, const int64_t* olens, const float
   FS2_REQUIRE(h && hm && before && after && e_out && p_out && ws, "fs2_decode: null argument");
   FS2_REQUIRE((es == nullptr) == (ps == nullptr), "fs2_decode: es and ps must both be given or both be NULL");
   if (!h->loaded) { set_error("fs2_decode: weights not loaded"); return FS2_ERR_NOT_LOADED; }
-  FS2_REQUIRE(L <= h->cfg.pe_len, "fs2_decode: L=%d exceeds the positional table (%d rows)", L, h->cfg.pe_len);
+  FS2_REQUIRE(L <= h->dec_pe_len, "fs2_decode: L=%d exceeds the positional table (%d rows)", L, h->dec_pe_len);
+  FS2_DEVICE_GUARD(h);
   cudaStream_t st = (cudaStream_t)stream;
   const fs2_config& c = h->cfg;
   const int64_t rows = (int64_t)B * L;
   t_prof = &h->prof;
   Bump b(ws, ws_bytes);
-  DecodePlan p = plan_decode(c, b, rows, B, L);
+  DecodePlan p = plan_decode(c, b, B, L);
   if (!b.ok()) { set_error("fs2_decode: workspace too small (%zu < %zu)", ws_bytes, b.off); return FS2_ERR_WORKSPACE; }
-  t_split_ws = p.split; t_split_of = nullptr;
-  const bool f16_ffn = c.math_mode == FS2_MATH_F16;                     // tf32 everywhere except the conv-FFN
-  const int mode = f16_ffn ? FS2_MATH_TF32 : c.math_mode;
-  const int precise = mode == FS2_MATH_FP32 ? FS2_MATH_FP32 : MATH_3XTF32;
+  const int mode = c.math_mode;
+  const bool pred_planes = mode != FS2_MATH_FP32;                              // predictors: 3xF16 in every tensor-core mode
+  const bool dec_planes = mode == FS2_MATH_3XTF32 || mode == FS2_MATH_F16;     // decoder side on operand planes
+  const bool x3 = mode == FS2_MATH_3XTF32;
   int rc;
-  // energy / pitch predictors on the length-regulated states (fastspeech.py:195-196,214-216); fp32-class
-  if ((rc = run_predictor(h->energy, hm, c.adim, B, L, p.t1, p.t2, olens, e_out, nullptr, precise, st))) return rc;
-  if ((rc = run_predictor(h->pitch, hm, c.adim, B, L, p.t1, p.t2, olens, p_out, nullptr, precise, st))) return rc;
-  // hs + pitch_embed(one_hot) + energy_embed(one_hot) (fastspeech.py:218-219)
+  // energy / pitch predictors on the length-regulated states (fastspeech.py:195-196,214-216); fp32-class.  hm enters the
+  // library as fp32 rows (the LengthRegulator is its own ABI stage), so this is the one operand pre-pass left in a step
+  if (pred_planes) {
+    ProfScope prof_scope(P_ROWNORM, 0, 8.0 * rows * c.adim, st);
+    if ((rc = split_rows(hm, c.adim, rows, c.adim, p.hmp, st))) return rc;
+  }
+  if ((rc = run_predictor(h->energy, hm, pred_planes ? p.hmp : nullptr, c.adim, B, L, p.t1, p.t2, p.t2p, olens, e_out, nullptr, st))) return rc;
+  if ((rc = run_predictor(h->pitch, hm, pred_planes ? p.hmp : nullptr, c.adim, B, L, p.t1, p.t2, p.t2p, olens, p_out, nullptr, st))) return rc;
+  // hs + pitch_embed(one_hot) + energy_embed(one_hot) (fastspeech.py:218-219); plane families: straight to the decoder
+  // input Linear's operand planes
   { ProfScope prof_scope(P_VAR_EMBED, 0, 4.0 * rows * c.adim * 4, st);
   if ((rc = variance_embed_add(hm, es ? es : e_out, ps ? ps : p_out, h->e_bins, h->p_bins, c.n_bins - 1, h->e_tab,
-                               h->e_tab_bias, h->p_tab, h->p_tab_bias, rows, c.adim, p.hm2, e_ids, p_ids, st))) return rc; }
+                               h->e_tab_bias, h->p_tab, h->p_tab_bias, rows, c.adim, dec_planes ? nullptr : p.hm2,
+                               dec_planes ? p.hm2p : nullptr, x3, e_ids, p_ids, st))) return rc; }
   // decoder input layer: Linear -> LayerNorm -> ReLU -> x + alpha*pe (core/encoder.py:118-125)
-  if ((rc = dense(make_gemm(h->dec_in, p.hm2, c.adim, B, L, ACT_NONE, nullptr, 0, p.y, c.ddim), mode, st, P_DEC_IN))) return rc;
   {
-    RowNorm r = make_norm(h->dec_in_ln, p.y, c.ddim, rows, c.ddim, p.x, c.ddim);
+    TapGemm g = dec_planes ? make_gemm_p(h->dec_in, p.hm2p, B, L, x3, ACT_NONE, nullptr, 0, p.w.y, c.ddim)
+                           : make_gemm(h->dec_in, p.hm2, c.adim, B, L, ACT_NONE, nullptr, 0, p.w.y, c.ddim);
+    if ((rc = dense(g, mode, st, P_DEC_IN))) return rc;
+    RowNorm r = make_norm(h->dec_in_ln, p.w.y, c.ddim, rows, c.ddim, p.w.x, c.ddim);
     r.relu_after = 1; r.pe = h->dec_pe; r.alpha = h->dec_alpha; r.L = L;
-    if (f16_ffn) { r.out_h = p.xh; r.ldo_h = c.ddim; }    // first block's q|k|v reads the fp16 copy
-    if ((rc = mode == MATH_3XTF32 ? norm_rows_split(r, st) : norm_rows(r, st))) return rc;
+    if (dec_planes) { r.split_out = p.w.xp; r.split_lo = x3; }    // first block's q|k|v reads the planes
+    if ((rc = norm_rows(r, st))) return rc;
   }
   float* dec_out = nullptr;
-  if ((rc = run_blocks(h->dec, p.x, p.y, p.qkv, p.vt, p.ctx, p.hid, olens, B, L, c.ddim, c.aheads, mode, true, st, &dec_out, f16_ffn ? p.xh : nullptr))) return rc;
-  // mel linear (fastspeech.py:228-230); FS2_MATH_F16: from the fp16 copy of the last block's output, and the Postnet
-  // chain stays in fp16 until the final residual layer
-  const bool f16_post = f16_ffn && (f16_parts_mask() & 4) && c.odim % 16 == 0;
+  if (dec_planes) { if ((rc = run_blocks_planes(h->dec, p.w, olens, B, L, c.ddim, c.aheads, x3, true, st, &dec_out))) return rc; }
+  else { if ((rc = run_blocks(h->dec, p.w, olens, B, L, c.ddim, c.aheads, mode, true, st, &dec_out))) return rc; }
+  // mel linear (fastspeech.py:228-230); plane families: from the planes of the last block's output, and the Postnet
+  // chain stays in planes until the final residual layer
   {
-    TapGemm g = make_gemm(h->feat_out, dec_out, c.ddim, B, L, ACT_NONE, nullptr, 0, before, c.odim);
-    if (f16_post) { g.x_h = p.xh; g.ldx_h = c.ddim; g.out_h = p.before_h; g.ldo_h = c.odim; }
+    TapGemm g = dec_planes ? make_gemm_p(h->feat_out, p.w.xp, B, L, x3, ACT_NONE, nullptr, 0, before, c.odim)
+                           : make_gemm(h->feat_out, dec_out, c.ddim, B, L, ACT_NONE, nullptr, 0, before, c.odim);
+    if (dec_planes) planes_out(g, p.beforep, c.odim, x3);
     if ((rc = dense(g, mode, st, P_FEAT_OUT))) return rc;
   }
   // Postnet + residual (fastspeech.py:236-238, modules.py:350-359)
   const float* cur = before; int curC = c.odim;
-  const __half* cur_h = p.before_h;
+  const __half* cur_p = p.beforep;
   float* pp[2] = {p.q1, p.q2};
   for (int i = 0; i < c.postnet_layers; ++i) {
-    bool last = i == c.postnet_layers - 1;
+    const bool last = i == c.postnet_layers - 1;
     float* dst = last ? after : pp[i & 1];
-    TapGemm g = make_gemm(h->postnet[i], cur, curC, B, L, last ? ACT_NONE : ACT_TANH, last ? before : nullptr, c.odim, dst,
-                          h->postnet[i].N);
-    if (f16_post) {
-      g.x_h = cur_h; g.ldx_h = curC;
-      if (!last) { g.out = nullptr; g.ldo = 0; g.out_h = reinterpret_cast<__half*>(dst); g.ldo_h = h->postnet[i].N; }
-      cur_h = reinterpret_cast<const __half*>(dst);
-    }
+    const int N = h->postnet[i].N;
+    TapGemm g = dec_planes ? make_gemm_p(h->postnet[i], cur_p, B, L, x3, last ? ACT_NONE : ACT_TANH, last ? before : nullptr, c.odim, last ? dst : nullptr, N)
+                           : make_gemm(h->postnet[i], cur, curC, B, L, last ? ACT_NONE : ACT_TANH, last ? before : nullptr, c.odim, dst, N);
+    if (dec_planes && !last) planes_out(g, reinterpret_cast<__half*>(dst), N, x3);
     if ((rc = dense(g, mode, st, P_POSTNET))) return rc;
-    cur = dst; curC = h->postnet[i].N;
+    cur = dst; cur_p = reinterpret_cast<const __half*>(dst); curC = N;
   }
   return FS2_OK;
 }
@@ -669,58 +741,84 @@ int fs2_one_hot(const int64_t* ids, int64_t n, int n_bins, float* out, void* str
   FS2_REQUIRE(ids && out, "fs2_one_hot: null argument");
   return one_hot(ids, n, n_bins, out, (cudaStream_t)stream);
 }
+
+namespace {
+// single-operator entries of the plane families (tests): operand planes of x and w are made on the fly in a
+// stream-ordered temporary; layout [x planes 2*nx][w hi nw][w lo nw][scale, inv]
+struct TempPlanes {
+  __half* base = nullptr; __half *xp, *w_hi, *w_lo; float* sc; cudaStream_t st;
+  int make(const float* x, long rows, int K, const float* w, long nw, cudaStream_t s) {
+    st = s;
+    const size_t nx = (size_t)rows * K, nx8 = (2 * nx + 15) & ~(size_t)15, nw8 = ((size_t)nw + 15) & ~(size_t)15;
+    FS2_CUDA_CHECK(cudaMallocAsync(&base, (nx8 + 2 * nw8) * sizeof(__half) + 64, st));
+    xp = base; w_hi = base + nx8; w_lo = w_hi + nw8; sc = reinterpret_cast<float*>(w_lo + nw8);
+    int rc = split_rows(x, K, rows, K, xp, st);
+    if (!rc) rc = weight_scale(w, nw, sc, sc + 1, st);
+    if (!rc) rc = split_f16(w, w_hi, w_lo, nw, sc, st);
+    return rc;
+  }
+  ~TempPlanes() { if (base) cudaFreeAsync(base, st); }
+};
+}  // namespace
+
 int fs2_op_tap_gemm(int math_mode, const float* x, int B, int L, int K, const float* w, const float* bias, int N, int taps,
                     int act, const float* resid, float* out, void* stream) {
   FS2_REQUIRE(x && w && out, "fs2_op_tap_gemm: null argument");
   Dense d; d.w = w; d.bias = bias; d.N = N; d.K = K; d.taps = taps;
   cudaStream_t st = (cudaStream_t)stream;
-  if (math_mode == FS2_MATH_F16) {   // single-operator entry for the f16 family (tests): fp16 copies made on the fly
-    const size_t nx = (size_t)B * L * K, nw = (size_t)N * K * taps;
-    __half* tmp = nullptr;
-    FS2_CUDA_CHECK(cudaMallocAsync(&tmp, (nx + nw + 16) * sizeof(__half), st));
-    __half* wh = tmp + ((nx + 7) & ~(size_t)7);
-    int rc = to_half(x, tmp, (long)nx, st);
-    if (!rc) rc = to_half(w, wh, (long)nw, st);
-    TapGemm g = make_gemm(d, x, K, B, L, act, resid, N, out, N);
-    g.x_h = tmp; g.ldx_h = K; g.w_h = wh;
-    if (!rc) rc = dense(g, FS2_MATH_TF32, st, P_DEC_W1);
-    cudaFreeAsync(tmp, st);
-    return rc;
-  }
-  if (math_mode != MATH_3XTF32) return dense(make_gemm(d, x, K, B, L, act, resid, N, out, N), math_mode, st, P_DEC_W1);
-  // single-operator entry for the error-compensated family (tests): split the weights on the fly
-  const size_t n = (size_t)N * K * taps, nx = (size_t)B * L * K;
-  __half* tmp = nullptr;
-  const size_t n8 = (n + 7) & ~(size_t)7;
-  FS2_CUDA_CHECK(cudaMallocAsync(&tmp, (2 * n8 + 2 * nx + 16) * sizeof(__half), st));
-  int rc = split_f16(w, tmp, tmp + n8, (long)n, st);
-  d.w_hi_h = tmp; d.w_lo_h = tmp + n8;
-  t_split_ws = tmp + 2 * n8; t_split_of = nullptr;
-  if (!rc) rc = dense(make_gemm(d, x, K, B, L, act, resid, N, out, N), math_mode, st, P_DEC_W1);
-  cudaFreeAsync(tmp, st);
-  return rc;
+  if (math_mode == FS2_MATH_FP32 || math_mode == FS2_MATH_TF32)
+    return dense(make_gemm(d, x, K, B, L, act, resid, N, out, N), math_mode, st, P_DEC_W1);
+  TempPlanes t;
+  int rc = t.make(x, (long)B * L, K, w, (long)N * K * taps, st);
+  if (rc) return rc;
+  d.w_hi = t.w_hi; d.w_lo = t.w_lo; d.w_inv = t.sc + 1;
+  return dense(make_gemm_p(d, t.xp, B, L, math_mode == MATH_3XTF32, act, resid, N, out, N), math_mode, st, P_DEC_W1);
 }
-int fs2_op_gemm_layernorm(const float* x, int64_t rows, int K, const float* w, const float* bias, const float* resid,
+int fs2_op_gemm_layernorm(int math_mode, const float* x, int64_t rows, int K, const float* w, const float* bias, const float* resid,
                           const float* gamma, const float* beta, float eps, float* out, void* stream) {
   FS2_REQUIRE(x && w && gamma && beta && out, "fs2_op_gemm_layernorm: null argument");
   FS2_REQUIRE(rows < (1LL << 31), "fs2_op_gemm_layernorm: too many rows");
+  FS2_REQUIRE(math_mode == FS2_MATH_TF32 || math_mode == FS2_MATH_F16, "fs2_op_gemm_layernorm: the fused epilogue exists for FS2_MATH_TF32 and FS2_MATH_F16");
+  cudaStream_t st = (cudaStream_t)stream;
   Dense d; d.w = w; d.bias = bias; d.N = 384; d.K = K; d.taps = 1;
-  TapGemm g = make_gemm(d, x, K, 1, (int)rows, ACT_NONE, resid, 384, out, 384);
+  if (math_mode == FS2_MATH_TF32) {
+    TapGemm g = make_gemm(d, x, K, 1, (int)rows, ACT_NONE, resid, 384, out, 384);
+    g.ln_gamma = gamma; g.ln_beta = beta; g.ln_eps = eps;
+    return dense(g, FS2_MATH_TF32, st, P_DEC_OUT);
+  }
+  TempPlanes t;
+  int rc = t.make(x, (long)rows, K, w, (long)384 * K, st);
+  if (rc) return rc;
+  d.w_hi = t.w_hi; d.w_lo = t.w_lo; d.w_inv = t.sc + 1;
+  TapGemm g = make_gemm_p(d, t.xp, 1, (int)rows, false, ACT_NONE, resid, 384, out, 384);
   g.ln_gamma = gamma; g.ln_beta = beta; g.ln_eps = eps;
-  return dense(g, FS2_MATH_TF32, (cudaStream_t)stream, P_DEC_OUT);
+  return dense(g, FS2_MATH_F16, st, P_DEC_OUT);
 }
 int fs2_op_attention(int math_mode, const float* qkv, const int64_t* lens, int B, int L, int C, int heads, float* ctx,
                      void* stream) {
   FS2_REQUIRE(qkv && ctx, "fs2_op_attention: null argument");
+  FS2_REQUIRE(heads > 0 && C % heads == 0, "fs2_op_attention: C=%d not divisible by heads=%d", C, heads);
   cudaStream_t st = (cudaStream_t)stream;
-  if (math_mode != FS2_MATH_TF32) return attention(math_mode, qkv, nullptr, 0, lens, B, L, C, heads, ctx, st, P_DEC_ATTN);
-  // single-operator entry (tests): build the transposed V the projection epilogue normally provides
-  float* vt = nullptr;
-  const int lpad = round4(L);
-  FS2_CUDA_CHECK(cudaMallocAsync(&vt, (size_t)B * C * lpad * sizeof(float), st));
-  int rc = transpose_v(qkv, B, L, C, heads, vt, lpad, st);
-  if (!rc) rc = attention(math_mode, qkv, vt, lpad, lens, B, L, C, heads, ctx, st, P_DEC_ATTN);
-  cudaFreeAsync(vt, st);
+  ProfScope prof_scope(P_DEC_ATTN, 4.0 * B * (double)L * L * C, 4.0 * 4.0 * B * (double)L * C, st);
+  if (math_mode == FS2_MATH_FP32) return attention_fp32(qkv, lens, B, L, C, heads, ctx, st);
+  if (math_mode == FS2_MATH_TF32) {
+    // single-operator entry (tests): build the transposed V the projection epilogue normally provides
+    float* vt = nullptr;
+    const int lpad = round4(L);
+    FS2_CUDA_CHECK(cudaMallocAsync(&vt, (size_t)B * C * lpad * sizeof(float) + 16, st));
+    int rc = transpose_v(qkv, B, L, C, heads, vt, lpad, st);
+    if (!rc) rc = attention_tf32(qkv, vt, lpad, lens, B, L, C, heads, ctx, st);
+    cudaFreeAsync(vt, st);
+    return rc;
+  }
+  // plane families: q|k planes and transposed V planes made on the fly
+  const int lpad = round8(L);
+  const size_t nqk = (((size_t)2 * B * L * 2 * C) + 15) & ~(size_t)15, nvt = (size_t)2 * B * C * lpad;
+  __half* tmp = nullptr;
+  FS2_CUDA_CHECK(cudaMallocAsync(&tmp, (nqk + nvt) * sizeof(__half) + 64, st));
+  int rc = qkv_to_planes(qkv, B, L, C, heads, tmp, tmp + nqk, lpad, st);
+  if (!rc) rc = attention_planes(tmp, tmp + nqk, lpad, lens, B, L, C, heads, math_mode == MATH_3XTF32, ctx, nullptr, st);
+  cudaFreeAsync(tmp, st);
   return rc;
 }
 int fs2_op_layernorm(const float* x, const float* resid, const float* g, const float* b, float eps, int64_t rows, int C,

@@ -1,0 +1,418 @@
+// Tensor-core multi-head self-attention core on fp16 operand planes (core/attention.py:52-73), sm_100a:
+//   F16 : S = Q K^T and O = P V as tcgen05.mma kind::f16 on the hi planes (FS2_MATH_F16's decoder);
+//   X3  : the error-compensated form -- Q, K, V^T and P each as fp16 hi + lo, three products per term
+//         (lo.hi + hi.lo + hi.hi), fp32 accumulation in TMEM, fp32 softmax statistics: fp32-class scores and context
+//         (the encoder in every tensor-core mode, the decoder in FS2_MATH_3XTF32).
+// S, P and O live in TMEM; the [B,h,L,L] score tensor never touches HBM.
+//
+//   ctx[b,t,h*dk:(h+1)*dk] = softmax_u( q.k_u / sqrt(dk) | u < len_b ) . v ,  0 for t >= len_b
+//   (lens == nullptr: no masking at all -- the reference's mask=None branch, attention.py:67)
+//
+// Operands (written by the q|k|v projection's epilogue, gemm_tc.cu; all scaled by kPlaneScale):
+//   Q, K : planes qkp [P][B*L][2C] fp16 (q | k, heads contiguous inside each; K-major: dk contiguous)
+//   V^T  : planes vtp [P][B*heads][dk][lpad] fp16, i.e. V stored transposed so that P.V has a K-major B operand too
+//   P    : written by the softmax warps straight into TMEM as packed fp16 pairs -- in place of the fp32 S tile: hi in
+//          columns [0,64), lo in [64,128) of the tile's 128 columns -- and consumed from there as the A operand.
+// Result: the context as the operand planes of the out-projection (hi, + lo in X3) and / or as fp32 rows.
+//
+// CTA = 128 queries of one (batch, head); 128 keys per step.  Softmax is single-pass ("online") with a *lazy* reference
+// maximum: m_ref only moves (and O, l are rescaled through tcgen05.ld/st) when a tile's row maximum exceeds it by more
+// than 2^8 in the exp2 domain, which after the first tile is rare.  O / l at the end is exact for any reference
+// (no overflow: P <= 2^8, well inside fp16).  In F16 the row sum l adds the *rounded* P values, so the weights the
+// tensor core applies still sum to one.
+//
+// Warp roles (10 warps): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..9 = softmax / epilogue (two threads per
+// query row == TMEM lane, 64 score columns each).  TMEM: two S/P buffers (2 x 128 columns) so the tensor core computes
+// S_{j+1} while the softmax warps work on tile j, plus DK columns of O.  Shared memory: Q resident (P x DK/64 boxes of
+// 16 KB) + a ring of K / V^T boxes (one 128-byte swizzle row = 64 fp16 wide).
+#include <math.h>
+
+#include "tc_common.cuh"
+
+namespace fs2 {
+namespace {
+using namespace tc;
+
+constexpr int BQ = 128, BKV = 128, CH = 64;   // CH: fp16 per 128-byte swizzle row
+constexpr int ATT_THREADS = 320;              // TMA, MMA, 8 softmax / epilogue warps
+
+template <int DK, bool X3>
+struct HCfg {
+  static constexpr int P = X3 ? 2 : 1;                 // operand planes
+  static constexpr int QCH = DK / CH;                  // K-chunks of the S product
+  static constexpr int Q_BOX = BQ * 128;               // 16 KB: 128 query rows x 64 dk
+  static constexpr int Q_BYTES = P * QCH * Q_BOX;      // resident Q
+  static constexpr int K_BOX = BKV * 128;              // 16 KB: 128 kv rows x 64 dk
+  static constexpr int V_BOX = DK * 128;               // DK rows x 64 kv
+  static constexpr int SLOT = V_BOX > K_BOX ? V_BOX : K_BOX;
+  static constexpr int SLOTS_MAX = (222 * 1024 - Q_BYTES) / SLOT;
+  static constexpr int SLOTS = SLOTS_MAX > 8 ? 8 : SLOTS_MAX;
+  static constexpr size_t SMEM = (size_t)Q_BYTES + (size_t)SLOTS * SLOT + 1024 + 512 + 4 * BQ * 4;
+  static constexpr uint32_t IDESC_S = idesc_f16(BQ, BKV);
+  static constexpr uint32_t IDESC_O = idesc_f16(BQ, DK);
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int O_COL = 2 * BKV;                // S/P buffers at columns 0 and 128
+  static_assert(DK % 64 == 0 && DK <= 256, "d_k");
+  static_assert(SLOT % 1024 == 0 && SLOTS >= 3, "ring");
+};
+
+struct HParams {
+  const int64_t* lens; int B, L, C, heads;
+  float* ctx;            // [B,L,C] fp32 or null
+  __half* ctxp;          // planes [P][B*L][C] or null
+  float scale_log2e;     // log2(e) / sqrt(dk) / kPlaneScale^2  (Q and K are both pre-scaled)
+};
+
+__device__ __forceinline__ void tmem_st32u(uint32_t taddr, const uint32_t* r) { tmem_st32(taddr, reinterpret_cast<const float*>(r)); }
+
+// exp2 of one thread's 64 scores -> packed fp16 P (hi, and lo when X3); returns the row-sum contribution
+template <bool X3, bool MASKED>
+__device__ __forceinline__ float softmax_tile(const float* v, float c_exp, float mb, int kv0, int len, uint32_t* ph, uint32_t* pl) {
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float e0 = fast_exp2(fmaf(v[2 * i], c_exp, -mb)), e1 = fast_exp2(fmaf(v[2 * i + 1], c_exp, -mb));
+    if (MASKED) { if (kv0 + 2 * i >= len) e0 = 0.f; if (kv0 + 2 * i + 1 >= len) e1 = 0.f; }
+    const __half2 h = __floats2half2_rn(e0, e1);
+    ph[i] = *reinterpret_cast<const uint32_t*>(&h);
+    if (X3) {
+      const float2 g = __half22float2(h);
+      const __half2 l = __floats2half2_rn(e0 - g.x, e1 - g.y);
+      pl[i] = *reinterpret_cast<const uint32_t*>(&l);
+      s0 += e0; s1 += e1;
+    } else {               // the tensor core sees the rounded weights: normalise by their sum
+      const float2 g = __half22float2(h);
+      s0 += g.x; s1 += g.y;
+    }
+  }
+  return s0 + s1;
+}
+
+template <int DK, bool X3>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constant__ CUtensorMap tmap_vt, HParams p) {
+  using A = HCfg<DK, X3>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* q_smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
+  uint8_t* ring = q_smem + A::Q_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)A::SLOTS * A::SLOT);
+  uint64_t* full_bar = bars;                   // [SLOTS]
+  uint64_t* empty_bar = bars + A::SLOTS;       // [SLOTS]
+  uint64_t* q_bar = bars + 2 * A::SLOTS;       // Q landed
+  uint64_t* s_full = q_bar + 1;                // [2] MMA -> softmax: S tile ready
+  uint64_t* pv_done = s_full + 2;              // MMA -> softmax: P.V of the previous tile has finished
+  uint64_t* p_full = pv_done + 2;              // [2] softmax -> MMA: P written
+  uint64_t* o_full = p_full + 2;               // all P.V done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  float* xchg = reinterpret_cast<float*>(tmem_slot + 4);   // [2 tiles][2 halves][BQ] row-statistic exchange between column halves
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+  const int len = p.lens ? (int)min((long)p.lens[b], (long)p.L) : p.L;   // keys >= len are masked
+  const int J = (len + BKV - 1) / BKV;                                   // kv tiles that contain valid keys
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < A::SLOTS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(q_bar, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&pv_done[i], 1); mbar_init(&p_full[i], 8); }
+    mbar_init(o_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, A::TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (J > 0) {
+    if (warp == 0) {
+      if (lane == 0) {  // ---- TMA producer: Q once, then K / V^T boxes in exactly the order the MMA warp consumes them ----
+        mbar_expect_tx(q_bar, A::Q_BYTES);
+        for (int pl = 0; pl < A::P; ++pl)
+          for (int c = 0; c < A::QCH; ++c)
+            tma_load_3d(q_smem + (size_t)(pl * A::QCH + c) * A::Q_BOX, &tmap_qk, q_bar, h * DK + c * CH, q0, b + pl * p.B);
+        int n = 0;
+        auto push_k = [&](int j) {
+          for (int c = 0; c < A::QCH; ++c)
+            for (int pl = 0; pl < A::P; ++pl, ++n) {
+              const int slot = n % A::SLOTS;
+              mbar_wait(&empty_bar[slot], ((n / A::SLOTS) & 1) ^ 1);
+              mbar_expect_tx(&full_bar[slot], A::K_BOX);
+              tma_load_3d(ring + (size_t)slot * A::SLOT, &tmap_qk, &full_bar[slot], p.C + h * DK + c * CH, j * BKV, b + pl * p.B);
+            }
+        };
+        auto push_v = [&](int j) {
+          for (int c = 0; c < BKV / CH; ++c)
+            for (int pl = 0; pl < A::P; ++pl, ++n) {
+              const int slot = n % A::SLOTS;
+              mbar_wait(&empty_bar[slot], ((n / A::SLOTS) & 1) ^ 1);
+              mbar_expect_tx(&full_bar[slot], A::V_BOX);
+              tma_load_3d(ring + (size_t)slot * A::SLOT, &tmap_vt, &full_bar[slot], j * BKV + c * CH, 0, b * p.heads + h + pl * p.B * p.heads);
+            }
+        };
+        push_k(0);
+        for (int j = 0; j < J; ++j) { if (j + 1 < J) push_k(j + 1); push_v(j); }
+      }
+    } else if (warp == 1) {
+      {  // ---- MMA issuer: all 32 lanes run the loop, one lane is elected inside each tcgen05 asm ----
+        mbar_wait(q_bar, 0);
+        tcgen05_fence_after();
+        const uint32_t q_addr = smem_u32(q_smem);
+        int n = 0;
+        auto take = [&]() -> uint64_t {   // next ring slot, as a descriptor
+          const int slot = n % A::SLOTS;
+          mbar_wait(&full_bar[slot], (n / A::SLOTS) & 1);
+          tcgen05_fence_after();
+          return make_sw128_kmajor_desc(smem_u32(ring + (size_t)slot * A::SLOT));
+        };
+        auto release = [&]() { tcgen05_commit(&empty_bar[n % A::SLOTS]); ++n; };
+        // S tile g goes to S/P buffer g & 1; S_{g+2} reuses it after P.V_g, which is issued earlier in this thread
+        auto issue_s = [&](int g) {
+          const uint32_t d = tmem_base + (uint32_t)((g & 1) * BKV);
+          for (int c = 0; c < A::QCH; ++c) {
+            const uint64_t q_hi = make_sw128_kmajor_desc(q_addr + c * A::Q_BOX);
+            const uint64_t k_hi = take();
+            if (X3) {
+              const uint64_t q_lo = make_sw128_kmajor_desc(q_addr + (A::QCH + c) * A::Q_BOX);
+#pragma unroll
+              for (int k = 0; k < CH / 16; ++k) {
+                umma_f16(d, q_lo + 2 * k, k_hi + 2 * k, A::IDESC_S, (c | k) != 0);
+                umma_f16(d, q_hi + 2 * k, k_hi + 2 * k, A::IDESC_S, 1);
+              }
+              release();
+              const uint64_t k_lo = take();
+#pragma unroll
+              for (int k = 0; k < CH / 16; ++k) umma_f16(d, q_hi + 2 * k, k_lo + 2 * k, A::IDESC_S, 1);
+              release();
+            } else {
+#pragma unroll
+              for (int k = 0; k < CH / 16; ++k) umma_f16(d, q_hi + 2 * k, k_hi + 2 * k, A::IDESC_S, (c | k) != 0);
+              release();
+            }
+          }
+          tcgen05_commit(&s_full[g & 1]);
+        };
+        issue_s(0);
+        for (int j = 0; j < J; ++j) {
+          if (j + 1 < J) issue_s(j + 1);                 // the tensor core computes S_{j+1} while the softmax warps work on tile j
+          mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+          tcgen05_fence_after();
+          const uint32_t p_hi = tmem_base + (uint32_t)((j & 1) * BKV), p_lo = p_hi + BKV / 2;   // packed fp16: 64 columns each
+          const uint32_t o = tmem_base + A::O_COL;
+          for (int c = 0; c < BKV / CH; ++c) {
+            const uint64_t v_hi = take();
+            if (X3) {
+#pragma unroll
+              for (int k = 0; k < CH / 16; ++k) {
+                umma_f16_ts(o, p_lo + (c * 4 + k) * 8, v_hi + 2 * k, A::IDESC_O, (j | c | k) != 0);
+                umma_f16_ts(o, p_hi + (c * 4 + k) * 8, v_hi + 2 * k, A::IDESC_O, 1);
+              }
+              release();
+              const uint64_t v_lo = take();
+#pragma unroll
+              for (int k = 0; k < CH / 16; ++k) umma_f16_ts(o, p_hi + (c * 4 + k) * 8, v_lo + 2 * k, A::IDESC_O, 1);
+              release();
+            } else {
+#pragma unroll
+              for (int k = 0; k < CH / 16; ++k) umma_f16_ts(o, p_hi + (c * 4 + k) * 8, v_hi + 2 * k, A::IDESC_O, (j | c | k) != 0);
+              release();
+            }
+          }
+          tcgen05_commit(&pv_done[0]);                   // lets the softmax warps rescale O if tile j+1 raises the reference max
+        }
+        tcgen05_commit(o_full);
+      }
+    } else {
+      // ---- softmax / epilogue: 8 warps; warps w and w+4 share TMEM lane quarter w%4 and split the columns ----
+      const int wq = warp & 3, half = (warp - 2) >> 2;          // half 0: columns [0,64), half 1: [64,128)
+      const int row = wq * 32 + lane;
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(wq * 32) << 16);
+      float v[64];
+      float m_ref = -INFINITY, l_row = 0.f;     // reference maximum (raw-score domain) and row sum relative to it
+      const float c_exp = p.scale_log2e;
+      for (int j = 0; j < J; ++j) {
+        mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+        tcgen05_fence_after();
+        const int kv0 = j * BKV + half * 64;
+        const bool masked = kv0 + 64 > len;                      // only the last tile of an utterance
+        __syncwarp();
+        const uint32_t tb = lane_addr + (uint32_t)((j & 1) * BKV);
+        tmem_ld32_nowait(tb + half * 64, v); tmem_ld32_nowait(tb + half * 64 + 32, v + 32); tmem_ld_wait_pin<64>(v);
+        float tmax = -INFINITY;
+        if (masked) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) if (kv0 + i < len) tmax = fmaxf(tmax, v[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) tmax = fmaxf(tmax, v[i]);
+        }
+        float* xr = xchg + (j & 1) * 2 * BQ;                     // double-buffered exchange: one barrier per tile
+        xr[half * BQ + row] = tmax;
+        named_bar_sync(1, 256);                                   // also: both halves of every row have read their S columns
+        tmax = fmaxf(tmax, xr[(half ^ 1) * BQ + row]);           // both threads of the row now hold the tile's row maximum
+        // lazy reference update: move m_ref only if the tile exceeds it by more than 2^8 in the exp2 domain
+        const bool bump = (tmax - m_ref) * c_exp > 8.0f;          // first tile: m_ref = -inf -> always
+        if (__any_sync(0xffffffffu, bump)) {
+          const float alpha = bump ? fast_exp2((m_ref - tmax) * c_exp) : 1.0f;   // exp2(-inf) = 0 on the first tile
+          if (j > 0) {   // O holds tiles 0..j-1: wait until P.V_{j-1} has landed, then scale this thread's half of the row
+            mbar_wait(&pv_done[0], (j - 1) & 1);
+            tcgen05_fence_after();
+            float o[32];
+#pragma unroll 1
+            for (int c0 = 0; c0 < DK / 2; c0 += 32) {
+              const uint32_t oa = lane_addr + (uint32_t)(A::O_COL + half * (DK / 2) + c0);
+              __syncwarp();
+              tmem_ld32(oa, o);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] *= alpha;
+              tmem_st32(oa, o);
+            }
+            tmem_st_wait();
+          }
+          l_row *= alpha;
+          if (bump) m_ref = tmax;
+        }
+        const float mb = m_ref * c_exp;
+        uint32_t ph[32], pl[32];
+        l_row += masked ? softmax_tile<X3, true>(v, c_exp, mb, kv0, len, ph, pl) : softmax_tile<X3, false>(v, c_exp, mb, kv0, len, ph, pl);
+        __syncwarp();
+        tmem_st32u(tb + half * 32, ph);                           // P hi: packed columns [0,64) of the tile's buffer
+        if (X3) tmem_st32u(tb + BKV / 2 + half * 32, pl);         // P lo: [64,128)
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[j & 1]);
+      }
+      named_bar_sync(1, 256);                                     // last exchange buffer is free again
+      xchg[half * BQ + row] = l_row;
+      named_bar_sync(1, 256);
+      l_row += xchg[(half ^ 1) * BQ + row];
+      // epilogue: O / l -> context rows (0 for masked query rows); each half stores DK/2 columns.  O carries V's
+      // kPlaneScale: the planes take it as is, the fp32 rows divide it out.
+      mbar_wait(o_full, 0);
+      tcgen05_fence_after();
+      const int t = q0 + row;
+      const bool store = t < p.L;
+      const float inv = (p.lens && t >= len) ? 0.f : 1.0f / l_row;
+      const long o_off = ((long)b * p.L + t) * p.C + h * DK + half * (DK / 2);
+      const long plane = (long)p.B * p.L * p.C;
+#pragma unroll 1
+      for (int c0 = 0; c0 < DK / 2; c0 += 32) {
+        __syncwarp();
+        tmem_ld32(lane_addr + (uint32_t)(A::O_COL + half * (DK / 2) + c0), v);
+        if (!store) continue;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= inv;
+        if (p.ctxp != nullptr) {
+          uint32_t hh[16], ll[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float a0 = fminf(fmaxf(v[2 * i], -65504.f), 65504.f), a1 = fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f);
+            const __half2 hv = __floats2half2_rn(a0, a1);
+            hh[i] = *reinterpret_cast<const uint32_t*>(&hv);
+            if (X3) {
+              const float2 g = __half22float2(hv);
+              const __half2 lv = __floats2half2_rn(a0 - g.x, a1 - g.y);
+              ll[i] = *reinterpret_cast<const uint32_t*>(&lv);
+            }
+          }
+          __half* dh = p.ctxp + o_off + c0;
+          st_global_v8_b32(dh, hh); st_global_v8_b32(dh + 16, hh + 8);
+          if (X3) { st_global_v8_b32(dh + plane, ll); st_global_v8_b32(dh + plane + 16, ll + 8); }
+        }
+        if (p.ctx != nullptr) {
+          float* dst = p.ctx + o_off + c0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(dst + q * 4) = make_float4(v[q * 4] * kPlaneInv, v[q * 4 + 1] * kPlaneInv, v[q * 4 + 2] * kPlaneInv, v[q * 4 + 3] * kPlaneInv);
+        }
+      }
+    }
+  } else if (warp >= 2 && warp < 6) {
+    // no valid key at all (len == 0): the reference's masked_fill turns the NaN rows into 0
+    const int t = q0 + (warp & 3) * 32 + lane;
+    if (t < p.L) {
+      const long o_off = ((long)b * p.L + t) * p.C + h * DK;
+      const long plane = (long)p.B * p.L * p.C;
+      if (p.ctx) for (int c = 0; c < DK; c += 4) *reinterpret_cast<float4*>(p.ctx + o_off + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.ctxp) for (int c = 0; c < DK; c += 8) {
+        *reinterpret_cast<uint4*>(p.ctxp + o_off + c) = make_uint4(0, 0, 0, 0);
+        if (X3) *reinterpret_cast<uint4*>(p.ctxp + plane + o_off + c) = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, A::TMEM_COLS);
+  }
+}
+
+template <int DK, bool X3>
+int launch(const __half* qkp, const __half* vtp, int lpad, const int64_t* lens, int B, int L, int C, int heads, float* ctx,
+           __half* ctxp, cudaStream_t st) {
+  using A = HCfg<DK, X3>;
+  static unsigned long long configured = 0;   // per-device bit mask
+  int rc;
+  if ((rc = ensure_smem_attr(attention_f16_kernel<DK, X3>, A::SMEM, &configured))) return rc;
+  CUtensorMap mqk, mvt;
+  const uint64_t row = (uint64_t)2 * C * 2;
+  if ((rc = make_map(&mqk, qkp, (uint64_t)2 * C, L, (uint64_t)B * A::P, row, row * L, BQ, true))) return rc;
+  // extent L (not lpad) along kv: alignment padding columns are never read, TMA zero-fills past L
+  if ((rc = make_map(&mvt, vtp, L, DK, (uint64_t)B * heads * A::P, (uint64_t)lpad * 2, (uint64_t)lpad * 2 * DK, DK, true))) return rc;
+  HParams p;
+  p.lens = lens; p.B = B; p.L = L; p.C = C; p.heads = heads; p.ctx = ctx; p.ctxp = ctxp;
+  p.scale_log2e = (1.0f / sqrtf((float)DK)) * 1.4426950408889634f * kPlaneInv * kPlaneInv;
+  dim3 grid((L + BQ - 1) / BQ, heads, B);
+  attention_f16_kernel<DK, X3><<<grid, ATT_THREADS, A::SMEM, st>>>(mqk, mvt, p);
+  FS2_LAUNCH_CHECK();
+  return FS2_OK;
+}
+
+// test helper (single-operator entry): qkv fp32 [B,L,3C] -> q|k planes [2][B*L][2C] and V^T planes [2][B*heads][dk][lpad]
+__global__ void qkv_to_planes_kernel(const float* __restrict__ qkv, int B, int L, int C, __half* __restrict__ qkp,
+                                     __half* __restrict__ vtp, int lpad) {
+  const long rows = (long)B * L;
+  const long total = rows * 3 * C;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / (3 * C); const int c = (int)(i - r * 3 * C);
+    const float x = fminf(fmaxf(qkv[i] * kPlaneScale, -65504.f), 65504.f);
+    const __half hi = __float2half_rn(x), lo = __float2half_rn(x - __half2float(hi));
+    if (c < 2 * C) {
+      qkp[r * 2 * C + c] = hi; qkp[(rows + r) * 2 * C + c] = lo;
+    } else {
+      const long bb = r / L; const int t = (int)(r - bb * L);
+      const long o = (bb * C + (c - 2 * C)) * (long)lpad + t;           // (b*heads + h)*dk + d == b*C + n
+      vtp[o] = hi; vtp[(long)B * C * lpad + o] = lo;
+    }
+  }
+}
+
+}  // namespace
+
+int qkv_to_planes(const float* qkv, int B, int L, int C, int heads, __half* qkp, __half* vtp, int lpad, cudaStream_t st) {
+  (void)heads;
+  const long total = (long)B * L * 3 * C;
+  if (total == 0) return FS2_OK;
+  long blocks = (total + 255) / 256;
+  qkv_to_planes_kernel<<<(int)(blocks > 148 * 16 ? 148 * 16 : blocks), 256, 0, st>>>(qkv, B, L, C, qkp, vtp, lpad);
+  FS2_LAUNCH_CHECK();
+  return FS2_OK;
+}
+
+int attention_planes(const __half* qkp, const __half* vtp, int lpad, const int64_t* lens, int B, int L, int C, int heads, bool x3,
+                     float* ctx, __half* ctxp, cudaStream_t st) {
+  FS2_REQUIRE(heads > 0 && C % heads == 0, "attention: C=%d not divisible by heads=%d", C, heads);
+  FS2_REQUIRE(qkp && vtp && lpad >= L && lpad % 8 == 0, "attention_planes: needs q|k planes and transposed V planes with a 16-byte aligned row pitch");
+  FS2_REQUIRE(ctx || ctxp, "attention_planes: no output");
+  FS2_REQUIRE(!ctxp || ((reinterpret_cast<uintptr_t>(ctxp) & 31) == 0 && (((long)B * L * C) % 16) == 0), "attention_planes: context planes must be 32-byte aligned");
+  if (B == 0 || L == 0) return FS2_OK;
+  const int dk = C / heads;
+  if (dk == 192) return x3 ? launch<192, true>(qkp, vtp, lpad, lens, B, L, C, heads, ctx, ctxp, st) : launch<192, false>(qkp, vtp, lpad, lens, B, L, C, heads, ctx, ctxp, st);
+  if (dk == 128) return x3 ? launch<128, true>(qkp, vtp, lpad, lens, B, L, C, heads, ctx, ctxp, st) : launch<128, false>(qkp, vtp, lpad, lens, B, L, C, heads, ctx, ctxp, st);
+  set_error("attention_planes: d_k=%d unsupported (128 or 192)", dk);
+  return FS2_ERR_INVALID;
+}
+
+}  // namespace fs2

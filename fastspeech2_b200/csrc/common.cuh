@@ -5,12 +5,14 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/fs2_b200.h"
 
 namespace fs2 {
 
 void set_error(const char* fmt, ...);
-extern unsigned long long g_kernel_launches;  // every kernel this library enqueues (fs2_kernel_launches())
+extern std::atomic<unsigned long long> g_kernel_launches;  // every kernel this library enqueues (fs2_kernel_launches())
 
 #define FS2_CUDA_CHECK(expr)                                                                   \
   do {                                                                                         \
@@ -40,37 +42,49 @@ extern unsigned long long g_kernel_launches;  // every kernel this library enque
 
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
 
+// fp16 operand planes: every activation that feeds a kind::f16 / 3xF16 contraction lives in HBM as
+//   hi = rn_fp16(clamp(x * kPlaneScale)),  lo = rn_fp16(x * kPlaneScale - hi)        (lo only where a 3xF16 consumer exists)
+// laid out [plane][row][K] (hi plane first, same row pitch), written by the kernel that produces x.  The power-of-two
+// pre-scale moves the fp16-subnormal threshold of `lo` from |x| < 2^-3 down to |x| < 2^-7 (full 22 mantissa bits above it)
+// and is undone exactly in the consuming epilogue (oscale).  Weights carry their own per-layer power-of-two scale.
+constexpr float kPlaneScale = 16.0f;
+constexpr float kPlaneInv = 1.0f / 16.0f;
+
 // out[m, n] = act( sum_{j<taps} sum_{k<K} x[b, t+j-pad, k] * w[j][n][k] + bias[n] ) (+ resid[m, n])
 // x rows have stride ldx floats, time extent L per utterance (zero outside [0,L)); m = b*L + t.
 struct TapGemm {
-  const float* x; int ldx;
+  const float* x; int ldx;      // fp32 activations (fp32 FMA and kind::tf32 families)
   int B, L, K;
   const float* w;      // [taps][N][K]
   const float* bias;   // [N] or nullptr
   int N, taps;
   int act;
   const float* resid; int ldr;  // nullptr => none
-  float* out; int ldo;
+  float* out; int ldo;          // fp32 result (may be null in the plane families when only planes are wanted)
   // tensor-core families, N == 384, taps == 1: fuse LayerNorm over the full output row into the epilogue (gemm_ln_tc.cu)
   const float* ln_gamma = nullptr; const float* ln_beta = nullptr; float ln_eps = 0.f;
-  // tensor-core families only: store output columns >= vt_col0 transposed into vt_out (see gemm_tc.cu)
+  // q|k|v projection: output columns >= vt_col0 (the V third) are stored transposed, [b*heads + h][d][t] with row pitch
+  // vt_lpad, for the attention kernel's K-major P.V operand: vt_out fp32 (kind::tf32 family) or vtp fp16 planes
   float* vt_out = nullptr; int vt_col0 = 0, vt_dk = 0, vt_heads = 0, vt_lpad = 0;
-  // f16 family (tap_gemm_f16): fp16 copies of the activations (row stride ldx_h halfs) and of w; the result goes to
-  // out (fp32, with the optional residual) and / or out_h (fp16, row stride ldo_h halfs, for the next f16 GEMM)
-  const __half* x_h = nullptr; int ldx_h = 0; const __half* w_h = nullptr; __half* out_h = nullptr; int ldo_h = 0;
-  // 3xF16 (the error-compensated family): w split into fp16 hi = rn(w), lo = rn(w - hi), same [taps][N][K] layout
-  const __half* w_hi_h = nullptr; const __half* w_lo_h = nullptr;
-  __half* split_ws = nullptr;   // scratch for the fp16 hi / lo planes of x: 2 * B*L * K halfs (= the bytes of x)
-  bool split_ready = false;     // the producer of x already wrote the planes (row_norm's split_out): skip the pre-pass
+  __half* vtp = nullptr;        // planes [P][B*heads][dk][vt_lpad], scaled by kPlaneScale
+  // plane families (kind::f16 on the hi plane; 3xF16 on hi + lo):
+  const __half* xp = nullptr;   // A operand planes [P][B*L][K], row pitch K halfs
+  const __half* w_hi = nullptr; const __half* w_lo = nullptr;   // weight planes, [taps][N][K], scaled by 1 / *w_inv
+  const float* w_inv = nullptr; // device scalar: inverse of the weight planes' power-of-two scale (null: 1)
+  float a_inv = 1.0f;           // inverse of the A planes' scale (kPlaneInv for planes written by this library)
+  __half* outp = nullptr; int ldo_p = 0; bool outp_lo = false;   // result as planes [P][B*L][ldo_p] (lo plane when outp_lo)
+  bool precise = false;         // 3xF16 (hi + lo operands) instead of plain kind::f16 on the hi planes
 };
 int tap_gemm_fp32(const TapGemm& g, cudaStream_t st);
-int tap_gemm_tf32(const TapGemm& g, cudaStream_t st);   // tcgen05 + TMA (gemm_tc.cu)
+int tap_gemm_tf32(const TapGemm& g, cudaStream_t st);   // tcgen05 + TMA, kind::tf32 on fp32 data (gemm_tc.cu)
 bool gemm_ln_tf32_supported(const TapGemm& g);         // row-complete GEMM + residual + LayerNorm (gemm_ln_tc.cu)
 int gemm_ln_tf32(const TapGemm& g, cudaStream_t st);
-int tap_gemm_3xtf32(const TapGemm& g, cudaStream_t st); // same kernel, error-compensated split operands ("3xF16")
-int tap_gemm_f16(const TapGemm& g, cudaStream_t st);    // same kernel, kind::f16 on x_h / w_h, fp32 accumulation
-int to_half(const float* src, __half* dst, long n, cudaStream_t st);
-int split_f16(const float* src, __half* hi, __half* lo, long n, cudaStream_t st);   // round to nearest, clamped to +-65504
+int tap_gemm_planes(const TapGemm& g, cudaStream_t st); // same kernel on fp16 operand planes: kind::f16 or 3xF16 (g.precise)
+int split_f16(const float* src, __half* hi, __half* lo, long n, const float* scale /*device scalar or null*/, cudaStream_t st);
+// x [rows][ldx] fp32 -> planes [2][rows][K] scaled by kPlaneScale (the one pre-pass left: LengthRegulator output, test entries)
+int split_rows(const float* x, int ldx, long rows, int K, __half* planes, cudaStream_t st);
+// power-of-two scale of a weight tensor: inv[0] = 2^-k with max|w| * 2^k in [2^13, 2^14), scale[0] = 2^k (1 for all-zero)
+int weight_scale(const float* w, long n, float* scale, float* inv, cudaStream_t st);
 constexpr int MATH_3XTF32 = FS2_MATH_3XTF32;            // also what the other tensor-core modes use for the encoder + predictors
 
 // Row LayerNorm with the fusions the path needs.
@@ -85,26 +99,34 @@ struct RowNorm {
   // optional scalar head (predictors): s = y . head_w + head_b, 0 where t >= lens[b]
   const float* head_w; const float* head_b; float* head_out; int64_t* dur_out;
   const int64_t* lens;            // optional mask for the head outputs
-  __half* out_h; int ldo_h;       // optional fp16 copy of y (A operand of an f16 GEMM)
-  __half* split_out;              // optional 3xF16 planes of y: hi at [row][C], lo at [rows + row][C] (A operand of a 3xF16 GEMM)
+  __half* split_out;              // optional operand planes of y (scaled by kPlaneScale): hi at [row][C], lo at [rows + row][C]
+  int split_lo;                   // write the lo plane too (3xF16 consumer)
 };
 int row_norm(const RowNorm& r, cudaStream_t st);
 
 int embed_posenc(const int64_t* xs, const float* table, int n_sym, const float* pe, const float* alpha, int B, int T,
-                 int C, float* out, cudaStream_t st);
+                 int C, float* out, __half* planes /*nullable: hi + lo*/, cudaStream_t st);
 
 int bucketize(const float* vals, const float* bins, int n_edges, int64_t n, int64_t* ids, cudaStream_t st);
 int one_hot(const int64_t* ids, int64_t n, int n_bins, float* out, cudaStream_t st);
 // out[r,:] = (hm[r,:] + (p_tab[p_id[r]] + p_bias)) + (e_tab[e_id[r]] + e_bias); ids from values (nullable id outs)
 int variance_embed_add(const float* hm, const float* e_val, const float* p_val, const float* e_bins, const float* p_bins,
                        int n_edges, const float* e_tab, const float* e_bias, const float* p_tab, const float* p_bias,
-                       int64_t rows, int C, float* out, int64_t* e_ids, int64_t* p_ids, cudaStream_t st);
+                       int64_t rows, int C, float* out, __half* planes /*nullable: hi (+ lo)*/, int planes_lo, int64_t* e_ids,
+                       int64_t* p_ids, cudaStream_t st);
 
 int attention_fp32(const float* qkv, const int64_t* lens, int B, int L, int C, int heads, float* ctx, cudaStream_t st);
 // tensor-core attention: q, k from qkv [B,L,3C]; v from the transposed buffer vt [B*heads, dk, lpad]
 int attention_tf32(const float* qkv, const float* vt, int lpad, const int64_t* lens, int B, int L, int C, int heads,
                    float* ctx, cudaStream_t st);
 
+// fp16-plane attention (attention_f16.cu): q, k from planes qkp [P][B*L][2C], v from vtp [P][B*heads][dk][lpad] (all scaled
+// by kPlaneScale); x3 = error-compensated (hi + lo planes, three kind::f16 products per term), else kind::f16 on the hi planes.
+// Result: ctx fp32 [B,L,C] (nullable) and / or ctxp planes [P][B*L][C] (nullable; lo plane when x3)
+int attention_planes(const __half* qkp, const __half* vtp, int lpad, const int64_t* lens, int B, int L, int C, int heads, bool x3,
+                     float* ctx, __half* ctxp, cudaStream_t st);
+// test helper: qkv fp32 [B,L,3C] -> qkp / vtp planes
+int qkv_to_planes(const float* qkv, int B, int L, int C, int heads, __half* qkp, __half* vtp, int lpad, cudaStream_t st);
 // vt[(b*heads + h)*dk + d][t] = qkv[b, t, 2C + h*dk + d]   (test helper for the single-operator entry)
 int transpose_v(const float* qkv, int B, int L, int C, int heads, float* vt, int lpad, cudaStream_t st);
 
@@ -126,6 +148,19 @@ int fold_batchnorm(const float* gamma, const float* beta, const float* mean, con
                    float* scale, float* shift, cudaStream_t st);
 
 // ---- small device helpers -----------------------------------------------------------------
+// two fp32 values -> packed fp16 hi pair and lo pair of (v * kPlaneScale), clamped to the fp16 range
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  a = fminf(fmaxf(a * kPlaneScale, -65504.f), 65504.f); b = fminf(fmaxf(b * kPlaneScale, -65504.f), 65504.f);
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 g = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - g.x, b - g.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h); lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ uint32_t hi_pair(float a, float b) {
+  a = fminf(fmaxf(a * kPlaneScale, -65504.f), 65504.f); b = fminf(fmaxf(b * kPlaneScale, -65504.f), 65504.f);
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

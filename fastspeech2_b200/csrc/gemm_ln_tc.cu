@@ -16,8 +16,9 @@
 //   pass B  partial sums of (y - mean)^2        (two-pass variance like nn.LayerNorm)
 //   pass C  (y - mean) * rstd * gamma + beta -> four 256-bit global stores per thread and chunk
 // Row statistics are exchanged between the two threads of a row through shared memory.
-// H16 = true: fp16 operands (kind::f16, 64 K-elements per 128-byte swizzle row) for FS2_MATH_F16's w_2 projection;
-// either variant can also emit the normalised rows as fp16 (out_h) for the f16 GEMM that consumes them next.
+// H16 = true: fp16 operand planes (kind::f16 on the hi planes, 64 K-elements per 128-byte swizzle row; the accumulator is
+// multiplied by the planes' exact inverse scale) for FS2_MATH_F16's out-projection and w_2; either variant can also emit
+// the normalised rows as the hi plane (scaled by kPlaneScale) of the contraction that consumes them next.
 #include "tc_common.cuh"
 
 namespace fs2 {
@@ -49,7 +50,8 @@ struct LnParams {
   const float* bias; const float* resid; int ldr;
   const float* gamma; const float* beta; float eps;
   float* out; int ldo;
-  __half* out_h; int ldo_h;     // optional fp16 copy of the result
+  __half* out_h; int ldo_h;     // optional hi plane of the result (scaled by kPlaneScale)
+  float a_inv; const float* w_inv;   // accumulator scale (operand planes' inverse pre-scale); 1 / null in the tf32 variant
 };
 
 template <int C, bool H16>
@@ -131,6 +133,7 @@ gemm_ln_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     float* xchg = reinterpret_cast<float*>(staging);          // [2][128] floats
     float v[32];
     int it = 0;
+    const float oscale = p.a_inv * (p.w_inv ? __ldg(p.w_inv) : 1.0f);
     for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, ++it) {
       const int r0 = tile * BM;
       const long m = (long)r0 + row;
@@ -159,8 +162,8 @@ gemm_ln_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tmem_ld32(taddr + c0, v);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          v[q * 4 + 0] += bv[q].x + rv[q].x; v[q * 4 + 1] += bv[q].y + rv[q].y;
-          v[q * 4 + 2] += bv[q].z + rv[q].z; v[q * 4 + 3] += bv[q].w + rv[q].w;
+          v[q * 4 + 0] = fmaf(v[q * 4 + 0], oscale, bv[q].x + rv[q].x); v[q * 4 + 1] = fmaf(v[q * 4 + 1], oscale, bv[q].y + rv[q].y);
+          v[q * 4 + 2] = fmaf(v[q * 4 + 2], oscale, bv[q].z + rv[q].z); v[q * 4 + 3] = fmaf(v[q * 4 + 3], oscale, bv[q].w + rv[q].w);
           sum += (v[q * 4] + v[q * 4 + 1]) + (v[q * 4 + 2] + v[q * 4 + 3]);
         }
         tmem_st32(taddr + c0, v);
@@ -207,10 +210,7 @@ gemm_ln_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (p.out_h != nullptr) {
             uint32_t h[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const __half2 t = __floats2half2_rn(fminf(fmaxf(v[2 * j], -65504.f), 65504.f), fminf(fmaxf(v[2 * j + 1], -65504.f), 65504.f));
-              h[j] = *reinterpret_cast<const uint32_t*>(&t);
-            }
+            for (int j = 0; j < 16; ++j) h[j] = hi_pair(v[2 * j], v[2 * j + 1]);
             __half* dh = p.out_h + m * p.ldo_h + c0;
             st_global_v8_b32(dh, h); st_global_v8_b32(dh + 16, h + 8);
           }
@@ -229,16 +229,6 @@ gemm_ln_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
-int sm_count_ln() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
-  return n;
-}
-
 }  // namespace
 
 bool gemm_ln_tf32_supported(const TapGemm& g) { return g.taps == 1 && g.N == 384 && g.K % 4 == 0 && g.ln_gamma && !g.vt_out && g.act == ACT_NONE; }
@@ -249,38 +239,36 @@ int launch_ln(const TapGemm& g, cudaStream_t st) {
   constexpr int C = 384;
   using L = LCfg<C, H16>;
   const uint64_t M = (uint64_t)g.B * g.L;
-  static bool configured = false;
-  if (!configured) {
-    FS2_CUDA_CHECK(cudaFuncSetAttribute(gemm_ln_tf32_kernel<C, H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
-    configured = true;
-  }
-  CUtensorMap ma, mb;
+  static unsigned long long configured = 0;   // per-device bit mask
   int rc;
+  if ((rc = ensure_smem_attr(gemm_ln_tf32_kernel<C, H16>, L::SMEM, &configured))) return rc;
+  CUtensorMap ma, mb;
   const int esz = H16 ? 2 : 4;
-  const uint64_t arow = H16 ? (uint64_t)g.ldx_h * 2 : (uint64_t)g.ldx * 4;
-  if ((rc = make_map(&ma, H16 ? (const void*)g.x_h : (const void*)g.x, g.K, M, 1, arow, arow * M, BM, H16))) return rc;
-  if ((rc = make_map(&mb, H16 ? (const void*)g.w_h : (const void*)g.w, g.K, C, 1, (uint64_t)g.K * esz, (uint64_t)g.K * esz * C, L::HALF, H16))) return rc;
+  const uint64_t arow = H16 ? (uint64_t)g.K * 2 : (uint64_t)g.ldx * 4;
+  if ((rc = make_map(&ma, H16 ? (const void*)g.xp : (const void*)g.x, g.K, M, 1, arow, arow * M, BM, H16))) return rc;
+  if ((rc = make_map(&mb, H16 ? (const void*)g.w_hi : (const void*)g.w, g.K, C, 1, (uint64_t)g.K * esz, (uint64_t)g.K * esz * C, L::HALF, H16))) return rc;
   LnParams p;
   p.M = (int)M; p.K = g.K; p.bias = g.bias; p.resid = g.resid; p.ldr = g.ldr;
   p.gamma = g.ln_gamma; p.beta = g.ln_beta; p.eps = g.ln_eps; p.out = g.out; p.ldo = g.ldo;
-  p.out_h = g.out_h; p.ldo_h = g.ldo_h;
+  p.out_h = g.outp; p.ldo_h = g.ldo_p;
+  p.a_inv = H16 ? g.a_inv : 1.0f; p.w_inv = H16 ? g.w_inv : nullptr;
   const int tiles = (int)((M + BM - 1) / BM);
-  const int grid = tiles < sm_count_ln() ? tiles : sm_count_ln();
+  const int grid = tiles < sm_count_current() ? tiles : sm_count_current();
   gemm_ln_tf32_kernel<C, H16><<<grid, LN_THREADS, L::SMEM, st>>>(ma, mb, p);
   FS2_LAUNCH_CHECK();
   return FS2_OK;
 }
 }  // namespace
 
-// g.x_h set: fp16 operands (x_h, w_h); g.out_h set: also emit the result as fp16
+// g.xp set: fp16 operand planes (hi planes of x and w); g.outp set: also emit the result's hi plane
 int gemm_ln_tf32(const TapGemm& g, cudaStream_t st) {
   FS2_REQUIRE(gemm_ln_tf32_supported(g), "gemm_ln_tf32: unsupported shape (N=%d taps=%d)", g.N, g.taps);
   FS2_REQUIRE(g.ldo % 8 == 0 && (!g.resid || g.ldr % 4 == 0) && g.out && (reinterpret_cast<uintptr_t>(g.out) & 31) == 0,
               "gemm_ln_tf32: row strides / output alignment");
-  FS2_REQUIRE(!g.out_h || (g.ldo_h % 16 == 0 && (reinterpret_cast<uintptr_t>(g.out_h) & 31) == 0), "gemm_ln_tf32: fp16 output rows must be 32-byte aligned");
+  FS2_REQUIRE(!g.outp || (g.ldo_p % 16 == 0 && (reinterpret_cast<uintptr_t>(g.outp) & 31) == 0), "gemm_ln_tf32: fp16 output rows must be 32-byte aligned");
   if ((uint64_t)g.B * g.L == 0) return FS2_OK;
-  if (g.x_h) {
-    FS2_REQUIRE(g.w_h && g.K % 8 == 0 && g.ldx_h % 8 == 0 && (reinterpret_cast<uintptr_t>(g.x_h) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.w_h) & 15) == 0,
+  if (g.xp) {
+    FS2_REQUIRE(g.w_hi && g.K % 8 == 0 && (reinterpret_cast<uintptr_t>(g.xp) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.w_hi) & 15) == 0,
                 "gemm_ln_tf32: fp16 operands must be 16-byte aligned with K a multiple of 8");
     return launch_ln<true>(g, st);
   }

@@ -6,12 +6,15 @@
 //
 // Same contract as gemm_fp32.cu (the CUDA-core family).  Three instantiation families:
 //   <BN, false, false>  plain tf32 (one MMA per product) on the fp32 activations themselves: the decoder side in
-//                       FS2_MATH_TF32, and the GEMMs whose A operand has no fp16 copy in FS2_MATH_F16;
-//   <BN, false, true>   kind::f16 on fp16 copies of activations and weights (FS2_MATH_F16: q|k|v, conv-FFN, mel
-//                       projection, Postnet); see "HALF" below;
-//   <BN, true,  true>   error-compensated "3xF16" (encoder and predictors in every tensor-core mode, everything in
-//                       FS2_MATH_3XTF32): their outputs feed round() / bucketize(), where 10-bit-mantissa noise
-//                       (~1e-3) would flip integers; see "PRECISE && HALF" below;
+//                       FS2_MATH_TF32;
+//   <BN, false, true>   kind::f16 on the hi planes of activations and weights (decoder side in FS2_MATH_F16);
+//                       see "HALF" below;
+//   <BN, true,  true>   error-compensated "3xF16" on hi + lo planes (encoder and predictors in every tensor-core mode,
+//                       everything in FS2_MATH_3XTF32): fp32-class results; their outputs feed round() / bucketize(),
+//                       where 10-bit-mantissa noise (~1e-3) would flip integers; see "PRECISE && HALF" below.
+// Operand planes (common.cuh): activations are pre-scaled by kPlaneScale, weights by a per-layer power of two; the
+// epilogue multiplies the accumulator by the exact inverse (oscale) in the same FMA that adds the bias.  Results leave as
+// fp32 rows and / or as the operand planes of the next contraction (no separate split / conversion pass).
 //
 // Why no im2col: activations are [B, time, channel] fp32 with channels innermost, which *is* the
 // K-major A operand of a GEMM.  Tap j of a 1-D convolution is the same matrix shifted by
@@ -36,16 +39,19 @@
 // spent on padding (at L = 800 that was 12 %).  Plain GEMMs (taps == 1) tile the flat [B*L, K] matrix.
 // Every mbarrier wait is bounded: a pipeline bug traps instead of hanging the GPU.
 //
-// PRECISE && HALF ("3xF16", the default error-compensated family): a small pre-pass (split_rows_f16_kernel) writes the
-// fp32 activations as two fp16 planes, hi = rn(x) and lo = rn(x - hi), the weights are split the same way at load
-// time, and the GEMM loads all four operand tiles by TMA and runs the three products on kind::f16 -- no split warps, no
-// shared-memory rewrite, and a pipeline step covers twice the K for the same 12 MMAs.  hi + lo carries 22 mantissa
-// bits where lo is a normal fp16 (|x| >= 2^-3); smaller elements -- all weights of a trained layer -- keep an absolute
-// error of up to 2^-25 = 3e-8 (subnormal lo), an output error floor of ~sqrt(K) * rms(x) * 2e-8 that sits well below
-// the tensor core's own accumulation error for O(1) results (tests/test_numerics_model.py).  The lo plane is addressed through the same tensor
-// map: plane stride = B*L rows, i.e. utterance index b + B.
+// PRECISE && HALF ("3xF16", the error-compensated family): the producer of x writes it as two fp16 planes, hi = rn(s x)
+// and lo = rn(s x - hi), the weights are split the same way at load time (with their own power-of-two scale, so the lo
+// plane of a trained layer's small weights is a normal fp16, not a subnormal), and the GEMM loads all four operand tiles
+// by TMA.  The three products run as TWO instructions per K = 16 step: the B stage holds [b_hi | b_lo] as one 2*BN-row
+// tile, so  a_hi . [b_hi | b_lo]  is a single N = 2*BN MMA into accumulator columns [0,BN) (main term) and [BN,2BN)
+// (correction), and  a_lo . b_hi  (N = BN) accumulates into the correction columns; the epilogue adds the two.  Versus
+// three N = BN MMAs into one accumulator: 20 % less shared-memory operand traffic (the N = BN 3xF16 loop sat at the
+// 128 B/clk port limit), a third of the issue slots, and the main sum sees K/16 round-toward-zero accumulation steps
+// instead of 3K/16.  (BN = 80 keeps three MMAs into one accumulator: its correction block would not start on a
+// 32-column TMEM boundary.)  The lo plane is addressed through the same tensor map: plane stride = B*L rows, i.e.
+// utterance index b + B.
 //
-// HALF = true, PRECISE = false (FS2_MATH_F16, the decoder's conv-FFN): the same pipeline on fp16 copies of the activations and weights
+// HALF = true, PRECISE = false (FS2_MATH_F16, the decoder side): the same pipeline on the hi planes of the activations and weights
 // with kind::f16 -- a 128-byte swizzle row then holds 64 K-elements and one MMA covers K = 16, so a pipeline step moves
 // the same bytes and issues the same four MMAs but does twice the work; the epilogue can emit the result as fp16 for
 // the next f16 GEMM (conv k=9 -> ReLU -> conv k=1).  fp16 has tf32's 10-bit mantissa; accumulation stays fp32.
@@ -73,14 +79,15 @@ struct TcParams {
   int K, taps, pad;
   const float* bias; const float* resid; int ldr; int act;
   float* out; int ldo;
-  __half* out_h; int ldo_h;      // HALF only: fp16 copy of the result (out may then be null)
+  float a_inv; const float* w_inv;   // accumulator scale = a_inv * (w_inv ? *w_inv : 1): undoes the operand planes' pre-scaling
+  __half* outp; __half* outp_lo; int ldo_p;   // result as operand planes (hi; lo when the consumer is 3xF16); out may then be null
   // optional: columns >= vt_col0 are the V third of a q|k|v projection and are stored transposed,
   // vt[(b*heads + h)*dk + d][t] with row pitch vt_lpad, for the attention kernel's K-major P.V operand
-  float* vt_out; int vt_col0, vt_dk, vt_heads, vt_lpad, vt_L;
+  float* vt_out; __half* vtp; __half* vtp_lo; int vt_col0, vt_dk, vt_heads, vt_lpad, vt_L;
   int debug;   // FS2_GEMM_DEBUG: bit0 skip tcgen05.ld, bit1 skip stores (profiling experiments only)
 };
 
-constexpr int pow2_at_least(int x) { return x <= 32 ? 32 : x <= 64 ? 64 : x <= 128 ? 128 : 256; }
+constexpr int pow2_at_least(int x) { return x <= 32 ? 32 : x <= 64 ? 64 : x <= 128 ? 128 : x <= 256 ? 256 : 512; }
 
 template <int BN, bool PRECISE, bool HALF = false>
 struct Cfg {
@@ -89,13 +96,15 @@ struct Cfg {
   static constexpr bool SPLIT16 = PRECISE;                // A hi / lo are fp16 planes in global memory, loaded like B hi / lo
   static_assert(!PRECISE || HALF, "the error-compensated family is 3xF16");
   static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
-  static constexpr int ACC_STRIDE = pow2_at_least(BN);     // TMEM columns per accumulator buffer
+  static constexpr bool WIDE = PRECISE && (BN % 32 == 0);  // main + correction accumulators, a_hi . [b_hi | b_lo] as one MMA
+  static constexpr int ACC_STRIDE = pow2_at_least(WIDE ? 2 * BN : BN);     // TMEM columns per accumulator buffer
   static constexpr int NACC = 512 / ACC_STRIDE > 4 ? 4 : 512 / ACC_STRIDE;   // accumulator buffers in flight (2 for BN > 128, else 4)
   static constexpr int TMEM_COLS = NACC * ACC_STRIDE;
   static constexpr int GROUPS = 2;       // epilogue warp groups (4 warps each), alternate 32-column chunks
   static constexpr int THREADS = 64 + GROUPS * 128;
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
   static constexpr uint32_t IDESC = HALF ? idesc_f16(BM, BN) : idesc_tf32(BM, BN);
+  static constexpr uint32_t IDESC_WIDE = idesc_f16(BM, WIDE ? 2 * BN : BN);
   static constexpr int BKE = HALF ? 2 * BK : BK;           // K elements per pipeline step
 
   static constexpr int A_LO = A_BYTES;                                  // offsets inside a stage
@@ -199,7 +208,11 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           const uint64_t a_hi = make_sw128_kmajor_desc(base), b_hi = make_sw128_kmajor_desc(base + C::B_HI);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {  // +32 bytes along K inside the swizzle row = +2 in descriptor units
-            if (PRECISE) {
+            if (C::WIDE) {
+              const uint64_t a_lo = make_sw128_kmajor_desc(base + C::A_LO);
+              umma_f16(d, a_hi + 2 * k, b_hi + 2 * k, C::IDESC_WIDE, (s | k) != 0);   // [0,BN) += a_hi b_hi, [BN,2BN) += a_hi b_lo
+              umma_f16(d + BN, a_lo + 2 * k, b_hi + 2 * k, C::IDESC, 1);              // [BN,2BN) += a_lo b_hi
+            } else if (PRECISE) {
               const uint64_t a_lo = make_sw128_kmajor_desc(base + C::A_LO), b_lo = make_sw128_kmajor_desc(base + C::B_LO);
               umma_f16(d, a_lo + 2 * k, b_hi + 2 * k, C::IDESC, (s | k) != 0);  // small terms first
               umma_f16(d, a_hi + 2 * k, b_lo + 2 * k, C::IDESC, 1);
@@ -225,6 +238,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     const int act = p.act, ldr = p.ldr, ldo = p.ldo;
     const float* __restrict__ resid = p.resid; float* __restrict__ out = p.out;
     const bool has_res = resid != nullptr;
+    const float oscale = p.a_inv * (p.w_inv ? __ldg(p.w_inv) : 1.0f);   // exact power of two (1 in the tf32 family)
     float v[32];
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -246,67 +260,95 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       mbar_wait(&acc_full[acc], (it / C::NACC) & 1);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + lane_off + (uint32_t)(acc * C::ACC_STRIDE);
-      const bool to_vt = p.vt_out != nullptr && n0 >= p.vt_col0;   // tile-uniform (tile widths divide the V third)
+      const bool to_vt = (p.vt_out != nullptr || p.vtp != nullptr) && n0 >= p.vt_col0;   // tile-uniform (tile widths divide the V third)
 #pragma unroll 1
       for (int c0 = grp * 32; c0 < BN; c0 += 32 * C::GROUPS) {
         // the residual is fetched first so the loads are in flight across the TMEM load; the bias comes from shared
         // memory (global loads next to their use stalled the whole epilogue: ncu long-scoreboard samples)
         float4 rv[8];
         const float4* bq = reinterpret_cast<const float4*>(bias_s + n0 + c0);
-        if (to_vt) {
-          __syncwarp();
-          tmem_ld32(taddr + c0, v);
-          if (row_ok) {
-            // transposed store: for a fixed column the 32 lanes hold 32 consecutive time steps -> 128-byte rows
-            const long ub = m / p.vt_L; const int ut = (int)(m - ub * p.vt_L);
-            const int rel = n0 + c0 - p.vt_col0, hh = rel / p.vt_dk, d0 = rel - hh * p.vt_dk;
-            float* dst = p.vt_out + ((ub * p.vt_heads + hh) * p.vt_dk + d0) * (long)p.vt_lpad + ut;
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c0 + i < BN) dst[(long)i * p.vt_lpad] = v[i] + bias_s[n0 + c0 + i];
-          }
-          continue;
-        }
         const bool full = c0 + 32 <= BN;          // all 32 columns of the chunk exist (always, except the N = 80 tail)
-        if (has_res && row_ok) {
+        if (has_res && row_ok && !to_vt) {
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             if (full || c0 + q * 4 < BN) rv[q] = __ldg(reinterpret_cast<const float4*>(resid + m * ldr + n0 + c0 + q * 4));
         }
         __syncwarp();
-        if (!(p.debug & 1)) tmem_ld32(taddr + c0, v);
-        if (row_ok && !(p.debug & 2)) {
-          // flags were hoisted into registers and the activation switch sits outside the element loops: the
-          // per-element predicate / constant-bank reloads of the first version made this epilogue latency-bound
+        if (!(p.debug & 1)) {
+          if (C::WIDE) {                          // main + correction accumulators
+            float v2[32];
+            tmem_ld32_nowait(taddr + c0, v); tmem_ld32_nowait(taddr + BN + c0, v2);
+            tmem_ld_wait_pin<32>(v); tmem_ld_wait_pin<32>(v2);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) { const float4 b4 = bq[q]; v[q * 4] += b4.x; v[q * 4 + 1] += b4.y; v[q * 4 + 2] += b4.z; v[q * 4 + 3] += b4.w; }
-          if (act == ACT_RELU) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-          } else if (act == ACT_TANH) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
+            for (int i = 0; i < 32; ++i) v[i] += v2[i];
+          } else {
+            tmem_ld32(taddr + c0, v);
           }
-          if (has_res) {
+        }
+        if (!row_ok || (p.debug & 2)) continue;
+        // flags were hoisted into registers and the activation switch sits outside the element loops: the
+        // per-element predicate / constant-bank reloads of the first version made this epilogue latency-bound
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-              if (full || c0 + q * 4 < BN) { v[q * 4] += rv[q].x; v[q * 4 + 1] += rv[q].y; v[q * 4 + 2] += rv[q].z; v[q * 4 + 3] += rv[q].w; }
-          }
-          if (HALF && p.out_h != nullptr) {              // fp16 copy for the next f16 GEMM: two 32-byte stores
-            uint32_t h[16];
+        for (int q = 0; q < 8; ++q) {
+          const float4 b4 = bq[q];
+          v[q * 4] = fmaf(v[q * 4], oscale, b4.x); v[q * 4 + 1] = fmaf(v[q * 4 + 1], oscale, b4.y);
+          v[q * 4 + 2] = fmaf(v[q * 4 + 2], oscale, b4.z); v[q * 4 + 3] = fmaf(v[q * 4 + 3], oscale, b4.w);
+        }
+        if (to_vt) {
+          // transposed store: for a fixed column the 32 lanes hold 32 consecutive time steps -> contiguous 128-byte
+          // (fp32) / 64-byte (fp16 plane) runs
+          const long ub = m / p.vt_L; const int ut = (int)(m - ub * p.vt_L);
+          const int rel = n0 + c0 - p.vt_col0, hh = rel / p.vt_dk, d0 = rel - hh * p.vt_dk;
+          const long o = ((ub * p.vt_heads + hh) * p.vt_dk + d0) * (long)p.vt_lpad + ut;
+          if (p.vt_out != nullptr) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const __half2 t = __floats2half2_rn(fminf(fmaxf(v[2 * i], -65504.f), 65504.f), fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f));
-              h[i] = *reinterpret_cast<const uint32_t*>(&t);
+            for (int i = 0; i < 32; ++i)
+              if (c0 + i < BN) p.vt_out[o + (long)i * p.vt_lpad] = v[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              if (c0 + i >= BN) break;
+              uint32_t hi, lo;
+              split_pair(v[i], v[i + 1], hi, lo);
+              const __half2 h2 = *reinterpret_cast<const __half2*>(&hi), l2 = *reinterpret_cast<const __half2*>(&lo);
+              p.vtp[o + (long)i * p.vt_lpad] = __low2half(h2); p.vtp[o + (long)(i + 1) * p.vt_lpad] = __high2half(h2);
+              if (p.vtp_lo != nullptr) { p.vtp_lo[o + (long)i * p.vt_lpad] = __low2half(l2); p.vtp_lo[o + (long)(i + 1) * p.vt_lpad] = __high2half(l2); }
             }
-            __half* dh = p.out_h + m * p.ldo_h + n0 + c0;
-            if (full || c0 + 16 <= BN) st_global_v8_b32(dh, h);
-            if (full) st_global_v8_b32(dh + 16, h + 8);
           }
+          continue;
+        }
+        if (act == ACT_RELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        } else if (act == ACT_TANH) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
+        }
+        if (has_res) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (full || c0 + q * 4 < BN) { v[q * 4] += rv[q].x; v[q * 4 + 1] += rv[q].y; v[q * 4 + 2] += rv[q].z; v[q * 4 + 3] += rv[q].w; }
+        }
+        if (HALF && p.outp != nullptr) {              // operand planes of the next contraction: two 32-byte stores per plane
+          uint32_t h[16], l[16];
+          if (p.outp_lo != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) split_pair(v[2 * i], v[2 * i + 1], h[i], l[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) h[i] = hi_pair(v[2 * i], v[2 * i + 1]);
+          }
+          const long off = m * p.ldo_p + n0 + c0;
+          if (full || c0 + 16 <= BN) st_global_v8_b32(p.outp + off, h);
+          if (full) st_global_v8_b32(p.outp + off + 16, h + 8);
+          if (p.outp_lo != nullptr) {
+            if (full || c0 + 16 <= BN) st_global_v8_b32(p.outp_lo + off, l);
+            if (full) st_global_v8_b32(p.outp_lo + off + 16, l + 8);
+          }
+        }
+        if (out != nullptr) {
           float* dst = out + m * ldo + n0 + c0;          // this thread's row: four sector-complete 32-byte stores
-          if (HALF && out == nullptr) {
-            // fp16-only result (the hidden activations of the conv-FFN)
-          } else if (full) {
+          if (full) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) st_global_v8(dst + q * 8, v + q * 8);
           } else {
@@ -330,8 +372,9 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   }
 }
 
-// 3xF16 pre-pass: x [rows][ldx] fp32 -> S[0] = hi plane, S[1] = lo plane, each [rows][K] fp16;
-// hi = rn(clamp(x)), lo = rn(x - hi).  One float4 per thread and step, 8-byte stores.
+// Pre-pass for tensors that enter the library as fp32 (LengthRegulator output, single-operator test entries):
+// x [rows][ldx] fp32 -> S[0] = hi plane, S[1] = lo plane, each [rows][K] fp16, scaled by kPlaneScale.
+// One float4 per thread and step, 8-byte stores.
 __global__ void split_rows_f16_kernel(const float* __restrict__ x, int ldx, long rows, int K, __half* __restrict__ S) {
   const int kq = K >> 2;
   const long quads = rows * kq;
@@ -340,51 +383,38 @@ __global__ void split_rows_f16_kernel(const float* __restrict__ x, int ldx, long
     const long r = i / kq;
     const int c = (int)(i - r * kq) * 4;
     const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
-    const float f0 = fminf(fmaxf(v.x, -65504.f), 65504.f), f1 = fminf(fmaxf(v.y, -65504.f), 65504.f);
-    const float f2 = fminf(fmaxf(v.z, -65504.f), 65504.f), f3 = fminf(fmaxf(v.w, -65504.f), 65504.f);
-    const __half2 h01 = __floats2half2_rn(f0, f1), h23 = __floats2half2_rn(f2, f3);
-    const float2 g01 = __half22float2(h01), g23 = __half22float2(h23);
-    const __half2 l01 = __floats2half2_rn(f0 - g01.x, f1 - g01.y), l23 = __floats2half2_rn(f2 - g23.x, f3 - g23.y);
     uint2 hv, lv;
-    hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
-    lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+    split_pair(v.x, v.y, hv.x, lv.x);
+    split_pair(v.z, v.w, hv.y, lv.y);
     *reinterpret_cast<uint2*>(S + r * K + c) = hv;
     *reinterpret_cast<uint2*>(lo_plane + r * K + c) = lv;
   }
 }
 
 // ---- host side ----------------------------------------------------------------------------------
-int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
-  return n;
-}
-
 template <int BN, bool PRECISE, bool HALF = false>
 int launch(const TapGemm& g, cudaStream_t st) {
   using C = Cfg<BN, PRECISE, HALF>;
-  static bool configured = false;
-  if (!configured) {
-    FS2_CUDA_CHECK(cudaFuncSetAttribute(tap_gemm_tf32_kernel<BN, PRECISE, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    configured = true;
-  }
+  static unsigned long long configured = 0;   // per-device bit mask
+  int rc;
+  if ((rc = ensure_smem_attr(tap_gemm_tf32_kernel<BN, PRECISE, HALF>, C::SMEM, &configured))) return rc;
   TcParams p;
   p.K = g.K; p.taps = g.taps; p.pad = (g.taps - 1) / 2;
   p.bias = g.bias; p.resid = g.resid; p.ldr = g.ldr; p.act = g.act; p.out = g.out; p.ldo = g.ldo;
-  p.out_h = HALF ? g.out_h : nullptr; p.ldo_h = g.ldo_h;
+  const long rows = (long)g.B * g.L;
+  p.a_inv = HALF ? g.a_inv : 1.0f; p.w_inv = HALF ? g.w_inv : nullptr;
+  p.outp = HALF ? g.outp : nullptr; p.ldo_p = g.ldo_p;
+  p.outp_lo = (HALF && g.outp && g.outp_lo) ? g.outp + rows * g.ldo_p : nullptr;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FS2_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
-  p.vt_out = g.vt_out; p.vt_col0 = g.vt_col0; p.vt_dk = g.vt_dk; p.vt_heads = g.vt_heads; p.vt_lpad = g.vt_lpad; p.vt_L = g.L;
+  p.vt_out = HALF ? nullptr : g.vt_out; p.vtp = HALF ? g.vtp : nullptr;
+  p.vtp_lo = (HALF && g.vtp && g.outp_lo) ? g.vtp + (long)g.B * g.vt_heads * g.vt_dk * g.vt_lpad : nullptr;
+  p.vt_col0 = g.vt_col0; p.vt_dk = g.vt_dk; p.vt_heads = g.vt_heads; p.vt_lpad = g.vt_lpad; p.vt_L = g.L;
   CUtensorMap ma, mb, mb_lo, ma16;
-  int rc;
   const int esz = HALF ? 2 : 4;
   constexpr bool AH = HALF;
-  constexpr int planes = HALF && PRECISE ? 2 : 1;          // 3xF16: [hi plane][lo plane], each [B*L][K] fp16 (split_rows_f16)
-  const void* xa = HALF ? (PRECISE ? (const void*)g.split_ws : (const void*)g.x_h) : (const void*)g.x;
-  const uint64_t row_bytes = HALF ? (PRECISE ? (uint64_t)g.K * 2 : (uint64_t)g.ldx_h * 2) : (uint64_t)g.ldx * 4;
+  constexpr int planes = HALF && PRECISE ? 2 : 1;          // 3xF16: [hi plane][lo plane], each [B*L][K] fp16
+  const void* xa = HALF ? (const void*)g.xp : (const void*)g.x;
+  const uint64_t row_bytes = HALF ? (uint64_t)g.K * 2 : (uint64_t)g.ldx * 4;
   if (g.taps == 1) {  // flat [B*L, K]
     const uint64_t M = (uint64_t)g.B * g.L;
     p.L = (int)M; p.tiles_per_utt = 0;
@@ -405,11 +435,11 @@ int launch(const TapGemm& g, cudaStream_t st) {
     if ((rc = make_map(&ma16, xa, g.K, g.L, (uint64_t)g.B * planes, row_bytes, row_bytes * g.L, 16, AH))) return rc;
   }
   p.n_tiles = g.N / BN;
-  const void* w_hi = PRECISE ? (const void*)g.w_hi_h : HALF ? (const void*)g.w_h : (const void*)g.w;
+  const void* w_hi = HALF ? (const void*)g.w_hi : (const void*)g.w;
   if ((rc = make_map(&mb, w_hi, g.K, g.N, g.taps, (uint64_t)g.K * esz, (uint64_t)g.K * esz * g.N, BN, HALF))) return rc;
-  if ((rc = make_map(&mb_lo, PRECISE ? (const void*)g.w_lo_h : w_hi, g.K, g.N, g.taps, (uint64_t)g.K * esz, (uint64_t)g.K * esz * g.N, BN, HALF))) return rc;
+  if ((rc = make_map(&mb_lo, PRECISE ? (const void*)g.w_lo : w_hi, g.K, g.N, g.taps, (uint64_t)g.K * esz, (uint64_t)g.K * esz * g.N, BN, HALF))) return rc;
   const int total = p.m_tiles * p.n_tiles;
-  const int grid = total < sm_count() ? total : sm_count();
+  const int grid = total < sm_count_current() ? total : sm_count_current();
   tap_gemm_tf32_kernel<BN, PRECISE, HALF><<<grid, C::THREADS, C::SMEM, st>>>(ma, mb, mb_lo, ma16, p);
   FS2_LAUNCH_CHECK();
   return FS2_OK;
@@ -419,7 +449,7 @@ int check_output(const TapGemm& g, const char* who) {
   FS2_REQUIRE((g.taps & 1) == 1, "%s: taps must be odd", who);
   FS2_REQUIRE(g.N % 16 == 0 && g.N <= 2048, "%s: N (%d) must be a multiple of 16 and fit the staged bias vector (2048)", who, g.N);
   FS2_REQUIRE(!g.resid || g.ldr % 4 == 0, "%s: row strides must be 16-byte multiples", who);
-  FS2_REQUIRE(g.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(g.out) & 31) == 0, "%s: output rows must be 32-byte aligned (256-bit stores)", who);
+  FS2_REQUIRE(!g.out || (g.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(g.out) & 31) == 0), "%s: output rows must be 32-byte aligned (256-bit stores)", who);
   return FS2_OK;
 }
 int check_common(const TapGemm& g, const char* who) {
@@ -452,61 +482,96 @@ int tap_gemm_tf32(const TapGemm& g, cudaStream_t st) {
   return FS2_ERR_INVALID;
 }
 
-int tap_gemm_3xtf32(const TapGemm& g, cudaStream_t st) {
-  int rc = check_common(g, "tap_gemm_3xtf32");
-  if (rc) return rc;
-  if ((long)g.B * g.L == 0) return FS2_OK;
-  FS2_REQUIRE(g.w_hi_h && g.w_lo_h && g.split_ws, "tap_gemm_3xtf32: split weights / activation scratch missing");
-  FS2_REQUIRE(g.K % 8 == 0, "tap_gemm_3xtf32: K (%d) must be a multiple of 8", g.K);
-  if (!g.split_ready) {
-    // pre-pass: fp32 activations -> fp16 hi / lo planes (rows of K contiguous halfs)
-    const long rows = (long)g.B * g.L;
-    const long quads = rows * (g.K / 4);
-    long blocks = (quads + 255) / 256;
-    split_rows_f16_kernel<<<(int)(blocks > 148 * 16 ? 148 * 16 : blocks), 256, 0, st>>>(g.x, g.ldx, rows, g.K, g.split_ws);
-    FS2_LAUNCH_CHECK();
+// kind::f16 on the hi planes (g.precise == false) or 3xF16 on hi + lo planes
+int tap_gemm_planes(const TapGemm& g, cudaStream_t st) {
+  const char* who = g.precise ? "tap_gemm_planes(3xF16)" : "tap_gemm_planes(f16)";
+  FS2_REQUIRE(g.xp && g.w_hi && (!g.precise || g.w_lo) && (g.out || g.outp || g.vtp), "%s: operand planes / an output missing", who);
+  FS2_REQUIRE(g.K % 8 == 0, "%s: K (%d) must be a multiple of 8 (16-byte plane rows)", who, g.K);
+  FS2_REQUIRE((reinterpret_cast<uintptr_t>(g.xp) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.w_hi) & 15) == 0, "%s: operands must be 16-byte aligned", who);
+  FS2_REQUIRE(!g.outp || (g.ldo_p % 16 == 0 && (reinterpret_cast<uintptr_t>(g.outp) & 31) == 0 && (((long)g.B * g.L * g.ldo_p) % 16) == 0),
+              "%s: output plane rows must be 32-byte aligned", who);
+  {
+    const int bn = g.precise ? 128 : (g.N % 256 == 0 ? 256 : g.N % 192 == 0 ? 192 : 128);
+    FS2_REQUIRE(!g.vtp || (g.vt_lpad % 8 == 0 && g.N % bn == 0 && g.vt_col0 % bn == 0 && g.vt_dk % 32 == 0),
+                "%s: transposed V planes need a 16-byte row pitch and tile-aligned thirds", who);
   }
-  // narrower tiles than the plain kernel: the stage holds four operand tiles and the encoder's M is small
-  if (g.N % 128 == 0) return launch<128, true, true>(g, st);
-  if (g.N % 96 == 0) return launch<96, true, true>(g, st);
-  if (g.N % 80 == 0) return launch<80, true, true>(g, st);
-  if (g.N % 64 == 0) return launch<64, true, true>(g, st);
-  set_error("tap_gemm_3xtf32: N=%d has no supported tile width", g.N);
-  return FS2_ERR_INVALID;
-}
-
-int tap_gemm_f16(const TapGemm& g, cudaStream_t st) {
-  const char* who = "tap_gemm_f16";
-  FS2_REQUIRE(g.x_h && g.w_h && (g.out || g.out_h), "%s: fp16 operands / an output missing", who);
-  FS2_REQUIRE(g.K % 8 == 0 && g.ldx_h % 8 == 0, "%s: K (%d) and the fp16 row stride must be multiples of 8", who, g.K);
-  FS2_REQUIRE((reinterpret_cast<uintptr_t>(g.x_h) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.w_h) & 15) == 0, "%s: operands must be 16-byte aligned", who);
-  FS2_REQUIRE(!g.out_h || (g.ldo_h % 16 == 0 && (reinterpret_cast<uintptr_t>(g.out_h) & 31) == 0), "%s: fp16 output rows must be 32-byte aligned", who);
   FS2_REQUIRE(!g.ln_gamma, "%s: the LayerNorm epilogue lives in gemm_ln_tc.cu", who);
   int rc = check_output(g, who);
   if (rc) return rc;
   if ((long)g.B * g.L == 0) return FS2_OK;
-  if (g.N % 256 == 0) return launch<256, false, true>(g, st);
-  if (g.N % 192 == 0) return launch<192, false, true>(g, st);
-  if (g.N % 128 == 0) return launch<128, false, true>(g, st);
-  if (g.N % 80 == 0) return launch<80, false, true>(g, st);
-  set_error("%s: N=%d has no supported tile width (multiples of 80, 128 or 192)", who, g.N);
+  if (g.precise) {
+    // narrower tiles than the plain kernel: the stage holds four operand tiles and the encoder's M is small
+    if (g.N % 128 == 0) return launch<128, true, true>(g, st);
+    if (g.N % 96 == 0) return launch<96, true, true>(g, st);
+    if (g.N % 80 == 0) return launch<80, true, true>(g, st);
+    if (g.N % 64 == 0) return launch<64, true, true>(g, st);
+  } else {
+    if (g.N % 256 == 0) return launch<256, false, true>(g, st);
+    if (g.N % 192 == 0) return launch<192, false, true>(g, st);
+    if (g.N % 128 == 0) return launch<128, false, true>(g, st);
+    if (g.N % 80 == 0) return launch<80, false, true>(g, st);
+  }
+  set_error("%s: N=%d has no supported tile width", who, g.N);
   return FS2_ERR_INVALID;
 }
 
+int split_rows(const float* x, int ldx, long rows, int K, __half* planes, cudaStream_t st) {
+  if (rows == 0) return FS2_OK;
+  FS2_REQUIRE(K % 4 == 0 && ldx % 4 == 0, "split_rows: K and the row stride must be multiples of 4");
+  const long quads = rows * (K / 4);
+  long blocks = (quads + 255) / 256;
+  split_rows_f16_kernel<<<(int)(blocks > 148 * 16 ? 148 * 16 : blocks), 256, 0, st>>>(x, ldx, rows, K, planes);
+  FS2_LAUNCH_CHECK();
+  return FS2_OK;
+}
+
 namespace {
-__global__ void split_f16_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo, long n) {
+// weights: hi = rn(s w), lo = rn(s w - hi) with the layer's power-of-two scale s (device scalar; null = 1)
+__global__ void split_f16_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo, long n,
+                                 const float* __restrict__ scale) {
+  const float s = scale ? __ldg(scale) : 1.0f;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    const float x = fminf(fmaxf(src[i], -65504.f), 65504.f);
+    const float x = fminf(fmaxf(src[i] * s, -65504.f), 65504.f);
     const __half h = __float2half_rn(x);
     hi[i] = h; lo[i] = __float2half_rn(x - __half2float(h));
   }
 }
+// one CTA: max |w| -> s = 2^k with s * max in [2^13, 2^14)  (fp16 max is 2^16: headroom for rounding, none of the
+// weight's lo plane below ~2^-17 of the layer maximum is subnormal)
+__global__ void weight_scale_kernel(const float* __restrict__ w, long n, float* __restrict__ scale, float* __restrict__ inv) {
+  __shared__ float red[32];
+  float m = 0.f;
+  for (long i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(w[i]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    m = warp_max(m);
+    if (threadIdx.x == 0) {
+      int k = 0;
+      if (m > 0.f && isfinite(m)) {
+        int e;
+        frexpf(m, &e);          // m = f * 2^e, f in [0.5, 1)  ->  m * 2^(14 - e) in [2^13, 2^14)
+        k = 14 - e;
+        k = k > 60 ? 60 : (k < -60 ? -60 : k);
+      }
+      scale[0] = ldexpf(1.0f, k); inv[0] = ldexpf(1.0f, -k);
+    }
+  }
+}
 }  // namespace
 
-int split_f16(const float* src, __half* hi, __half* lo, long n, cudaStream_t st) {
+int split_f16(const float* src, __half* hi, __half* lo, long n, const float* scale, cudaStream_t st) {
   if (n == 0) return FS2_OK;
   long blocks = (n + 255) / 256;
-  split_f16_kernel<<<(int)(blocks > 1184 ? 1184 : blocks), 256, 0, st>>>(src, hi, lo, n);
+  split_f16_kernel<<<(int)(blocks > 1184 ? 1184 : blocks), 256, 0, st>>>(src, hi, lo, n, scale);
+  FS2_LAUNCH_CHECK();
+  return FS2_OK;
+}
+
+int weight_scale(const float* w, long n, float* scale, float* inv, cudaStream_t st) {
+  weight_scale_kernel<<<1, 1024, 0, st>>>(w, n, scale, inv);
   FS2_LAUNCH_CHECK();
   return FS2_OK;
 }

@@ -13,7 +13,7 @@ constexpr int ROWS_PER_CTA = 8;  // 8 warps
 template <int NV>  // float4 per lane
 __global__ void embed_posenc_kernel(const int64_t* __restrict__ xs, const float* __restrict__ table, int n_sym,
                                     const float* __restrict__ pe, const float* __restrict__ alpha, long rows, int T,
-                                    float* __restrict__ out) {
+                                    float* __restrict__ out, __half* __restrict__ planes) {
   const int C = NV * 128;
   long row = (long)blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -31,6 +31,12 @@ __global__ void embed_posenc_kernel(const int64_t* __restrict__ xs, const float*
     o.x = __fadd_rn(e.x, __fmul_rn(a, p.x)); o.y = __fadd_rn(e.y, __fmul_rn(a, p.y));
     o.z = __fadd_rn(e.z, __fmul_rn(a, p.z)); o.w = __fadd_rn(e.w, __fmul_rn(a, p.w));
     *reinterpret_cast<float4*>(out + row * C + c) = o;
+    if (planes) {   // operand planes of the first q|k|v projection (3xF16)
+      uint2 hv, lv;
+      split_pair(o.x, o.y, hv.x, lv.x); split_pair(o.z, o.w, hv.y, lv.y);
+      *reinterpret_cast<uint2*>(planes + row * C + c) = hv;
+      *reinterpret_cast<uint2*>(planes + (rows + row) * C + c) = lv;
+    }
   }
 }
 
@@ -86,24 +92,11 @@ __global__ void row_norm_kernel(RowNorm r) {
       dot += (y.x * w.x + y.y * w.y) + (y.z * w.z + y.w * w.w);
     }
     if (r.out) *reinterpret_cast<float4*>(r.out + row * r.ldo + c) = y;
-    if (r.split_out) {   // 3xF16 operand planes: hi = rn(y), lo = rn(y - hi), what split_rows_f16_kernel would write
-      const float f0 = fminf(fmaxf(y.x, -65504.f), 65504.f), f1 = fminf(fmaxf(y.y, -65504.f), 65504.f);
-      const float f2 = fminf(fmaxf(y.z, -65504.f), 65504.f), f3 = fminf(fmaxf(y.w, -65504.f), 65504.f);
-      const __half2 h01 = __floats2half2_rn(f0, f1), h23 = __floats2half2_rn(f2, f3);
-      const float2 g01 = __half22float2(h01), g23 = __half22float2(h23);
-      const __half2 l01 = __floats2half2_rn(f0 - g01.x, f1 - g01.y), l23 = __floats2half2_rn(f2 - g23.x, f3 - g23.y);
+    if (r.split_out) {   // operand planes of the next contraction: hi = rn(s y), lo = rn(s y - hi), 8-byte stores
       uint2 hv, lv;
-      hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
-      lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+      split_pair(y.x, y.y, hv.x, lv.x); split_pair(y.z, y.w, hv.y, lv.y);
       *reinterpret_cast<uint2*>(r.split_out + row * C + c) = hv;
-      *reinterpret_cast<uint2*>(r.split_out + (r.rows + row) * C + c) = lv;
-    }
-    if (r.out_h) {   // fp16 copy (A operand of the f16 conv-FFN), 8-byte store
-      const __half2 lo = __floats2half2_rn(fminf(fmaxf(y.x, -65504.f), 65504.f), fminf(fmaxf(y.y, -65504.f), 65504.f));
-      const __half2 hi = __floats2half2_rn(fminf(fmaxf(y.z, -65504.f), 65504.f), fminf(fmaxf(y.w, -65504.f), 65504.f));
-      uint2 u;
-      u.x = *reinterpret_cast<const uint32_t*>(&lo); u.y = *reinterpret_cast<const uint32_t*>(&hi);
-      *reinterpret_cast<uint2*>(r.out_h + row * r.ldo_h + c) = u;
+      if (r.split_lo) *reinterpret_cast<uint2*>(r.split_out + (r.rows + row) * C + c) = lv;
     }
   }
   if (r.head_w) {
@@ -150,6 +143,7 @@ __global__ void variance_embed_add_kernel(const float* __restrict__ hm, const fl
                                           const float* __restrict__ p_bins, int n_edges, const float* __restrict__ e_tab,
                                           const float* __restrict__ e_bias, const float* __restrict__ p_tab,
                                           const float* __restrict__ p_bias, int64_t rows, float* __restrict__ out,
+                                          __half* __restrict__ planes, int planes_lo,
                                           int64_t* __restrict__ e_ids, int64_t* __restrict__ p_ids) {
   const int C = NV * 128;
   int64_t row = (int64_t)blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5);
@@ -174,7 +168,13 @@ __global__ void variance_embed_add_kernel(const float* __restrict__ hm, const fl
     o.y = __fadd_rn(__fadd_rn(h.y, __fadd_rn(pw.y, pb.y)), __fadd_rn(ew.y, eb.y));
     o.z = __fadd_rn(__fadd_rn(h.z, __fadd_rn(pw.z, pb.z)), __fadd_rn(ew.z, eb.z));
     o.w = __fadd_rn(__fadd_rn(h.w, __fadd_rn(pw.w, pb.w)), __fadd_rn(ew.w, eb.w));
-    *reinterpret_cast<float4*>(out + row * C + c) = o;
+    if (out) *reinterpret_cast<float4*>(out + row * C + c) = o;
+    if (planes) {   // operand planes of the decoder input Linear
+      uint2 hv, lv;
+      split_pair(o.x, o.y, hv.x, lv.x); split_pair(o.z, o.w, hv.y, lv.y);
+      *reinterpret_cast<uint2*>(planes + row * C + c) = hv;
+      if (planes_lo) *reinterpret_cast<uint2*>(planes + (rows + row) * C + c) = lv;
+    }
   }
 }
 
@@ -277,37 +277,25 @@ inline int grid_for(long n, int block, int cap = 148 * 8) {
 }  // namespace
 
 int embed_posenc(const int64_t* xs, const float* table, int n_sym, const float* pe, const float* alpha, int B, int T,
-                 int C, float* out, cudaStream_t st) {
+                 int C, float* out, __half* planes, cudaStream_t st) {
   long rows = (long)B * T;
   if (rows == 0) return FS2_OK;
   int grid = (int)((rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
-  if (C == 256) embed_posenc_kernel<2><<<grid, 256, 0, st>>>(xs, table, n_sym, pe, alpha, rows, T, out);
-  else if (C == 384) embed_posenc_kernel<3><<<grid, 256, 0, st>>>(xs, table, n_sym, pe, alpha, rows, T, out);
+  if (C == 256) embed_posenc_kernel<2><<<grid, 256, 0, st>>>(xs, table, n_sym, pe, alpha, rows, T, out, planes);
+  else if (C == 384) embed_posenc_kernel<3><<<grid, 256, 0, st>>>(xs, table, n_sym, pe, alpha, rows, T, out, planes);
   else { set_error("embed_posenc: C=%d unsupported (256 or 384)", C); return FS2_ERR_INVALID; }
   FS2_LAUNCH_CHECK();
   return FS2_OK;
 }
 
-__global__ void to_half_kernel(const float* __restrict__ src, __half* __restrict__ dst, long n) {
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
-    dst[i] = __float2half_rn(fminf(fmaxf(src[i], -65504.f), 65504.f));
-}
-
 int row_norm(const RowNorm& r, cudaStream_t st) {
   if (r.rows == 0) return FS2_OK;
   FS2_REQUIRE(r.ldx % 4 == 0 && (!r.out || r.ldo % 4 == 0) && (!r.resid || r.ldr % 4 == 0), "row_norm: strides must be 16-byte multiples");
-  FS2_REQUIRE(!r.out_h || (r.ldo_h % 4 == 0 && (reinterpret_cast<uintptr_t>(r.out_h) & 7) == 0), "row_norm: fp16 output rows must be 8-byte aligned");
+  FS2_REQUIRE(!r.split_out || (reinterpret_cast<uintptr_t>(r.split_out) & 7) == 0, "row_norm: operand planes must be 8-byte aligned");
   int grid = (int)((r.rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
   if (r.C == 256) row_norm_kernel<2><<<grid, 256, 0, st>>>(r);
   else if (r.C == 384) row_norm_kernel<3><<<grid, 256, 0, st>>>(r);
   else { set_error("row_norm: C=%d unsupported (256 or 384)", r.C); return FS2_ERR_INVALID; }
-  FS2_LAUNCH_CHECK();
-  return FS2_OK;
-}
-
-int to_half(const float* src, __half* dst, long n, cudaStream_t st) {
-  if (n == 0) return FS2_OK;
-  to_half_kernel<<<grid_for(n, 256), 256, 0, st>>>(src, dst, n);
   FS2_LAUNCH_CHECK();
   return FS2_OK;
 }
@@ -329,15 +317,16 @@ int one_hot(const int64_t* ids, int64_t n, int n_bins, float* out, cudaStream_t 
 
 int variance_embed_add(const float* hm, const float* e_val, const float* p_val, const float* e_bins, const float* p_bins,
                        int n_edges, const float* e_tab, const float* e_bias, const float* p_tab, const float* p_bias,
-                       int64_t rows, int C, float* out, int64_t* e_ids, int64_t* p_ids, cudaStream_t st) {
+                       int64_t rows, int C, float* out, __half* planes, int planes_lo, int64_t* e_ids, int64_t* p_ids,
+                       cudaStream_t st) {
   if (rows == 0) return FS2_OK;
   int grid = (int)((rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
   if (C == 256)
     variance_embed_add_kernel<2><<<grid, 256, 0, st>>>(hm, e_val, p_val, e_bins, p_bins, n_edges, e_tab, e_bias, p_tab,
-                                                       p_bias, rows, out, e_ids, p_ids);
+                                                       p_bias, rows, out, planes, planes_lo, e_ids, p_ids);
   else if (C == 384)
     variance_embed_add_kernel<3><<<grid, 256, 0, st>>>(hm, e_val, p_val, e_bins, p_bins, n_edges, e_tab, e_bias, p_tab,
-                                                       p_bias, rows, out, e_ids, p_ids);
+                                                       p_bias, rows, out, planes, planes_lo, e_ids, p_ids);
   else { set_error("variance_embed_add: C=%d unsupported", C); return FS2_ERR_INVALID; }
   FS2_LAUNCH_CHECK();
   return FS2_OK;

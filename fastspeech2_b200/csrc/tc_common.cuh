@@ -118,6 +118,16 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// kind::f16 with the A operand in TMEM: fp16 elements packed two per 32-bit column (element k of a row in the low / high
+// half of column k / 2), so one K = 16 instruction covers 8 columns
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
@@ -172,6 +182,32 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
 // same with A = B = f16 ([7,10) = [10,13) = 0), for kind::f16
 __host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- host: per-device launch configuration ---------------------------------------------------------
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: remember which devices it has
+// been set on (a process may drive several GPUs, one handle each)
+template <typename K>
+inline int ensure_smem_attr(K kernel, size_t bytes, unsigned long long* done_mask) {
+  int dev = 0;
+  FS2_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev >= 64 || !((*done_mask >> dev) & 1ull)) {
+    FS2_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (dev < 64) *done_mask |= 1ull << dev;
+  }
+  return FS2_OK;
+}
+inline int sm_count_current() {
+  static int cached[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!cached[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
 }
 
 // ---- host: tensor maps ---------------------------------------------------------------------------

@@ -15,6 +15,11 @@ arithmetic happens in hand-written sm_100a kernels behind the C ABI (include/fs2
 There is no CPU path and no PyTorch fallback: CPU tensors, a missing library or train mode
 raise.  Train-mode forward/backward (dropout, BatchNorm batch statistics, autograd) is the
 next scope item and raises NotImplementedError today.
+
+Precision (`precision=` / FS2_PRECISION): "3xf16" (default; alias "3xtf32") is the reference-precision
+mode -- every contraction, attention included, error-compensated on the tensor cores, fp32-class
+results; "f16" and "tf32" are the 10-bit-mantissa fast modes for the decoder side; "fp32" is exact
+fp32 FMA on CUDA cores (include/fs2_b200.h, FS2_MATH_*).
 """
 from __future__ import annotations
 
@@ -29,7 +34,7 @@ from . import _lib
 from . import length_regulator as _lr
 from .weights import ModelDims, positional_table, variance_bins
 
-DEFAULT_PRECISION = os.environ.get("FS2_PRECISION", "f16")
+DEFAULT_PRECISION = os.environ.get("FS2_PRECISION", "3xf16")
 
 
 def _get(node: Any, key: str, default: Any = None) -> Any:
@@ -56,6 +61,10 @@ def dims_from_hp(idim: int, odim: int, hp: Any) -> ModelDims:
     need(bool(_get(m, "use_batch_norm", True)), "use_batch_norm=True only")
     need(int(_get(m, "reduction_factor", 1)) == 1, "reduction_factor=1 only")
     need(int(_get(m, "postnet_layers", 5)) >= 1, "postnet_layers >= 1")
+    # Energy/PitchPredictor ignore hp and are always VariancePredictor(idim) = 2 x 256 x k3
+    # (variance_predictor.py:125,198); the kernels share one predictor shape, so the duration predictor must match it
+    need((int(_get(m, "duration_predictor_layers")), int(_get(m, "duration_predictor_chans")), int(_get(m, "duration_predictor_kernel_size"))) == (2, 256, 3),
+         "duration_predictor_{layers,chans,kernel_size} must be (2, 256, 3), the fixed shape of the energy / pitch predictors")
     return ModelDims(
         idim=int(idim), odim=int(odim), adim=int(_get(m, "adim")),
         aheads=int(_get(m, "aheads")), elayers=int(_get(m, "elayers")), eunits=int(_get(m, "eunits")),
@@ -63,7 +72,7 @@ def dims_from_hp(idim: int, odim: int, hp: Any) -> ModelDims:
         ffn_kernel=int(_get(m, "positionwise_conv_kernel_size")),
         # DurationPredictor honours hp; Energy/PitchPredictor hard-code VariancePredictor(idim)
         # defaults 2 x 256 x k3 (variance_predictor.py:125,198).  One shape for all three is
-        # what default.yaml yields; anything else is rejected.
+        # what default.yaml yields; anything else was rejected above.
         pred_layers=int(_get(m, "duration_predictor_layers")), pred_chans=int(_get(m, "duration_predictor_chans")),
         pred_kernel=int(_get(m, "duration_predictor_kernel_size")),
         postnet_layers=int(_get(m, "postnet_layers")), postnet_chans=int(_get(m, "postnet_chans")),
@@ -251,6 +260,8 @@ class FeedForwardTransformer(nn.Module):
         self.encoder.embed[-1].alpha.data = torch.tensor(float(_get(m, "initial_encoder_alpha", 1.0)))
         self.decoder.embed[-1].alpha.data = torch.tensor(float(_get(m, "initial_decoder_alpha", 1.0)))
 
+        self._epoch = 0
+        self._sd_cache: Optional[list] = None
         self._handle: Optional[C.c_void_p] = None
         self._handle_device: Optional[torch.device] = None
         self._fingerprint: Optional[Tuple] = None
@@ -269,7 +280,38 @@ class FeedForwardTransformer(nn.Module):
         return self.feat_out.weight.device
 
     def _current_fingerprint(self) -> Tuple:
-        return tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
+        """(data_ptr, _version) of every checkpoint tensor plus the explicit epoch.  In-place writes through `.data`
+        (`p.data.copy_()`, EMA, the reference's own `initialize()`) do not bump `_version`: call `invalidate()` after
+        such an update (`load_state_dict` and `.to()` / `_apply` do it themselves)."""
+        if self._sd_cache is None:
+            self._sd_cache = list(self.state_dict(keep_vars=True).values())
+        return (self._epoch,) + tuple((t.data_ptr(), t._version) for t in self._sd_cache)
+
+    def invalidate(self) -> None:
+        """Force a repack of the checkpoint into the kernel layout on the next forward (after weight updates the
+        version counters cannot see).  Captured `GraphedForward` objects refuse to replay afterwards."""
+        self._epoch += 1
+        self._sd_cache = None
+
+    repack = invalidate
+
+    def load_state_dict(self, *a, **k):
+        out = super().load_state_dict(*a, **k)
+        self.invalidate()
+        return out
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self.invalidate()
+        return out
+
+    def _extend_pe(self, stack: "_FFTStack", n: int) -> None:
+        """core/embedding.py:48-66 `extend_pe`: regenerate a longer sinusoid table when the input outgrows it."""
+        pos = stack.embed[-1]
+        if pos.pe.shape[1] >= n:
+            return
+        pos.pe = positional_table(n, pos.pe.shape[2]).to(device=pos.pe.device, dtype=pos.pe.dtype)
+        self.invalidate()
 
     def _ready(self, like: torch.Tensor) -> C.c_void_p:
         """Handle with weights packed for the current parameters (repacks after load_state_dict,
@@ -335,6 +377,11 @@ class FeedForwardTransformer(nn.Module):
         if xs.dim() != 2:
             raise ValueError("xs must be [B, Tmax]")
         B, T = xs.shape
+        if T > self.encoder.embed[-1].pe.shape[1] or (es is not None and es.dim() == 2 and es.shape[1] > self.decoder.embed[-1].pe.shape[1]):
+            self._extend_pe(self.encoder, T)
+            if es is not None and es.dim() == 2:
+                self._extend_pe(self.decoder, int(es.shape[1]))
+            h = self._ready(xs)
         xs = xs.to(torch.int64).contiguous()
         ilens = ilens.to(device=dev, dtype=torch.int64).contiguous()
         f32 = dict(dtype=torch.float32, device=dev)
@@ -363,6 +410,9 @@ class FeedForwardTransformer(nn.Module):
             L = int(lmax)
             if L <= 0:
                 raise RuntimeError("inference produced zero frames")
+            if L > self.decoder.embed[-1].pe.shape[1]:
+                self._extend_pe(self.decoder, L)
+                h = self._ready(xs)
             olens_dec = None  # decoder unmasked, fastspeech.py:221-224
         else:
             L = L_known
@@ -454,37 +504,70 @@ class FeedForwardTransformer(nn.Module):
 class GraphedForward:
     """Teacher-forced `_forward` of one fixed shape replayed as a single CUDA graph.
 
-    The ~95 kernel launches of a step (each with its TMA descriptors baked into the launch parameters) are captured
-    once; a call copies the inputs into the graph's static buffers, replays, and returns the static output tensors
-    `(before, after, d_outs, e_outs, p_outs)` (valid until the next call).  `validate=True` (default) reads the same
-    four length words as the eager path afterwards and raises on the same conditions.  Weight updates require a
-    new capture (the packed-weight arena pointers are part of the graph)."""
+    The ~90 kernel launches of a step (each with its TMA descriptors baked into the launch parameters) are captured
+    once; a call copies the inputs into the graph's static buffers (`self.inputs`; callers may also fill those directly
+    and call `replay()`), replays, and returns the static output tensors `(before, after, d_outs, e_outs, p_outs)`
+    (valid until the next replay).
+
+    Validation of the length words (what the eager path reads back after every forward):
+      validate=True        read them now (one host sync per call) and raise like the eager path;
+      validate="deferred"  copy them to pinned host memory asynchronously; the check of replay i runs at the start of
+                           call i+1 (or in `flush()`), so replays queue back to back with no host bubble;
+      validate=False       no check.
+    The graph owns references to the workspace and static buffers it was captured with, so later eager calls that grow
+    the model's workspace cannot hand that memory to anyone else.  Weight updates require a new capture (the packed
+    weight arena is part of the graph): `__call__` raises if the model was repacked or its parameters changed."""
 
     def __init__(self, model: FeedForwardTransformer, xs, ilens, olens, ds, es, ps):
         self.model = model
         dev = xs.device
         self.inputs = [t.detach().clone().contiguous() for t in (xs, ilens.to(dev), olens.to(dev), ds, es, ps)]
-        self._fingerprint = None
         with torch.no_grad():
             for _ in range(2):                      # warm-up: packs weights, sizes the workspace, sets kernel attributes
                 model._forward(*self.inputs, is_inference=False)
             torch.cuda.synchronize(dev)
             self._fingerprint = model._current_fingerprint()
+            self._params = list(model._sd_cache)
+            self._versions = sum(t._version for t in self._params)
+            self._workspace = model._workspace      # keep the captured scratch alive for the life of the graph
             self.graph = torch.cuda.CUDAGraph()
             deferred: list = []
             with torch.cuda.graph(self.graph):
                 self.outputs = model._forward(*self.inputs, is_inference=False, _defer_check=deferred)
             self._chk, self._T, self._L = deferred[0]
+        self._chk_host = torch.empty(self._chk.shape, dtype=self._chk.dtype).pin_memory()
+        self._chk_event = torch.cuda.Event()
+        self._pending = False
 
-    def __call__(self, xs, ilens, olens, ds, es, ps, validate: bool = True):
-        if self.model._current_fingerprint() != self._fingerprint:
+    def _check_model(self) -> None:
+        m = self.model
+        if m._epoch != self._fingerprint[0] or sum(t._version for t in self._params) != self._versions:
             raise RuntimeError("model parameters changed since capture: build a new GraphedForward")
+
+    def flush(self) -> None:
+        """Run the outstanding deferred validation (waits for the replay it belongs to)."""
+        if self._pending:
+            self._pending = False
+            self._chk_event.synchronize()
+            FeedForwardTransformer._validate_lengths(self._chk_host.tolist(), self._T, self._L)
+
+    def replay(self, validate=True):
+        """Replay on the current contents of `self.inputs`."""
+        self._check_model()
+        self.flush()
+        self.graph.replay()
+        if validate == "deferred":
+            self._chk_host.copy_(self._chk, non_blocking=True)
+            self._chk_event.record()
+            self._pending = True
+        elif validate:
+            FeedForwardTransformer._validate_lengths(self._chk.tolist(), self._T, self._L)
+        return self.outputs
+
+    def __call__(self, xs, ilens, olens, ds, es, ps, validate=True):
         for dst, src in zip(self.inputs, (xs, ilens, olens, ds, es, ps)):
             if dst.shape != src.shape:
                 raise ValueError(f"captured for shape {tuple(dst.shape)}, got {tuple(src.shape)}")
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
-        self.graph.replay()
-        if validate:
-            FeedForwardTransformer._validate_lengths(self._chk.tolist(), self._T, self._L)
-        return self.outputs
+        return self.replay(validate)

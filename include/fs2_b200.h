@@ -43,19 +43,16 @@ extern "C" {
 #define FS2_DUR_F32 1
 #define FS2_DUR_I32 2
 
-/* arithmetic of the dense contractions.
+/* arithmetic of the dense contractions (accumulation is fp32 in TMEM / registers everywhere).
  *   FS2_MATH_FP32: fp32 FMA on CUDA cores everywhere.
- *   FS2_MATH_TF32: tcgen05 tensor-core tiles fed by TMA with fp32 (TMEM) accumulation:
- *     decoder side (decoder embed, decoder FFT blocks incl. attention, mel linear, Postnet) in
- *     plain kind::tf32; encoder GEMMs and the three predictors error-compensated (every operand split into fp16
- *     hi + lo, three kind::f16 products per term, fp32-class accuracy; "3xF16") because their outputs feed
- *     round() / bucketize().
- *   FS2_MATH_3XTF32: every dense contraction error-compensated on the tensor cores (decoder side too); attention cores on
- *     the exact-fp32 kernel.  ~1e-4-class results at about a third of the fp32 mode's run time.
- *   FS2_MATH_F16 (the Python class's default): FS2_MATH_TF32 with the decoder's q|k|v projection, conv-FFN (conv k=9
- *     -> ReLU -> conv k=1, two thirds of the model's flops), mel projection and Postnet on kind::f16: fp16 copies of
- *     the activations and weights (the same 10-bit mantissa as tf32, round-to-nearest instead of truncation, values
- *     clamped to +-65504), fp32 accumulation, twice the MMA rate.  Same stated tolerance as FS2_MATH_TF32.
+ *   FS2_MATH_3XTF32 ("3xf16", the reference-precision tensor-core mode and the Python class's default): every dense
+ *     contraction -- projections, convolutions AND both attention products -- error-compensated on tcgen05: each operand
+ *     is held as two fp16 planes hi = rn(s x), lo = rn(s x - hi) (s an exact power of two, undone in the epilogue), and
+ *     a product is accumulated as hi.hi + hi.lo + lo.hi.  fp32-class results (max-abs ~1e-5 on the mels).
+ *   FS2_MATH_F16: encoder + predictors as in FS2_MATH_3XTF32 (their outputs feed round() / bucketize()); the decoder
+ *     side (input Linear, q|k|v, attention, out-projection, conv-FFN, mel Linear, Postnet) on kind::f16 over the hi
+ *     planes only: 10-bit-mantissa operands (like tf32, round-to-nearest), twice the tf32 MMA rate.
+ *   FS2_MATH_TF32: encoder + predictors as above; decoder side on kind::tf32 reading the fp32 rows directly.
  * Normalisation, softmax statistics, gathers and every integer kernel are fp32 / exact in all modes. */
 #define FS2_MATH_FP32 0
 #define FS2_MATH_TF32 1
@@ -74,7 +71,7 @@ typedef struct fs2_config {
   int32_t pred_layers, pred_chans, pred_kernel; /* 2, 256, 3                              */
   int32_t postnet_layers, postnet_chans, postnet_filts; /* 5, 256, 5                      */
   int32_t n_bins;                   /* 256 pitch / energy buckets                         */
-  int32_t pe_len;                   /* rows of the positional table in the checkpoint     */
+  int32_t pe_len;                   /* informational: the positional tables' row counts are read off the tensors at load time */
   int32_t math_mode;                /* FS2_MATH_*                                         */
 } fs2_config;
 
@@ -173,16 +170,18 @@ int fs2_bucketize(const float* vals, const float* bins, int n_edges, int64_t n, 
 int fs2_one_hot(const int64_t* ids, int64_t n, int n_bins, float* out, void* stream);
 /* out[b,t,:] = act(sum_j x[b,t+j-pad,:] . W[j] + bias) (+ resid); W [taps][N][K].
  * math_mode selects the kernel family: FS2_MATH_FP32 (CUDA cores), FS2_MATH_TF32 (kind::tf32), FS2_MATH_3XTF32 (the
- * error-compensated tensor-core family every tensor-core mode uses for the encoder and the predictors) or
- * FS2_MATH_F16 (kind::f16 on fp16 copies of x and w made on the fly).
+ * error-compensated tensor-core family) or FS2_MATH_F16 (kind::f16); the last two run on fp16 operand planes of x and
+ * w made on the fly here (inside a stage the producing kernel writes them).
  * act: 0 none, 1 relu, 2 tanh */
 int fs2_op_tap_gemm(int math_mode, const float* x, int B, int L, int K, const float* w, const float* bias, int N, int taps,
                     int act, const float* resid, float* out, void* stream);
 /* out = LayerNorm_384(x . w^T + bias + resid) * gamma + beta in one tcgen05 kernel (x [rows,K], w [384,K]);
- * the fused form of core/encoder.py:60-62 / :67-69 used for the decoder blocks in FS2_MATH_TF32 */
-int fs2_op_gemm_layernorm(const float* x, int64_t rows, int K, const float* w, const float* bias, const float* resid,
-                          const float* gamma, const float* beta, float eps, float* out, void* stream);
-/* qkv [B,L,3C] (q | k | v, heads contiguous inside each) -> ctx [B,L,C]; lens NULL => no mask */
+ * the fused form of core/encoder.py:60-62 / :67-69 used for the decoder blocks in FS2_MATH_TF32 (kind::tf32 on the
+ * fp32 rows) and FS2_MATH_F16 (kind::f16 on operand planes made on the fly here) */
+int fs2_op_gemm_layernorm(int math_mode, const float* x, int64_t rows, int K, const float* w, const float* bias,
+                          const float* resid, const float* gamma, const float* beta, float eps, float* out, void* stream);
+/* qkv [B,L,3C] (q | k | v, heads contiguous inside each) -> ctx [B,L,C]; lens NULL => no mask.  FS2_MATH_FP32: CUDA cores;
+ * FS2_MATH_TF32: tcgen05 kind::tf32; FS2_MATH_F16 / FS2_MATH_3XTF32: tcgen05 kind::f16 / error-compensated 3xF16 on planes */
 int fs2_op_attention(int math_mode, const float* qkv, const int64_t* lens, int B, int L, int C, int heads, float* ctx,
                      void* stream);
 /* y = LayerNorm_C(x (+resid)) * g + b over the last dim (C in {256,384}) */

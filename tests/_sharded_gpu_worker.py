@@ -1,0 +1,67 @@
+"""Worker of tests/test_gpu_robustness.py::test_sharded_two_ranks_vs_per_shard_oracle (launched under torchrun, one rank
+per GPU, NCCL): every rank runs `synthesize_sharded` on the same global batch; rank 0 compares the gathered mels with the
+CPU oracle evaluated PER SHARD with the same partition (an utterance's result depends on the padded
+lengths of its shard)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def main():
+    from fastspeech2_b200 import FeedForwardTransformer, synthetic_state_dict
+    from fastspeech2_b200.hparams import load_hp
+    from fastspeech2_b200.sharded import gather_mels_to_root, shard_bounds, synthesize_sharded
+    from oracle import fs2_oracle as O
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    sd = synthetic_state_dict(7)
+    g = torch.Generator().manual_seed(123)
+    ilens = [41, 38, 30, 22, 17, 9, 5]                      # 7 utterances over 2 ranks: shards of 4 and 3, different Tmax
+    xs = torch.zeros(len(ilens), max(ilens), dtype=torch.int64)
+    for b, n in enumerate(ilens):
+        xs[b, :n] = torch.randint(1, 68, (n,), generator=g)
+    il = torch.tensor(ilens)
+    ok = True
+    for prec, tol in (("fp32", 1e-4), ("3xf16", 1e-4)):
+        m = FeedForwardTransformer(68, 80, load_hp(), precision=prec)
+        m.load_state_dict(sd, strict=True)
+        m = m.to(dev).eval()
+        mels, olens = synthesize_sharded(m, xs.to(dev), il.to(dev))
+        root = gather_mels_to_root(mels[shard_bounds(len(ilens), rank, world)[0]:shard_bounds(len(ilens), rank, world)[0] + 1].contiguous(), dst=0)
+        torch.cuda.synchronize()
+        if rank == 0:
+            assert root is not None and root.shape[0] == world
+            want_parts, want_lens = [], []
+            for r in range(world):
+                lo, hi = shard_bounds(len(ilens), r, world)
+                t = int(il[lo:hi].max())
+                with torch.no_grad():
+                    w = O.forward_path(sd, xs[lo:hi, :t], il[lo:hi], is_inference=True)
+                want_parts.append(w[1]); want_lens.append(w[2].sum(1))
+            Lmax = max(p.shape[1] for p in want_parts)
+            want = torch.cat([torch.nn.functional.pad(p, (0, 0, 0, Lmax - p.shape[1])) for p in want_parts], 0)
+            want_lens = torch.cat(want_lens)
+            assert torch.equal(olens.cpu(), want_lens), (prec, olens.cpu(), want_lens)
+            got = mels.cpu()
+            assert got.shape == want.shape, (got.shape, want.shape)
+            valid = torch.arange(Lmax)[None] < want_lens[:, None]
+            err = float((got - want).abs()[valid].max())
+            print(f"sharded[{prec}]: max-abs err vs per-shard oracle {err:.3e}", flush=True)
+            ok = ok and err <= tol
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        assert ok
+        print("SHARDED_OK", flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,13 +1,15 @@
 """Parity of the CUDA path (through the C ABI) against the golden vectors of the reference
 and against the CPU oracle on seeded inputs.  Needs a B200: run with `-m gpu`.
 
-Tolerances (stated, per SURVEY.md section 7 "fp32 tolerance vs tensor cores"):
+Tolerances (stated, per SURVEY.md section 7 "fp32 tolerance vs tensor cores"; gates sit at <= 2x the error
+observed on the B200, profiles/r02_parity_errors.md):
   FS2_MATH_FP32 : max-abs <= 1e-4 on mels (output rms ~0.6; the oracle's own fp32 noise floor
                   vs fp64 is 2.4e-6, long K=3456 fp32 reductions in a different order add ~1e-5)
-  FS2_MATH_TF32 : max-abs <= 1e-2, mean-abs <= 1e-3 on mels (tf32 operands: 10-bit mantissa)
-  FS2_MATH_3XTF32: max-abs <= 1e-3, mean-abs <= 1e-4 (operand rounding compensated; tensor-core accumulation rounds to zero)
-  FS2_MATH_F16  : as FS2_MATH_TF32 (the decoder conv-FFN reads fp16 copies: the same 10-bit mantissa, round-to-nearest)
-  integer outputs (durations, bucket ids, LengthRegulator rows): bit-exact in both modes.
+  FS2_MATH_3XTF32 ("3xf16", the default): max-abs <= 1e-4, mean-abs <= 1e-5 -- the reference-precision gate: every
+                  contraction incl. attention error-compensated; what remains is the tensor core's fp32 accumulation
+  FS2_MATH_TF32 : max-abs <= 1e-2, mean-abs <= 1e-3 on mels (tf32 operands: 10-bit mantissa, truncation)
+  FS2_MATH_F16  : max-abs <= 5e-3, mean-abs <= 5e-4 (decoder side on fp16 hi planes: 10-bit mantissa, round-to-nearest)
+  integer outputs (durations, bucket ids, LengthRegulator rows): bit-exact in every mode.
 """
 import numpy as np
 import pytest
@@ -20,10 +22,10 @@ from oracle import fs2_oracle as O
 
 pytestmark = pytest.mark.gpu
 T_ = torch.from_numpy
-TOL = {"fp32": dict(max=1e-4, mean=1e-5), "tf32": dict(max=1e-2, mean=1e-3), "3xtf32": dict(max=1e-3, mean=1e-4),
-       "f16": dict(max=1e-2, mean=1e-3)}
+TOL = {"fp32": dict(max=1e-4, mean=1e-5), "tf32": dict(max=1e-2, mean=1e-3), "3xtf32": dict(max=1e-4, mean=1e-5),
+       "f16": dict(max=5e-3, mean=5e-4)}
 PRECISIONS = ["fp32", "tf32", "3xtf32", "f16"]
-LOSS_REL = {"fp32": 1e-4, "tf32": 2e-3, "3xtf32": 3e-4, "f16": 2e-3}     # relative tolerance on the seven loss terms
+LOSS_REL = {"fp32": 1e-4, "tf32": 2e-3, "3xtf32": 1e-4, "f16": 2e-3}     # relative tolerance on the seven loss terms
 
 
 def close(got, want, tol, what=""):
@@ -305,8 +307,8 @@ def test_tap_gemm_f16_vs_torch(shape):
     close(got, ref(x, w), dict(max=1e-2, mean=1e-3), f"{shape} vs exact operands")
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32"])
-@pytest.mark.parametrize("C,L,masked", [(256, 100, True), (384, 333, True), (384, 800, False), (256, 37, False)])
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "3xtf32", "f16"])
+@pytest.mark.parametrize("C,L,masked", [(256, 100, True), (384, 333, True), (384, 800, False), (256, 37, False), (384, 129, True)])
 def test_attention_vs_torch(prec, C, L, masked):
     B, H = 3, 2
     g = torch.Generator().manual_seed(C + L)
@@ -326,12 +328,14 @@ def test_attention_vs_torch(prec, C, L, masked):
     qkv_c, lens_c = qkv.cuda(), lens.cuda()
     _lib.check(lib.fs2_op_attention(_lib.MATH_MODES[prec], _lib.ptr(qkv_c), _lib.ptr(lens_c) if masked else None, B, L, C, H,
                                     _lib.ptr(ctx), _lib.stream_ptr(ctx.device)), "fs2_op_attention")
-    tol = dict(max=2e-5, mean=2e-6) if prec == "fp32" else dict(max=1e-2, mean=1e-3)
+    # 3xtf32 = error-compensated tcgen05 attention (fp16 hi + lo planes for Q, K, V^T and P): fp32-class
+    tol = {"fp32": dict(max=2e-5, mean=2e-6), "3xtf32": dict(max=5e-5, mean=5e-6)}.get(prec, dict(max=1e-2, mean=1e-3))
     close(ctx, want, tol, f"attention C={C} L={L} masked={masked}")
 
 
+@pytest.mark.parametrize("prec", ["tf32", "f16"])
 @pytest.mark.parametrize("rows,K,with_resid", [(1000, 384, True), (51, 1024, True), (4097, 256, False)])
-def test_fused_gemm_layernorm_vs_torch(rows, K, with_resid):
+def test_fused_gemm_layernorm_vs_torch(prec, rows, K, with_resid):
     """tcgen05 GEMM with residual + LayerNorm fused into the epilogue (decoder out-projection / conv-FFN w_2)."""
     g = torch.Generator().manual_seed(rows + K)
     x = torch.randn(rows, K, generator=g); w = torch.randn(384, K, generator=g) / K ** 0.5; bias = torch.randn(384, generator=g)
@@ -341,7 +345,7 @@ def test_fused_gemm_layernorm_vs_torch(rows, K, with_resid):
     out = torch.empty(rows, 384, device="cuda")
     lib = _lib.load()
     xc, wc, bc, rc, gc, btc = x.cuda(), w.cuda(), bias.cuda(), resid.cuda(), gamma.cuda(), beta.cuda()
-    _lib.check(lib.fs2_op_gemm_layernorm(_lib.ptr(xc), rows, K, _lib.ptr(wc), _lib.ptr(bc), _lib.ptr(rc) if with_resid else None,
+    _lib.check(lib.fs2_op_gemm_layernorm(_lib.MATH_MODES[prec], _lib.ptr(xc), rows, K, _lib.ptr(wc), _lib.ptr(bc), _lib.ptr(rc) if with_resid else None,
                                          _lib.ptr(gc), _lib.ptr(btc), 1e-5, _lib.ptr(out), _lib.stream_ptr(out.device)), "fs2_op_gemm_layernorm")
     close(out, want, dict(max=1e-2, mean=1e-3), f"gemm+ln rows={rows} K={K}")
 
@@ -400,12 +404,21 @@ def test_inference_batch_matches_oracle_durations(models, weights):
             close(got[1], want[1], TOL[prec], f"after {prec}")
 
 
-def test_positional_table_limit_is_loud(models):
-    m = models["fp32"]
-    xs = torch.ones(1, 10, dtype=torch.int64).cuda(); il = torch.tensor([10]).cuda()
-    ds = torch.full((1, 10), 600, dtype=torch.int64).cuda()       # 6000 frames > 5000-row positional table
-    with pytest.raises(_lib.Fs2Error, match="positional table"):
-        m._forward(xs, il, torch.tensor([6000]).cuda(), ds, torch.zeros(1, 6000).cuda(), torch.zeros(1, 6000).cuda())
+def test_positional_table_extends_like_reference(weights):
+    """core/embedding.py:48-66: an input longer than the stored sinusoid table regenerates it.  5100 frames > the 5000
+    rows of the checkpoint; checked against the oracle (whose table is generated for the needed length too)."""
+    m = FeedForwardTransformer(68, 80, load_hp(), precision="fp32")
+    m.load_state_dict(weights, strict=True)
+    m = m.cuda().eval()
+    bt = make_batch(1, 10, 5100, seed=31)
+    sd = dict(weights)
+    from fastspeech2_b200.weights import positional_table
+    sd["decoder.embed.4.pe"] = positional_table(5100, 384)
+    with torch.no_grad():
+        want = O.forward_path(sd, bt["xs"], bt["ilens"], bt["olens"], bt["ds"].clone(), bt["es"], bt["ps"], False)
+        got = m._forward(*[bt[k].cuda() for k in ("xs", "ilens", "olens", "ds", "es", "ps")], is_inference=False)
+    assert m.decoder.embed[-1].pe.shape[1] == 5100 and m.encoder.embed[-1].pe.shape[1] == 5000
+    close(got[1], want[1], TOL["fp32"], "after, 5100 frames")
 
 
 def test_sharded_synthesis_single_rank(models, weights):

@@ -84,9 +84,9 @@ def test_from_reference_checkpoint(tmp_path, weights):
 
 
 def test_precision_names(model):
-    """The extra `precision` keyword: default from FS2_PRECISION else "f16"; unknown names are rejected; the header's
+    """The extra `precision` keyword: default from FS2_PRECISION else "3xf16" (the reference-precision mode); unknown names are rejected; the header's
     FS2_MATH_* values and the ctypes table agree."""
-    assert model.precision == os.environ.get("FS2_PRECISION", "f16")
+    assert model.precision == os.environ.get("FS2_PRECISION", "3xf16")
     with pytest.raises(ValueError):
         FeedForwardTransformer(68, 80, load_hp(), precision="bf16")
     hdr = open(os.path.join(REPO, "include", "fs2_b200.h")).read()
