@@ -53,47 +53,68 @@ def collate_tts(batch: Sequence[tuple]):
     return inputs, torch.tensor(il, dtype=torch.int64), mels, labels, torch.tensor(ol, dtype=torch.int64), ids, durations, energys, pitches
 
 
+class _Collated(tuple):
+    """The 9-tuple of `collate_tts` plus the pinned slot it lives in."""
+    slot = -1
+
+
 class PinnedCollator:
     """`collate_tts` into reusable pinned host buffers + asynchronous upload.
 
-    `collator(batch)` returns the 9-tuple with pinned CPU tensors (views of the buffers, valid until the next call);
-    `collator.to_device(tuple, device)` issues the H2D copies with `non_blocking=True` on the current stream.
+    `collator(batch)` returns the 9-tuple with pinned CPU tensors (views of one of `slots` buffer sets);
+    `collator.to_device(tuple, device)` issues the H2D copies with `non_blocking=True` on the current stream and records a
+    CUDA event for that slot.  Before a slot is refilled its event is waited for, so a loader that runs ahead of the GPU
+    can never overwrite host memory an earlier asynchronous copy is still reading (with `slots` batches in flight).
     """
 
-    def __init__(self, max_batch: int, max_T: int, max_L: int, n_mels: int = 80, pin: Optional[bool] = None):
+    def __init__(self, max_batch: int, max_T: int, max_L: int, n_mels: int = 80, pin: Optional[bool] = None, slots: int = 2):
         pin = torch.cuda.is_available() if pin is None else pin
         mk = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory() if pin else torch.zeros(shape, dtype=dt)
         self.cap = (max_batch, max_T, max_L)
-        self.inputs = mk((max_batch, max_T), torch.int64)
-        self.durations = mk((max_batch, max_T), torch.int64)
-        self.mels = mk((max_batch, max_L, n_mels), torch.float32)
-        self.labels = mk((max_batch, max_L), torch.float32)
-        self.energys = mk((max_batch, max_L), torch.float32)
-        self.pitches = mk((max_batch, max_L), torch.float32)
-        self.ilens = mk((max_batch,), torch.int64)
-        self.olens = mk((max_batch,), torch.int64)
+        self.n_mels = n_mels
+        self.slots = [dict(inputs=mk((max_batch, max_T), torch.int64), durations=mk((max_batch, max_T), torch.int64),
+                           mels=mk((max_batch, max_L, n_mels), torch.float32), labels=mk((max_batch, max_L), torch.float32),
+                           energys=mk((max_batch, max_L), torch.float32), pitches=mk((max_batch, max_L), torch.float32),
+                           ilens=mk((max_batch,), torch.int64), olens=mk((max_batch,), torch.int64), event=None)
+                      for _ in range(max(1, int(slots)))]
+        self._next = 0
 
     def __call__(self, batch: Sequence[tuple]):
         il, ol = _lens(batch)
         B, T, L = len(batch), max(il), max(ol)
         if B > self.cap[0] or T > self.cap[1] or L > self.cap[2]:
             raise ValueError(f"batch {B}x{T}x{L} exceeds the pinned capacity {self.cap}")
+        idx = self._next
+        self._next = (idx + 1) % len(self.slots)
+        s = self.slots[idx]
+        if s["event"] is not None:          # the upload that last read this slot must have finished
+            s["event"].synchronize()
+            s["event"] = None
         # dense [B, T] / [B, L] windows of the big buffers are not contiguous; stage into contiguous prefixes instead
-        n_mels = self.mels.shape[-1]
-        inputs = self.inputs.view(-1)[: B * T].view(B, T).zero_()
-        durations = self.durations.view(-1)[: B * T].view(B, T).zero_()
-        mels = self.mels.view(-1)[: B * L * n_mels].view(B, L, n_mels).zero_()
-        labels = self.labels.view(-1)[: B * L].view(B, L).zero_()
-        energys = self.energys.view(-1)[: B * L].view(B, L).zero_()
-        pitches = self.pitches.view(-1)[: B * L].view(B, L).zero_()
+        n_mels = self.n_mels
+        inputs = s["inputs"].view(-1)[: B * T].view(B, T).zero_()
+        durations = s["durations"].view(-1)[: B * T].view(B, T).zero_()
+        mels = s["mels"].view(-1)[: B * L * n_mels].view(B, L, n_mels).zero_()
+        labels = s["labels"].view(-1)[: B * L].view(B, L).zero_()
+        energys = s["energys"].view(-1)[: B * L].view(B, L).zero_()
+        pitches = s["pitches"].view(-1)[: B * L].view(B, L).zero_()
         _fill(batch, inputs, mels, durations, energys, pitches, labels)
-        ilens, olens = self.ilens[:B], self.olens[:B]
+        ilens, olens = s["ilens"][:B], s["olens"][:B]
         ilens.copy_(torch.tensor(il)); olens.copy_(torch.tensor(ol))
-        return inputs, ilens, mels, labels, olens, [it[2] for it in batch], durations, energys, pitches
+        out = _Collated((inputs, ilens, mels, labels, olens, [it[2] for it in batch], durations, energys, pitches))
+        out.slot = idx
+        return out
 
-    @staticmethod
-    def to_device(collated, device):
-        return tuple(t.to(device, non_blocking=True) if torch.is_tensor(t) else t for t in collated)
+    def to_device(self, collated, device):
+        """Asynchronous H2D of every tensor of `collated` on the current stream of `device`; remembers an event so the
+        slot is not refilled before the copies have run."""
+        out = tuple(t.to(device, non_blocking=True) if torch.is_tensor(t) else t for t in collated)
+        slot = getattr(collated, "slot", -1)
+        if slot >= 0 and torch.device(device).type == "cuda":
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(device))
+            self.slots[slot]["event"] = ev
+        return out
 
 
 class BucketBatchSampler:

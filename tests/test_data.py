@@ -25,16 +25,18 @@ def test_collate_matches_reference(golden):
 
 def test_pinned_collator_matches_and_reuses_buffers(golden):
     g = golden("collate")
-    pc = PinnedCollator(max_batch=8, max_T=20, max_L=64, pin=False)
+    pc = PinnedCollator(max_batch=8, max_T=20, max_L=64, pin=False, slots=2)
     out = pc(items_from(g))
     check(out, g)
     ptr = out[2].data_ptr()
-    out2 = pc(items_from(g)[:2])                     # smaller batch: same storage, stale tail must be zero
+    mid = pc(items_from(g))                          # second slot: a different buffer set (the first may still be uploading)
+    assert mid[2].data_ptr() != ptr and mid.slot != out.slot
+    out2 = pc(items_from(g)[:2])                     # round robin back to the first slot, smaller batch: stale tail must be zero
     assert out2[2].data_ptr() == ptr and out2[2].shape == (2, 50, 80)
     ref2 = collate_tts(items_from(g)[:2])
     for i in (0, 1, 2, 3, 4, 6, 7, 8):
         assert torch.equal(out2[i], ref2[i])
-    moved = PinnedCollator.to_device(out2, "cpu")
+    moved = pc.to_device(out2, "cpu")
     assert moved[5] == ["utt0", "utt1"] and torch.equal(moved[0], ref2[0])
 
 
