@@ -289,7 +289,7 @@ def run_b200(args):
     from fastspeech2_b200 import FeedForwardTransformer, _lib, synthetic_state_dict
     from fastspeech2_b200.hparams import load_hp
     from fastspeech2_b200.synthetic import make_batch
-    from fastspeech2_b200.sharded import gather_mels_to_root
+    from fastspeech2_b200.sharded import PeerGather, gather_mels_to_root
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -323,6 +323,9 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    peer = PeerGather((B, L, 80), dev) if (world > 1 and args.collective == "peer_copy") else None
+    step_no = [0]
+
     def timed(fn, steps, warmup):
         for i in range(warmup):
             fn(i)
@@ -331,6 +334,11 @@ def run_b200(args):
         e0.record()
         for i in range(steps):
             fn(i)
+        if peer is not None:      # the timed region ends when the last shard has landed on the root, not when it was enqueued
+            if rank == 0:
+                peer.wait(step_no[0])
+            elif peer.pushed is not None:
+                torch.cuda.current_stream(dev).wait_event(peer.pushed)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -347,20 +355,33 @@ def run_b200(args):
         graphs = [model.graphed_forward(*[devin[k] for k in keys]) for _ in range(2)] if args.graph else None
         copied = [torch.cuda.Event(), torch.cuda.Event()]
 
-        def collective(mel):
-            if world > 1:   # the single exchange step: gather the final mel batch over NVLink
-                if args.collective == "gather":     # rank 0 receives everything, the others only send their shard
-                    gather_mels_to_root(mel, dst=0, out=gathered if rank == 0 else None)
-                else:
-                    dist.all_gather_into_tensor(gathered, mel)
+        pushed = [None, None]
+
+        def collective(mel, i):
+            if world == 1:
+                return
+            # the single exchange step: gather the final mel batch over NVLink
+            if peer is not None:                # copy-engine push into the root's buffer on a side stream (csrc/peer.cu)
+                step_no[0] += 1
+                peer.push(mel, step_no[0])
+                pushed[i & 1] = peer.pushed     # this graph's output buffer is busy until the transfer has read it
+            elif args.collective == "gather":   # NCCL: rank 0 receives everything, the others only send their shard
+                gather_mels_to_root(mel, dst=0, out=gathered if rank == 0 else None)
+            else:                               # NCCL all-gather: every rank receives every shard
+                dist.all_gather_into_tensor(gathered, mel)
+
+        def source_free(i):
+            if pushed[i & 1] is not None:
+                torch.cuda.current_stream(dev).wait_event(pushed[i & 1])
 
         def step(i):
             with torch.no_grad():
                 if graphs is not None:
+                    source_free(i)
                     out = graphs[i & 1].replay(validate="deferred")    # inputs already sit in the graph's static buffers
                 else:
                     out = model._forward(*[devin[k] for k in keys], is_inference=False)
-            collective(out[1])
+            collective(out[1], i)
             return out[1]
 
         def step_e2e(i):
@@ -368,6 +389,7 @@ def run_b200(args):
             with torch.no_grad():
                 if graphs is not None:
                     g = graphs[i & 1]
+                    source_free(i)
                     cur.wait_event(copied[i & 1])                       # its previous output has left for the host
                     for dst, k in zip(g.inputs, keys):
                         dst.copy_(host[k], non_blocking=True)           # H2D straight into the graph's static inputs
@@ -375,7 +397,7 @@ def run_b200(args):
                 else:
                     inp = [host[k].to(dev, non_blocking=True) for k in keys]
                     out = model._forward(*inp, is_inference=False)
-            collective(out[1])
+            collective(out[1], i)
             done = torch.cuda.Event()
             done.record(cur)
             with torch.cuda.stream(copy_stream):
@@ -483,6 +505,8 @@ def run_b200(args):
             del m2, st2, st2_e2e, fl2
             torch.cuda.empty_cache()
 
+    if peer is not None:
+        peer.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -527,7 +551,9 @@ def run_b200(args):
                                  "f16": "decoder side on kind::f16 (10-bit mantissa operands), encoder + predictors error-compensated",
                                  "tf32": "decoder side on kind::tf32, encoder + predictors error-compensated",
                                  "fp32": "fp32 FMA on CUDA cores"}[args.precision],
-                   "collective": (f"one NCCL {args.collective} of the [B,L,80] mel shard" if world > 1 else "none"),
+                   "collective": ({"peer_copy": "gather to rank 0 over NVLink peer memory: one copy-engine transfer of the [B,L,80] shard per rank on a side stream + flag words (csrc/peer.cu), no SM-occupying collective kernel",
+                                   "gather": "one NCCL gather of the [B,L,80] mel shard to rank 0",
+                                   "all_gather": "one NCCL all-gather of the [B,L,80] mel shard"}[args.collective] if world > 1 else "none"),
                    "l2": "per-step working set ~0.9 GB of activations >> 126 MB L2; no flush needed",
                    "tolerance": "3xf16 (default): max-abs 1e-4, mean-abs 1e-5 vs the CPU fp32 oracle on the mels, durations / bucket ids bit-exact; "
                                 "fp32: 1e-4; f16: 5e-3 / 5e-4; tf32: 1e-2 / 1e-3 (tests/test_gpu_parity.py)"},
@@ -569,8 +595,8 @@ def main():
     ap.add_argument("--modes", default="f16,tf32", help="N=1: other precision modes measured beside the headline ('' = none)")
     ap.add_argument("--cpu-sample-batch", type=int, default=64, help="utterances per CPU-reference step (64 = the full c2 batch)")
     ap.add_argument("--cpu-threads", type=int, default=32, help="host threads of the CPU reference (fixed; oversubscription is slower)")
-    ap.add_argument("--collective", default="all_gather", choices=["all_gather", "gather"],
-                    help="N>1: all ranks receive all mels (default, measured) or only rank 0 does (gather to root)")
+    ap.add_argument("--collective", default="peer_copy", choices=["peer_copy", "all_gather", "gather"],
+                    help="N>1: gather to rank 0 by copy-engine pushes over NVLink peer memory (default), or NCCL gather / all_gather")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (default), 0: eager launches")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -58,6 +58,13 @@ SIGNATURES = {
     "fs2_op_attention": [_I, _P, _P, _I, _I, _I, _I, _P, _P],
     "fs2_op_gemm_layernorm": [_I, _P, _L, _I, _P, _P, _P, _P, _P, _F, _P, _P],
     "fs2_op_layernorm": [_P, _P, _P, _P, _F, _L, _I, _P, _P],
+    "fs2_peer_alloc": [_SZ, C.POINTER(_P), _P],
+    "fs2_peer_free": [_P],
+    "fs2_peer_open": [_P, C.POINTER(_P)],
+    "fs2_peer_close": [_P],
+    "fs2_peer_copy": [_P, _P, _SZ, _P],
+    "fs2_flag_signal": [_P, _L, _P],
+    "fs2_flag_wait": [_P, _I, _I, _L, _P],
 }
 OTHER_SYMBOLS = ("fs2_last_error", "fs2_version", "fs2_destroy", "fs2_kernel_launches", "fs2_profile_label")
 ALL_SYMBOLS = tuple(SIGNATURES) + OTHER_SYMBOLS

@@ -78,6 +78,107 @@ def gather_mels_to_root(mel: torch.Tensor, dst: int = 0, group: Optional[dist.Pr
     return None
 
 
+class _RawCudaBuffer:
+    """Zero-copy tensor view of a raw device pointer (local cudaMalloc or a peer's IPC mapping)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class PeerGather:
+    """Gather-to-root of equal-shape `[B, L, odim]` mel shards over NVLink peer memory (csrc/peer.cu): one copy-engine
+    transfer per rank and step on a side stream, flag words for completion, no NCCL kernel on the SMs.
+
+        pg = PeerGather((B, L, odim), device)            # collective: every rank of the group calls it once
+        pg.push(mel, step)                               # every rank, after its step's mel is complete on the current stream
+        pg.wait(step)                                    # root: later work on the current stream sees all shards of `step`
+        pg.gathered                                      # root: [world*B, L, odim] view of the receive buffer
+
+    `push` returns immediately (the transfer runs on `pg.stream`); the source tensor must stay untouched until
+    `pg.pushed` (an event recorded after the transfer) has completed.  With a non-CUDA tensor (gloo host-logic tests) the
+    class degrades to `gather_mels_to_root`."""
+
+    HEADER = 256          # bytes reserved for the flag words in front of the shards
+
+    def __init__(self, shard_shape, device, dtype=torch.float32, root: int = 0, group: Optional[dist.ProcessGroup] = None):
+        self.group, self.root = group, root
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.shape = tuple(int(v) for v in shard_shape)
+        self.device = torch.device(device)
+        self.gathered = None
+        self.pushed = None
+        self._cuda = self.device.type == "cuda"
+        if not self._cuda or self.world == 1:
+            return
+        import ctypes as C
+        from . import _lib
+        self._lib = _lib.load()
+        n = 1
+        for v in self.shape:
+            n *= v
+        self.shard_bytes = n * torch.empty((), dtype=dtype).element_size()
+        total = self.HEADER + self.world * self.shard_bytes
+        assert self.world * 8 <= self.HEADER
+        handle = (C.c_char * 64)()
+        ptr = C.c_void_p()
+        with torch.cuda.device(self.device):
+            if self.rank == root:
+                _lib.check(self._lib.fs2_peer_alloc(total, C.byref(ptr), handle), "fs2_peer_alloc")
+            obj = [bytes(handle) if self.rank == root else None]
+            dist.broadcast_object_list(obj, src=root, group=group, device=self.device)
+            if self.rank != root:
+                _lib.check(self._lib.fs2_peer_open(C.create_string_buffer(obj[0], 64), C.byref(ptr)), "fs2_peer_open")
+        self._base = int(ptr.value)
+        self._flags = self._base
+        self._data = self._base + self.HEADER
+        self.stream = torch.cuda.Stream(self.device)
+        if self.rank == root:
+            raw = torch.as_tensor(_RawCudaBuffer(self._data, self.world * self.shard_bytes), device=self.device)
+            self.gathered = raw.view(dtype).view((self.world * self.shape[0],) + self.shape[1:])
+        dist.barrier(group=group)
+
+    def push(self, mel: torch.Tensor, step: int) -> None:
+        if not self._cuda or self.world == 1:
+            out = gather_mels_to_root(mel, dst=self.root, group=self.group)
+            if self.rank == self.root:
+                self.gathered = out
+            return
+        from . import _lib
+        cur = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        self.stream.wait_event(ready)
+        st = self.stream.cuda_stream
+        dst = self._data + self.rank * self.shard_bytes
+        _lib.check(self._lib.fs2_peer_copy(dst, mel.data_ptr(), self.shard_bytes, st), "fs2_peer_copy")
+        if self.rank != self.root:
+            _lib.check(self._lib.fs2_flag_signal(self._flags + 8 * self.rank, int(step), st), "fs2_flag_signal")
+        self.pushed = torch.cuda.Event()
+        self.pushed.record(self.stream)
+
+    def wait(self, step: int) -> None:
+        """Root: order the current stream after the arrival of every rank's shard of `step` (and its own local copy)."""
+        if not self._cuda or self.world == 1 or self.rank != self.root:
+            return
+        from . import _lib
+        cur = torch.cuda.current_stream(self.device)
+        if self.pushed is not None:
+            cur.wait_event(self.pushed)
+        _lib.check(self._lib.fs2_flag_wait(self._flags, self.world, self.root, int(step), cur.cuda_stream), "fs2_flag_wait")
+
+    def close(self) -> None:
+        if not self._cuda or self.world == 1 or self._base == 0:
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        if self.rank == self.root:
+            self.gathered = None
+            self._lib.fs2_peer_free(self._base)
+        else:
+            self._lib.fs2_peer_close(self._base)
+        self._base = 0
+
+
 def synthesize_sharded(model, xs: torch.Tensor, ilens: torch.Tensor, group: Optional[dist.ProcessGroup] = None):
     """Batched `is_inference=True` synthesis of a global batch: every rank passes the same global
     `xs [B,T]` / `ilens [B]`, runs its shard and receives all mels.  Returns (mels, olens)."""

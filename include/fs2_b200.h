@@ -188,6 +188,25 @@ int fs2_op_attention(int math_mode, const float* qkv, const int64_t* lens, int B
 int fs2_op_layernorm(const float* x, const float* resid, const float* g, const float* b, float eps, int64_t rows, int C,
                      float* out, void* stream);
 
+/* ---- multi-GPU exchange step: gather of the final mel shards on one rank over NVLink peer memory ----------------- */
+/* Replaces what a reference user would write as torch.distributed.gather / all_gather of `after_outs` (the reference has
+ * no multi-GPU path; SURVEY.md section 8e defines the step).  The root rank owns one receive buffer and exports it with
+ * CUDA IPC; the other ranks map it and push their shard with a copy-engine transfer followed by a release-store of the
+ * step number into a flag word; the root waits on the flags with a one-warp acquire-spin kernel.  No collective kernel
+ * occupies SMs and nothing is sent to ranks that do not need it.  fastspeech2_b200/sharded.py::PeerGather drives these.
+ *   fs2_peer_alloc  cudaMalloc + zero `bytes` on the current device, IPC handle (64 bytes) out
+ *   fs2_peer_open   map a peer's allocation into this process (enables peer access lazily); fs2_peer_close unmaps
+ *   fs2_peer_copy   asynchronous device-to-(peer-)device copy on `stream`
+ *   fs2_flag_signal one-thread kernel: system-scope fence, *flag = value
+ *   fs2_flag_wait   one-warp kernel: spin until flags[r] >= value for all r < n, r != skip (bounded: traps after ~10 s) */
+int fs2_peer_alloc(size_t bytes, void** ptr, void* handle64);
+int fs2_peer_free(void* ptr);
+int fs2_peer_open(const void* handle64, void** ptr);
+int fs2_peer_close(void* ptr);
+int fs2_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
+int fs2_flag_signal(int64_t* flag, int64_t value, void* stream);
+int fs2_flag_wait(const int64_t* flags, int n, int skip, int64_t value, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
