@@ -26,6 +26,7 @@
 // S_{j+1} while the softmax warps work on tile j, plus DK columns of O.  Shared memory: Q resident (P x DK/64 boxes of
 // 16 KB) + a ring of K / V^T boxes (one 128-byte swizzle row = 64 fp16 wide).
 #include <math.h>
+#include <stdlib.h>
 
 #include "tc_common.cuh"
 
@@ -349,6 +350,265 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// F16, two query tiles in flight per CTA (FS2_MATH_F16's decoder): the single-tile kernel above leaves the tensor pipe idle
+// while a tile's softmax runs (S -> exp2 -> P -> P.V is one dependency chain per tile; profiles/r01_ncu_attn_tf32_v18.md:
+// tensor pipe 33 % active).  Here a CTA owns TWO 128-query tiles A and B of the same (batch, head), each with its own S/P
+// buffer, O accumulator and softmax warpgroup, sharing one K / V^T stream (half the L2 traffic per query): the MMA warp
+// alternates   P.V_A(j), S_A(j+1) | P.V_B(j), S_B(j+1)   so one tile's MMAs run under the other tile's softmax.
+//   keys per step: 64 -> S tile 128 x 64 fp32 = 64 TMEM columns; TMEM = S_A | S_B | O_A | O_B = 64 + 64 + 2 DK <= 512
+//   one softmax thread owns a whole 64-score row: no cross-thread exchange, no block barrier in the loop
+//   shared memory: Q_A, Q_B resident (2 x DK/64 x 16 KB) + a ring of 64-key K boxes / V^T boxes (DK x 128 B each)
+constexpr int BKV2 = 64;
+constexpr int ATT2_THREADS = 320;   // TMA, MMA, 4 softmax warps per tile
+
+template <int DK>
+struct H2Cfg {
+  static constexpr int QCH = DK / CH;
+  static constexpr int Q_BOX = BQ * 128;                 // 16 KB: 128 query rows x 64 dk
+  static constexpr int Q_TILE = QCH * Q_BOX;
+  static constexpr int Q_BYTES = 2 * Q_TILE;
+  static constexpr int K_CHUNK = BKV2 * 128;             // 8 KB: 64 keys x 64 dk
+  static constexpr int SLOT = DK * 128;                  // K step = QCH chunks = DK * 128 B; V^T step = DK rows x 64 keys: same size
+  static constexpr int SLOTS_MAX = (222 * 1024 - Q_BYTES) / SLOT;
+  static constexpr int SLOTS = SLOTS_MAX > 8 ? 8 : SLOTS_MAX;
+  static constexpr size_t SMEM = (size_t)Q_BYTES + (size_t)SLOTS * SLOT + 1024 + 512;
+  static constexpr uint32_t IDESC_S = idesc_f16(BQ, BKV2);
+  static constexpr uint32_t IDESC_O = idesc_f16(BQ, DK);
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int S_COL(int x) { return x * BKV2; }
+  static constexpr int O_COL(int x) { return 2 * BKV2 + x * DK; }
+  static_assert(DK % 64 == 0 && 2 * BKV2 + 2 * DK <= 512, "TMEM budget");
+  static_assert(QCH * K_CHUNK == SLOT && SLOT % 1024 == 0 && SLOTS >= 4, "ring");
+};
+
+template <int DK>
+__global__ void __launch_bounds__(ATT2_THREADS, 1)
+attention_f16x2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                       const __grid_constant__ CUtensorMap tmap_vt, HParams p) {
+  using A = H2Cfg<DK>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* q_smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* ring = q_smem + A::Q_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)A::SLOTS * A::SLOT);
+  uint64_t* full_bar = bars;                   // [SLOTS]
+  uint64_t* empty_bar = bars + A::SLOTS;       // [SLOTS]
+  uint64_t* q_bar = bars + 2 * A::SLOTS;
+  uint64_t* s_full = q_bar + 1;                // [2] MMA -> softmax X: S tile ready
+  uint64_t* p_full = s_full + 2;               // [2] softmax X -> MMA: P written
+  uint64_t* pv_done = p_full + 2;              // [2] MMA -> softmax X: P.V of the previous step has finished (O may be rescaled)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 2 * BQ, h = blockIdx.y, b = blockIdx.z;
+  const int len = p.lens ? (int)min((long)p.lens[b], (long)p.L) : p.L;
+  const int J = (len + BKV2 - 1) / BKV2;
+  const bool has_b = q0 + BQ < p.L;            // the second tile exists (CTA-uniform)
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < A::SLOTS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(q_bar, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, A::TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (J > 0) {
+    if (warp == 0) {
+      if (lane == 0) {  // ---- TMA producer: both Q tiles once, then K_0, V_0, K_1, V_1, ... ----
+        mbar_expect_tx(q_bar, has_b ? A::Q_BYTES : A::Q_TILE);
+        for (int x = 0; x < (has_b ? 2 : 1); ++x)
+          for (int c = 0; c < A::QCH; ++c)
+            tma_load_3d(q_smem + (size_t)x * A::Q_TILE + (size_t)c * A::Q_BOX, &tmap_q, q_bar, h * DK + c * CH, q0 + x * BQ, b);
+        for (int n = 0; n < 2 * J; ++n) {
+          const int slot = n % A::SLOTS, j = n >> 1;
+          mbar_wait(&empty_bar[slot], ((n / A::SLOTS) & 1) ^ 1);
+          mbar_expect_tx(&full_bar[slot], A::SLOT);
+          uint8_t* dst = ring + (size_t)slot * A::SLOT;
+          if (n & 1) {
+            tma_load_3d(dst, &tmap_vt, &full_bar[slot], j * BKV2, 0, b * p.heads + h);
+          } else {
+            for (int c = 0; c < A::QCH; ++c)
+              tma_load_3d(dst + (size_t)c * A::K_CHUNK, &tmap_k, &full_bar[slot], p.C + h * DK + c * CH, j * BKV2, b);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      {  // ---- MMA issuer (warp-uniform loop, one lane elected inside each tcgen05 asm) ----
+        mbar_wait(q_bar, 0);
+        tcgen05_fence_after();
+        const uint32_t q_addr = smem_u32(q_smem);
+        auto slot_ready = [&](int n) -> uint32_t {
+          const int slot = n % A::SLOTS;
+          mbar_wait(&full_bar[slot], (n / A::SLOTS) & 1);
+          tcgen05_fence_after();
+          return smem_u32(ring + (size_t)slot * A::SLOT);
+        };
+        auto issue_s = [&](int x, int j) {      // S_x(j) = Q_x K_j^T -> S/P buffer x
+          const uint32_t kbase = slot_ready(2 * j);
+          const uint32_t d = tmem_base + (uint32_t)A::S_COL(x);
+#pragma unroll
+          for (int c = 0; c < A::QCH; ++c) {
+            const uint64_t qd = make_sw128_kmajor_desc(q_addr + x * A::Q_TILE + c * A::Q_BOX);
+            const uint64_t kd = make_sw128_kmajor_desc(kbase + c * A::K_CHUNK);
+#pragma unroll
+            for (int k = 0; k < CH / 16; ++k) umma_f16(d, qd + 2 * k, kd + 2 * k, A::IDESC_S, (c | k) != 0);
+          }
+          if (x == 1 || !has_b) tcgen05_commit(&empty_bar[(2 * j) % A::SLOTS]);   // last reader of K_j
+          tcgen05_commit(&s_full[x]);
+        };
+        auto issue_pv = [&](int x, int j) {     // O_x += P_x(j) V_j
+          mbar_wait(&p_full[x], j & 1);
+          tcgen05_fence_after();
+          const uint64_t vd = make_sw128_kmajor_desc(slot_ready(2 * j + 1));
+          const uint32_t pa = tmem_base + (uint32_t)A::S_COL(x), o = tmem_base + (uint32_t)A::O_COL(x);
+#pragma unroll
+          for (int k = 0; k < BKV2 / 16; ++k) umma_f16_ts(o, pa + k * 8, vd + 2 * k, A::IDESC_O, (j | k) != 0);
+          if (x == 1 || !has_b) tcgen05_commit(&empty_bar[(2 * j + 1) % A::SLOTS]);   // last reader of V_j
+          tcgen05_commit(&pv_done[x]);
+        };
+        issue_s(0, 0);
+        if (has_b) issue_s(1, 0);
+        for (int j = 0; j < J; ++j) {
+          issue_pv(0, j);
+          if (j + 1 < J) issue_s(0, j + 1);
+          if (has_b) {
+            issue_pv(1, j);
+            if (j + 1 < J) issue_s(1, j + 1);
+          }
+        }
+      }
+    } else {
+      // ---- softmax / epilogue: warps 2-5 = tile A, 6-9 = tile B; thread == query row == TMEM lane ----
+      const int x = (warp - 2) >> 2, wq = warp & 3;
+      if (x == 0 || has_b) {
+        const int row = wq * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(wq * 32) << 16);
+        const uint32_t s_addr = lane_addr + (uint32_t)A::S_COL(x), o_addr = lane_addr + (uint32_t)A::O_COL(x);
+        float v[64];
+        float m_ref = -INFINITY, l_row = 0.f;
+        const float c_exp = p.scale_log2e;
+        for (int j = 0; j < J; ++j) {
+          mbar_wait(&s_full[x], j & 1);
+          tcgen05_fence_after();
+          const int kv0 = j * BKV2;
+          const bool masked = kv0 + BKV2 > len;
+          __syncwarp();
+          tmem_ld32_nowait(s_addr, v); tmem_ld32_nowait(s_addr + 32, v + 32); tmem_ld_wait_pin<64>(v);
+          float t0 = -INFINITY, t1 = -INFINITY, t2 = -INFINITY, t3 = -INFINITY;     // four chains: the serial max is latency
+          if (masked) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) if (kv0 + i < len) t0 = fmaxf(t0, v[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { t0 = fmaxf(t0, v[i]); t1 = fmaxf(t1, v[16 + i]); t2 = fmaxf(t2, v[32 + i]); t3 = fmaxf(t3, v[48 + i]); }
+          }
+          const float tmax = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
+          const bool bump = (tmax - m_ref) * c_exp > 8.0f;
+          if (__any_sync(0xffffffffu, bump)) {
+            const float alpha = bump ? fast_exp2((m_ref - tmax) * c_exp) : 1.0f;
+            if (j > 0) {
+              mbar_wait(&pv_done[x], (j - 1) & 1);
+              tcgen05_fence_after();
+              float o[32];
+#pragma unroll 1
+              for (int c0 = 0; c0 < DK; c0 += 32) {
+                __syncwarp();
+                tmem_ld32(o_addr + c0, o);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] *= alpha;
+                tmem_st32(o_addr + c0, o);
+              }
+              tmem_st_wait();
+            }
+            l_row *= alpha;
+            if (bump) m_ref = tmax;
+          }
+          const float mb = m_ref * c_exp;
+          uint32_t ph[32], pl_unused[1];
+          l_row += masked ? softmax_tile<false, true>(v, c_exp, mb, kv0, len, ph, pl_unused) : softmax_tile<false, false>(v, c_exp, mb, kv0, len, ph, pl_unused);
+          __syncwarp();
+          tmem_st32u(s_addr, ph);                                   // P (packed fp16) over the first 32 columns of the S tile
+          tmem_st_wait();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[x]);
+        }
+        // epilogue: O / l -> hi plane of the context (and / or fp32 rows)
+        mbar_wait(&pv_done[x], (J - 1) & 1);
+        tcgen05_fence_after();
+        const int t = q0 + x * BQ + row;
+        const bool store = t < p.L;
+        const float inv = (p.lens && t >= len) ? 0.f : 1.0f / l_row;
+        const long o_off = ((long)b * p.L + t) * p.C + h * DK;
+#pragma unroll 1
+        for (int c0 = 0; c0 < DK; c0 += 32) {
+          __syncwarp();
+          tmem_ld32(o_addr + c0, v);
+          if (!store) continue;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= inv;
+          if (p.ctxp != nullptr) {
+            uint32_t hh[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const __half2 hv = __floats2half2_rn(fminf(fmaxf(v[2 * i], -65504.f), 65504.f), fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f));
+              hh[i] = *reinterpret_cast<const uint32_t*>(&hv);
+            }
+            st_global_v8_b32(p.ctxp + o_off + c0, hh); st_global_v8_b32(p.ctxp + o_off + c0 + 16, hh + 8);
+          }
+          if (p.ctx != nullptr) {
+            float* dst = p.ctx + o_off + c0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(dst + q * 4) = make_float4(v[q * 4] * kPlaneInv, v[q * 4 + 1] * kPlaneInv, v[q * 4 + 2] * kPlaneInv, v[q * 4 + 3] * kPlaneInv);
+          }
+        }
+      }
+    }
+  } else if (warp >= 2) {
+    // no valid key at all (len == 0): the reference's masked_fill turns the NaN rows into 0
+    const int x = (warp - 2) >> 2;
+    const int t = q0 + x * BQ + (warp & 3) * 32 + lane;
+    if (t < p.L) {
+      const long o_off = ((long)b * p.L + t) * p.C + h * DK;
+      if (p.ctx) for (int c = 0; c < DK; c += 4) *reinterpret_cast<float4*>(p.ctx + o_off + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.ctxp) for (int c = 0; c < DK; c += 8) *reinterpret_cast<uint4*>(p.ctxp + o_off + c) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, A::TMEM_COLS);
+  }
+}
+
+template <int DK>
+int launch_x2(const __half* qkp, const __half* vtp, int lpad, const int64_t* lens, int B, int L, int C, int heads, float* ctx,
+              __half* ctxp, cudaStream_t st) {
+  using A = H2Cfg<DK>;
+  static unsigned long long configured = 0;   // per-device bit mask
+  int rc;
+  if ((rc = ensure_smem_attr(attention_f16x2_kernel<DK>, A::SMEM, &configured))) return rc;
+  CUtensorMap mq, mk, mvt;
+  const uint64_t row = (uint64_t)2 * C * 2;
+  if ((rc = make_map(&mq, qkp, (uint64_t)2 * C, L, B, row, row * L, BQ, true))) return rc;
+  if ((rc = make_map(&mk, qkp, (uint64_t)2 * C, L, B, row, row * L, BKV2, true))) return rc;
+  if ((rc = make_map(&mvt, vtp, L, DK, (uint64_t)B * heads, (uint64_t)lpad * 2, (uint64_t)lpad * 2 * DK, DK, true))) return rc;
+  HParams p;
+  p.lens = lens; p.B = B; p.L = L; p.C = C; p.heads = heads; p.ctx = ctx; p.ctxp = ctxp;
+  p.scale_log2e = (1.0f / sqrtf((float)DK)) * 1.4426950408889634f * kPlaneInv * kPlaneInv;
+  dim3 grid((L + 2 * BQ - 1) / (2 * BQ), heads, B);
+  attention_f16x2_kernel<DK><<<grid, ATT2_THREADS, A::SMEM, st>>>(mq, mk, mvt, p);
+  FS2_LAUNCH_CHECK();
+  return FS2_OK;
+}
+
 template <int DK, bool X3>
 int launch(const __half* qkp, const __half* vtp, int lpad, const int64_t* lens, int B, int L, int C, int heads, float* ctx,
            __half* ctxp, cudaStream_t st) {
@@ -409,6 +669,12 @@ int attention_planes(const __half* qkp, const __half* vtp, int lpad, const int64
   FS2_REQUIRE(!ctxp || ((reinterpret_cast<uintptr_t>(ctxp) & 31) == 0 && (((long)B * L * C) % 16) == 0), "attention_planes: context planes must be 32-byte aligned");
   if (B == 0 || L == 0) return FS2_OK;
   const int dk = C / heads;
+  if (!x3) {
+    static int use_x2 = -1;   // FS2_ATT_X2=0 (debug / A-B): single-tile kernel in F16 too
+    if (use_x2 < 0) { const char* e = getenv("FS2_ATT_X2"); use_x2 = e ? atoi(e) : 1; }
+    if (use_x2 && dk == 192) return launch_x2<192>(qkp, vtp, lpad, lens, B, L, C, heads, ctx, ctxp, st);
+    if (use_x2 && dk == 128) return launch_x2<128>(qkp, vtp, lpad, lens, B, L, C, heads, ctx, ctxp, st);
+  }
   if (dk == 192) return x3 ? launch<192, true>(qkp, vtp, lpad, lens, B, L, C, heads, ctx, ctxp, st) : launch<192, false>(qkp, vtp, lpad, lens, B, L, C, heads, ctx, ctxp, st);
   if (dk == 128) return x3 ? launch<128, true>(qkp, vtp, lpad, lens, B, L, C, heads, ctx, ctxp, st) : launch<128, false>(qkp, vtp, lpad, lens, B, L, C, heads, ctx, ctxp, st);
   set_error("attention_planes: d_k=%d unsupported (128 or 192)", dk);
