@@ -799,15 +799,15 @@ int fs2_op_attention(int math_mode, const float* qkv, const int64_t* lens, int B
   FS2_REQUIRE(qkv && ctx, "fs2_op_attention: null argument");
   FS2_REQUIRE(heads > 0 && C % heads == 0, "fs2_op_attention: C=%d not divisible by heads=%d", C, heads);
   cudaStream_t st = (cudaStream_t)stream;
-  ProfScope prof_scope(P_DEC_ATTN, 4.0 * B * (double)L * L * C, 4.0 * 4.0 * B * (double)L * C, st);
-  if (math_mode == FS2_MATH_FP32) return attention_fp32(qkv, lens, B, L, C, heads, ctx, st);
+  const double flop = 4.0 * B * (double)L * L * C, bytes = 4.0 * 4.0 * B * (double)L * C;
+  if (math_mode == FS2_MATH_FP32) { ProfScope prof_scope(P_DEC_ATTN, flop, bytes, st); return attention_fp32(qkv, lens, B, L, C, heads, ctx, st); }
   if (math_mode == FS2_MATH_TF32) {
     // single-operator entry (tests): build the transposed V the projection epilogue normally provides
     float* vt = nullptr;
     const int lpad = round4(L);
     FS2_CUDA_CHECK(cudaMallocAsync(&vt, (size_t)B * C * lpad * sizeof(float) + 16, st));
     int rc = transpose_v(qkv, B, L, C, heads, vt, lpad, st);
-    if (!rc) rc = attention_tf32(qkv, vt, lpad, lens, B, L, C, heads, ctx, st);
+    if (!rc) { ProfScope prof_scope(P_DEC_ATTN, flop, bytes, st); rc = attention_tf32(qkv, vt, lpad, lens, B, L, C, heads, ctx, st); }
     cudaFreeAsync(vt, st);
     return rc;
   }
@@ -817,7 +817,7 @@ int fs2_op_attention(int math_mode, const float* qkv, const int64_t* lens, int B
   __half* tmp = nullptr;
   FS2_CUDA_CHECK(cudaMallocAsync(&tmp, (nqk + nvt) * sizeof(__half) + 64, st));
   int rc = qkv_to_planes(qkv, B, L, C, heads, tmp, tmp + nqk, lpad, st);
-  if (!rc) rc = attention_planes(tmp, tmp + nqk, lpad, lens, B, L, C, heads, math_mode == MATH_3XTF32, ctx, nullptr, st);
+  if (!rc) { ProfScope prof_scope(P_DEC_ATTN, flop, bytes, st); rc = attention_planes(tmp, tmp + nqk, lpad, lens, B, L, C, heads, math_mode == MATH_3XTF32, ctx, nullptr, st); }
   cudaFreeAsync(tmp, st);
   return rc;
 }

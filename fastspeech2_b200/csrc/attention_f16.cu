@@ -62,7 +62,13 @@ struct HParams {
   float* ctx;            // [B,L,C] fp32 or null
   __half* ctxp;          // planes [P][B*L][C] or null
   float scale_log2e;     // log2(e) / sqrt(dk) / kPlaneScale^2  (Q and K are both pre-scaled)
+  int debug;             // FS2_ATT_DEBUG (profiling experiments only): 1 skip exp math, 2 skip the S load, 4 skip the P store
 };
+inline int att_debug() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FS2_ATT_DEBUG"); v = e ? atoi(e) : 0; }
+  return v;
+}
 
 __device__ __forceinline__ void tmem_st32u(uint32_t taddr, const uint32_t* r) { tmem_st32(taddr, reinterpret_cast<const float*>(r)); }
 
@@ -498,7 +504,11 @@ attention_f16x2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
           const int kv0 = j * BKV2;
           const bool masked = kv0 + BKV2 > len;
           __syncwarp();
-          tmem_ld32_nowait(s_addr, v); tmem_ld32_nowait(s_addr + 32, v + 32); tmem_ld_wait_pin<64>(v);
+          if (!(p.debug & 2)) { tmem_ld32_nowait(s_addr, v); tmem_ld32_nowait(s_addr + 32, v + 32); tmem_ld_wait_pin<64>(v); }
+          else {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] = (float)(i + row) * 1e-3f;
+          }
           float t0 = -INFINITY, t1 = -INFINITY, t2 = -INFINITY, t3 = -INFINITY;     // four chains: the serial max is latency
           if (masked) {
 #pragma unroll
@@ -530,10 +540,18 @@ attention_f16x2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
           }
           const float mb = m_ref * c_exp;
           uint32_t ph[32], pl_unused[1];
-          l_row += masked ? softmax_tile<false, true>(v, c_exp, mb, kv0, len, ph, pl_unused) : softmax_tile<false, false>(v, c_exp, mb, kv0, len, ph, pl_unused);
+          if (!(p.debug & 1)) {
+            l_row += masked ? softmax_tile<false, true>(v, c_exp, mb, kv0, len, ph, pl_unused) : softmax_tile<false, false>(v, c_exp, mb, kv0, len, ph, pl_unused);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ph[i] = __float_as_uint(v[2 * i]);
+            l_row += 1.f;
+          }
           __syncwarp();
-          tmem_st32u(s_addr, ph);                                   // P (packed fp16) over the first 32 columns of the S tile
-          tmem_st_wait();
+          if (!(p.debug & 4)) {
+            tmem_st32u(s_addr, ph);                                 // P (packed fp16) over the first 32 columns of the S tile
+            tmem_st_wait();
+          }
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&p_full[x]);
@@ -603,6 +621,7 @@ int launch_x2(const __half* qkp, const __half* vtp, int lpad, const int64_t* len
   HParams p;
   p.lens = lens; p.B = B; p.L = L; p.C = C; p.heads = heads; p.ctx = ctx; p.ctxp = ctxp;
   p.scale_log2e = (1.0f / sqrtf((float)DK)) * 1.4426950408889634f * kPlaneInv * kPlaneInv;
+  p.debug = att_debug();
   dim3 grid((L + 2 * BQ - 1) / (2 * BQ), heads, B);
   attention_f16x2_kernel<DK><<<grid, ATT2_THREADS, A::SMEM, st>>>(mq, mk, mvt, p);
   FS2_LAUNCH_CHECK();
@@ -624,6 +643,7 @@ int launch(const __half* qkp, const __half* vtp, int lpad, const int64_t* lens, 
   HParams p;
   p.lens = lens; p.B = B; p.L = L; p.C = C; p.heads = heads; p.ctx = ctx; p.ctxp = ctxp;
   p.scale_log2e = (1.0f / sqrtf((float)DK)) * 1.4426950408889634f * kPlaneInv * kPlaneInv;
+  p.debug = 0;
   dim3 grid((L + BQ - 1) / BQ, heads, B);
   attention_f16_kernel<DK, X3><<<grid, ATT_THREADS, A::SMEM, st>>>(mqk, mvt, p);
   FS2_LAUNCH_CHECK();
