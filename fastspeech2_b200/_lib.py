@@ -58,6 +58,30 @@ SIGNATURES = {
     "fs2_op_attention": [_I, _P, _P, _I, _I, _I, _I, _P, _P],
     "fs2_op_gemm_layernorm": [_I, _P, _L, _I, _P, _P, _P, _P, _P, _F, _P, _P],
     "fs2_op_layernorm": [_P, _P, _P, _P, _F, _L, _I, _P, _P],
+    "fs2_dropout_mask": [_P, _L, _F, C.c_uint64, C.c_uint64, _P],
+    "fs2_dropout_apply": [_P, _P, _F, _P, _L, _P],
+    "fs2_act_backward": [_P, _P, _I, _P, _L, _P],
+    "fs2_relu": [_P, _P, _L, _P],
+    "fs2_add": [_P, _P, _P, _L, _P],
+    "fs2_colsum": [_P, _L, _I, _P, _P],
+    "fs2_conv_forward": [_P, _I, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "fs2_conv_dgrad": [_P, _I, _I, _I, _P, _I, _I, _P, _P, _P],
+    "fs2_conv_wgrad": [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
+    "fs2_layernorm_backward": [_P, _P, _P, _F, _L, _I, _P, _P, _P, _P],
+    "fs2_batchnorm_train": [_P, _L, _I, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P, _P],
+    "fs2_batchnorm_backward": [_P, _P, _P, _P, _F, _L, _I, _P, _P, _P, _P, _P],
+    "fs2_bgemm": [_P, _L, _L, _L, _L, _P, _L, _L, _L, _L, _P, _L, _L, _L, _L, _I, _I, _I, _I, _I, _F, _P],
+    "fs2_attn_softmax": [_P, _P, _P, _F, _I, _I, _I, _P, _P, _P],
+    "fs2_attn_softmax_backward": [_P, _P, _P, _F, _I, _I, _I, _P, _P],
+    "fs2_embed_posenc": [_P, _P, _I, _P, _P, _I, _I, _I, _P, _P],
+    "fs2_embed_backward": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
+    "fs2_posenc_add": [_P, _P, _P, _I, _I, _I, _P, _P],
+    "fs2_onehot_linear_forward": [_P, _P, _P, _P, _L, _I, _I, _P, _P],
+    "fs2_onehot_linear_backward": [_P, _P, _L, _I, _I, _P, _P, _P],
+    "fs2_length_regulator_backward": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
+    "fs2_rowdot": [_P, _P, _P, _P, _L, _I, _I, _P, _P],
+    "fs2_rowdot_backward": [_P, _P, _P, _P, _L, _I, _I, _P, _P, _P, _P],
+    "fs2_loss_backward": [_P, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "fs2_peer_alloc": [_SZ, C.POINTER(_P), _P],
     "fs2_peer_free": [_P],
     "fs2_peer_open": [_P, C.POINTER(_P)],

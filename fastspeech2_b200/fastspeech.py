@@ -12,9 +12,11 @@ Surface kept from the reference:
 The sub-modules below are *parameter holders* laid out so that `state_dict()` has the
 reference's keys in the reference's order; they carry no PyTorch compute graph.  All
 arithmetic happens in hand-written sm_100a kernels behind the C ABI (include/fs2_b200.h).
-There is no CPU path and no PyTorch fallback: CPU tensors, a missing library or train mode
-raise.  Train-mode forward/backward (dropout, BatchNorm batch statistics, autograd) is the
-next scope item and raises NotImplementedError today.
+There is no CPU path and no PyTorch fallback: CPU tensors or a missing library raise.
+`forward()` in train mode (`model.train()`, train_fastspeech.py:100-123) runs the train path of
+fastspeech2_b200/train.py: dropout, BatchNorm batch statistics and a backward through every stage,
+all on the library's kernels with torch.autograd as the graph only; `_forward` / `inference` in train
+mode raise (the reference's scripts call those under `model.eval()`).
 
 Precision (`precision=` / FS2_PRECISION): "3xf16" (default; alias "3xtf32") is the reference-precision
 mode -- every contraction, attention included, error-compensated on the tensor cores, fp32-class
@@ -260,6 +262,9 @@ class FeedForwardTransformer(nn.Module):
         self.encoder.embed[-1].alpha.data = torch.tensor(float(_get(m, "initial_encoder_alpha", 1.0)))
         self.decoder.embed[-1].alpha.data = torch.tensor(float(_get(m, "initial_decoder_alpha", 1.0)))
 
+        self.postnet_dropout_rate = float(_get(m, "postnet_dropout_rate", 0.5))
+        self.duration_dropout_rate = float(_get(m, "duration_predictor_dropout_rate", 0.1))
+        self.dropout_masks = None           # train.MaskSource override (tests inject the reference's masks)
         self._epoch = 0
         self._sd_cache: Optional[list] = None
         self._handle: Optional[C.c_void_p] = None
@@ -318,8 +323,9 @@ class FeedForwardTransformer(nn.Module):
         .to(), optimizer steps ...)."""
         if self.training:
             raise NotImplementedError(
-                "fastspeech2_b200 implements the eval-mode forward path; call model.eval(). Train-mode forward/backward "
-                "(dropout, BatchNorm batch statistics, autograd) is not implemented and there is no silent fallback.")
+                "_forward / inference run the eval-mode path; call model.eval() (the reference's scripts do: inference.py:115, "
+                "evaluation.py:19, train_fastspeech.py:152).  In train mode use model(xs, ilens, ys, olens, ds, es, ps), which "
+                "runs the train path (dropout, BatchNorm batch statistics, backward).")
         dev = self._device()
         if dev.type != "cuda":
             raise _lib.Fs2Error("model parameters are on %s: the B200 path has no CPU fallback, call model.to('cuda')" % dev)
@@ -466,7 +472,12 @@ class FeedForwardTransformer(nn.Module):
 
     def forward(self, xs: torch.Tensor, ilens: torch.Tensor, ys: torch.Tensor, olens: torch.Tensor, ds: torch.Tensor,
                 es: torch.Tensor, ps: torch.Tensor) -> Tuple[torch.Tensor, List[Dict[str, float]]]:
-        """Eval-mode loss computation (fastspeech.py:245-337). Returns (loss, report_keys)."""
+        """Loss computation (fastspeech.py:245-337). Returns (loss, report_keys).  In train mode the loss is attached to
+        the autograd graph of the train path (fastspeech2_b200/train.py) so `loss.backward()` fills `.grad` of every
+        parameter the reference trains; `self.dropout_masks` (a train.MaskSource) may be set to inject masks."""
+        if self.training:
+            from .train import train_forward
+            return train_forward(self, xs, ilens, ys, olens, ds, es, ps, masks=self.dropout_masks)
         self._ready(xs)
         lib = _lib.load()
         dev = xs.device

@@ -188,6 +188,64 @@ int fs2_op_attention(int math_mode, const float* qkv, const int64_t* lens, int B
 int fs2_op_layernorm(const float* x, const float* resid, const float* g, const float* b, float eps, int64_t rows, int C,
                      float* out, void* stream);
 
+/* ---- train mode: dropout, BatchNorm batch statistics and the backward of every stage ------- */
+/* What `model.train(); loss, _ = model(...); loss.backward()` of train_fastspeech.py:100-123 needs; fp32 on CUDA cores
+ * (csrc/train.cu).  fastspeech2_b200/train.py chains these with torch.autograd.Function objects (autograd = graph plumbing
+ * only).  Weights are taken in the REFERENCE's layouts (nn.Conv1d [N,K,taps], nn.Linear [N,K]); gradients are accumulated
+ * (+=) into caller-zeroed buffers of the same layouts.  Activations are [B, time, channel] fp32 like the eval path. */
+/* nn.Dropout (train): mask[i] = 1 keep / 0 drop from a Philox4x32-10 stream keyed by (seed, offset + i/4); out = x * mask / (1-p) */
+int fs2_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
+int fs2_dropout_apply(const float* x, const uint8_t* mask, float p, float* out, int64_t n, void* stream);
+/* dx = dy * f'(y) from the saved output y: act 1 = relu, 2 = tanh */
+int fs2_act_backward(const float* dy, const float* y, int act, float* dx, int64_t n, void* stream);
+int fs2_relu(const float* x, float* y, int64_t n, void* stream);
+int fs2_add(const float* a, const float* b, float* y, int64_t n, void* stream);
+int fs2_colsum(const float* x, int64_t rows, int C, float* out /* += */, void* stream);
+/* Conv1d("same") / Linear: forward (core/modules.py:247-248, attention.py:48-50,74, ...), input gradient, weight + bias
+ * gradient.  scratch: N*K*taps floats */
+int fs2_conv_forward(const float* x, int B, int L, int K, const float* w, const float* bias, int N, int taps, int act, const float* resid,
+                     float* out, float* scratch, void* stream);
+int fs2_conv_dgrad(const float* dy, int B, int L, int N, const float* w, int K, int taps, float* dx, float* scratch, void* stream);
+int fs2_conv_wgrad(const float* dy, const float* x, int B, int L, int N, int K, int taps, float* dw /* += */, float* dbias /* += or NULL */, void* stream);
+/* nn.LayerNorm backward from the saved input rows (C in {256, 384}) */
+int fs2_layernorm_backward(const float* x, const float* dy, const float* gamma, float eps, int64_t rows, int C, float* dx, float* dgamma /* += */,
+                           float* dbeta /* += */, void* stream);
+/* BatchNorm1d over the rows of [rows, C] with batch statistics (core/modules.py:296), optional tanh (act 2); updates the running
+ * statistics in place (momentum, unbiased variance); stats [2C] = mean | biased variance; scratch: 2*C doubles */
+int fs2_batchnorm_train(const float* x, int64_t rows, int C, const float* gamma, const float* beta, float eps, float momentum, int act,
+                        float* running_mean, float* running_var, float* stats, float* y, void* scratch, void* stream);
+int fs2_batchnorm_backward(const float* x, const float* dy, const float* stats, const float* gamma, float eps, int64_t rows, int C, float* dx,
+                           float* dgamma /* += */, float* dbeta /* += */, void* scratch, void* stream);
+/* strided batched fp32 GEMM over (batch, head): C = alpha * A . B, every operand as (pointer, batch stride, head stride, row
+ * stride, column stride) in floats -- the attention products and their transposes in forward and backward */
+int fs2_bgemm(const float* a, int64_t abs_, int64_t ahs, int64_t ars, int64_t acs, const float* b, int64_t bbs, int64_t bhs, int64_t brs, int64_t bcs,
+              float* c, int64_t cbs, int64_t chs, int64_t crs, int64_t ccs, int batch, int heads, int M, int N, int K, float alpha, void* stream);
+/* core/attention.py:58-69 on materialised scores [B*heads, L, L]: mask, softmax, masked_fill(0) -> p; dropout -> pd; and its backward */
+int fs2_attn_softmax(const float* s, const int64_t* lens, const uint8_t* dmask, float p_drop, int B, int heads, int L, float* p, float* pd, void* stream);
+int fs2_attn_softmax_backward(const float* p, const float* dpd, const uint8_t* dmask, float p_drop, int B, int heads, int L, float* ds, void* stream);
+/* encoder input (fastspeech.py:65-67 + embedding.py:105-120 before its dropout) and its backward; decoder-side x + alpha*pe */
+int fs2_embed_posenc(const int64_t* xs, const float* table, int n_sym, const float* pe, const float* alpha, int B, int T, int C, float* out,
+                     void* stream);
+int fs2_embed_backward(const int64_t* xs /* NULL: positional part only */, const float* dy, const float* pe, int B, int T, int C, int n_sym,
+                       float* dtable /* += or NULL */, float* dalpha /* += */, void* stream);
+int fs2_posenc_add(const float* x, const float* pe, const float* alpha, int B, int T, int C, float* y, void* stream);
+/* pitch / energy embedding = Linear(n_bins -> C) on a one-hot (fastspeech.py:102,113,218-219), W [C, n_bins] */
+int fs2_onehot_linear_forward(const float* x, const int64_t* ids, const float* W, const float* b, int64_t rows, int C, int n_bins, float* y,
+                              void* stream);
+int fs2_onehot_linear_backward(const int64_t* ids, const float* dy, int64_t rows, int C, int n_bins, float* dW /* += */, float* dbias /* += or NULL */,
+                               void* stream);
+/* LengthRegulator backward: dhs[b,i,:] = sum of dout[b,j,:] over the frames j expanded from phoneme i (cum from fs2_length_plan) */
+int fs2_length_regulator_backward(const float* dout, const int32_t* cum, const int64_t* ilens, int B, int T, int C, int Lcap, float* dhs, void* stream);
+/* predictor head Linear(C -> 1) + masked_fill(pad, 0) (duration_predictor.py:75,83-84) and its backward */
+int fs2_rowdot(const float* x, const float* w, const float* bias, const int64_t* lens, int64_t rows, int L, int C, float* y, void* stream);
+int fs2_rowdot_backward(const float* x, const float* w, const float* dy, const int64_t* lens, int64_t rows, int L, int C, float* dx, float* dw /* += */,
+                        float* dbias /* += */, void* stream);
+/* gradients of the total loss of fs2_masked_losses w.r.t. its five predicted inputs; grad_loss: device scalar dL/dloss */
+int fs2_loss_backward(const float* before, const float* after, const float* ys, int ld_ys_time, const float* d_out, const void* ds, int ds_dtype,
+                      const float* e_out, const float* p_out, const float* es, const float* ps, const int64_t* ilens, const int64_t* olens,
+                      int B, int T, int L, int odim, const float* grad_loss, float* g_before, float* g_after, float* g_d, float* g_e, float* g_p,
+                      void* stream);
+
 /* ---- multi-GPU exchange step: gather of the final mel shards on one rank over NVLink peer memory ----------------- */
 /* Replaces what a reference user would write as torch.distributed.gather / all_gather of `after_outs` (the reference has
  * no multi-GPU path; SURVEY.md section 8e defines the step).  The root rank owns one receive buffer and exports it with
