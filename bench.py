@@ -117,13 +117,17 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def ncu_traffic(kernel: str, precision: str = "tf32"):
+def ncu_traffic(kernel: str, precision: str = "tf32", info: bool = False):
     """DRAM bytes per launch of `kernel` in `precision` mode from the committed `ncu --set full` capture
-    (profiles/ncu_traffic.json; keys are "<class>" for tf32 captures and "<class>@<precision>" otherwise), or None."""
+    (profiles/ncu_traffic.json; keys are "<class>" for tf32 captures and "<class>@<precision>" otherwise), or None.
+    The number is a property of the build that was captured, not of this run: `info=True` returns where it came from."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         d = json.load(open(p))
-        return d.get(kernel if precision == "tf32" else f"{kernel}@{precision}", {}).get("dram_bytes_per_launch")
+        e = d.get(kernel if precision == "tf32" else f"{kernel}@{precision}", {})
+        if info:
+            return (f"{e.get('source')} ({e.get('build')})" if e else None)
+        return e.get("dram_bytes_per_launch")
     except Exception:
         return None
 
@@ -531,6 +535,7 @@ def run_b200(args):
         achieved = pk["flop"] / (pk["ms"] * 1e-3) / 1e12 if pk["ms"] > 0 else 0.0
         roof = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                 "frac": achieved / tensor_peak, "traffic": ncu_traffic(top, args.precision),
+                "traffic_source": ncu_traffic(top, args.precision, info=True),
                 "algorithmic_bytes_per_launch": pk["bytes"] / pk["launches"], "algorithmic_flop_per_launch": pk["flop"] / pk["launches"],
                 "avg_launch_ms": pk["ms"] / pk["launches"], "share_of_step": pk["ms"] / tot,
                 "peak_source": peak_src + " burst bf16 figure (kernel timed alone by CUDA events); " + peak_note,
