@@ -310,7 +310,17 @@ def run_b200(args):
     sd = synthetic_state_dict(0)
     bt = make_batch(B, T, L, seed=1234 + rank)          # rank r owns utterances [r*B, (r+1)*B)
     keys = ("xs", "ilens", "olens", "ds", "es", "ps")
-    host = {k: bt[k].pin_memory() for k in keys}
+    # e2e host side = the repo's input pipeline (fastspeech2_b200/data.py): the batch is collated from per-utterance items into
+    # PinnedCollator's page-locked slots (the reference's collate_tts contract), uploads are asynchronous from there
+    from fastspeech2_b200.data import PinnedCollator
+    items = [(bt["xs"][b, : int(bt["ilens"][b])].numpy(), bt["ys"][b, : int(bt["olens"][b])].numpy(), f"utt{b}", int(bt["olens"][b]),
+              bt["ds"][b, : int(bt["ilens"][b])].numpy(), bt["es"][b, : int(bt["olens"][b])].numpy(), bt["ps"][b, : int(bt["olens"][b])].numpy())
+             for b in range(B)]
+    collator = PinnedCollator(B, T, L, n_mels=80, slots=2)
+    pinned = [collator(items), collator(items)]                       # 9-tuples: inputs, ilens, mels, labels, olens, ids, durations, energys, pitches
+    FIELD = {"xs": 0, "ilens": 1, "olens": 4, "ds": 6, "es": 7, "ps": 8}
+    host = {k: pinned[0][FIELD[k]] for k in keys}
+    assert all(torch.equal(host[k], bt[k]) for k in keys), "collated batch differs from the synthetic batch"
     devin = {k: bt[k].to(dev) for k in keys}
     frames_rank = int(bt["olens"].sum())
     gathered = torch.empty((world * B, L, 80), dtype=torch.float32, device=dev) if world > 1 else None
@@ -395,11 +405,15 @@ def run_b200(args):
                     g = graphs[i & 1]
                     source_free(i)
                     cur.wait_event(copied[i & 1])                       # its previous output has left for the host
+                    col = pinned[i & 1]
+                    dst9 = [None] * 9
                     for dst, k in zip(g.inputs, keys):
-                        dst.copy_(host[k], non_blocking=True)           # H2D straight into the graph's static inputs
+                        dst9[FIELD[k]] = dst
+                    collator.upload_into(col, dst9)                     # H2D from the pinned slot straight into the graph's static inputs
                     out = g.replay(validate="deferred")
                 else:
-                    inp = [host[k].to(dev, non_blocking=True) for k in keys]
+                    up = collator.to_device(pinned[i & 1], dev)
+                    inp = [up[FIELD[k]] for k in keys]
                     out = model._forward(*inp, is_inference=False)
             collective(out[1], i)
             done = torch.cuda.Event()

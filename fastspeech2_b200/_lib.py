@@ -82,6 +82,10 @@ SIGNATURES = {
     "fs2_rowdot": [_P, _P, _P, _P, _L, _I, _I, _P, _P],
     "fs2_rowdot_backward": [_P, _P, _P, _P, _L, _I, _I, _P, _P, _P, _P],
     "fs2_loss_backward": [_P, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "fs2_stft_frames": [_P, _I, _I, _I, _I, _I, _P, _P],
+    "fs2_stft_magphase": [_P, _I, _I, _I, _I, _P, _P, _P],
+    "fs2_istft_recombine": [_P, _P, _I, _I, _I, _I, _P, _P],
+    "fs2_istft_overlap_add": [_P, _I, _I, _I, _I, _P, _F, _P, _P],
     "fs2_peer_alloc": [_SZ, C.POINTER(_P), _P],
     "fs2_peer_free": [_P],
     "fs2_peer_open": [_P, C.POINTER(_P)],

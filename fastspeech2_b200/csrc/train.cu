@@ -326,8 +326,9 @@ bgemm_kernel(BgemmOperand A, BgemmOperand Bm, float* __restrict__ Cp, long cbs, 
 // attention.py:58-69 on materialised scores s [B*h, L, L]: mask (query AND key < len_b), softmax over keys, masked_fill(0),
 // then dropout: p (pre-dropout probabilities, saved for backward) and pd = p * mask / (1 - rate).  One warp per row.
 __global__ void attn_softmax_kernel(const float* __restrict__ s, const int64_t* __restrict__ lens, const uint8_t* __restrict__ dmask,
-                                    float keep_scale, int heads, int L, float* __restrict__ p, float* __restrict__ pd) {
+                                    float keep_scale, int heads, int L, long rows, float* __restrict__ p, float* __restrict__ pd) {
   const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const long z = row / L; const int t = (int)(row - z * L);
   const int b = (int)(z / heads);
@@ -349,8 +350,9 @@ __global__ void attn_softmax_kernel(const float* __restrict__ s, const int64_t* 
 }
 // dS = P o (dP - rowsum(dP o P)) with dP = dPd * mask * keep_scale; masked positions have P = 0 -> dS = 0
 __global__ void attn_softmax_backward_kernel(const float* __restrict__ p, const float* __restrict__ dpd, const uint8_t* __restrict__ dmask,
-                                             float keep_scale, int L, float* __restrict__ ds) {
+                                             float keep_scale, int L, long rows, float* __restrict__ ds) {
   const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const float* pr = p + row * L; const float* gr = dpd + row * L; float* dr = ds + row * L;
   float dot = 0.f;
@@ -649,7 +651,7 @@ int fs2_attn_softmax(const float* s, const int64_t* lens, const uint8_t* dmask, 
   FS2_REQUIRE(s && p && pd && p_drop >= 0.f && p_drop < 1.f, "fs2_attn_softmax: bad argument");
   const long rows = (long)B * heads * L;
   if (rows == 0) return FS2_OK;
-  attn_softmax_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(s, lens, dmask, 1.0f / (1.0f - p_drop), heads, L, p, pd);
+  attn_softmax_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(s, lens, dmask, 1.0f / (1.0f - p_drop), heads, L, rows, p, pd);
   FS2_LAUNCH_CHECK();
   return FS2_OK;
 }
@@ -657,7 +659,7 @@ int fs2_attn_softmax_backward(const float* p, const float* dpd, const uint8_t* d
   FS2_REQUIRE(p && dpd && ds, "fs2_attn_softmax_backward: null argument");
   const long rows = (long)B * heads * L;
   if (rows == 0) return FS2_OK;
-  attn_softmax_backward_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(p, dpd, dmask, 1.0f / (1.0f - p_drop), L, ds);
+  attn_softmax_backward_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(p, dpd, dmask, 1.0f / (1.0f - p_drop), L, rows, ds);
   FS2_LAUNCH_CHECK();
   return FS2_OK;
 }

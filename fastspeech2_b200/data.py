@@ -116,6 +116,20 @@ class PinnedCollator:
             self.slots[slot]["event"] = ev
         return out
 
+    def upload_into(self, collated, dst: Sequence[Optional[torch.Tensor]]):
+        """Like `to_device`, but copies into existing device tensors (e.g. the static inputs of a captured CUDA graph):
+        `dst[i]` receives `collated[i]` (None / non-tensor entries are skipped).  Asynchronous, same slot bookkeeping."""
+        dev = None
+        for src, d in zip(collated, dst):
+            if d is not None and torch.is_tensor(src):
+                d.copy_(src, non_blocking=True)
+                dev = d.device
+        slot = getattr(collated, "slot", -1)
+        if slot >= 0 and dev is not None and dev.type == "cuda":
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            self.slots[slot]["event"] = ev
+
 
 class BucketBatchSampler:
     """Batches of indices with similar length: sort by length, cut into bins of `bin_size`, shuffle inside and

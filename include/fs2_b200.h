@@ -246,6 +246,19 @@ int fs2_loss_backward(const float* before, const float* after, const float* ys, 
                       int B, int T, int L, int odim, const float* grad_loss, float* g_before, float* g_after, float* g_d, float* g_e, float* g_p,
                       void* stream);
 
+/* ---- vocoder hand-off: the STFT / inverse STFT Griffin-Lim iterates ------------------------- */
+/* utils/stft.py:82-151 without cuFFT, like the reference (which runs them as conv1d / conv_transpose1d with Fourier bases):
+ * the two GEMMs go through fs2_op_tap_gemm, these are the kernels around them.  fastspeech2_b200/vocoder.py drives them.
+ *   fs2_stft_frames       frames[b,f,k] = reflect_pad(x, n_fft/2)[b, f*hop + k]                       (:89-95)
+ *   fs2_stft_magphase     spec [B*frames, ld] (real | imag) -> magnitude, phase [B, cutoff, frames]   (:105-112)
+ *   fs2_istft_recombine   (magnitude, phase) -> [B*frames, ld] = mag*cos | mag*sin | 0-padding        (:115-117)
+ *   fs2_istft_overlap_add overlap-add of [B, frames, n_fft] at stride hop, / window_sum where > tiny, * n_fft/hop, trimmed
+ *                         by n_fft/2 at both ends -> y [B, (frames-1)*hop]                              (:119-149) */
+int fs2_stft_frames(const float* x, int B, int n, int n_fft, int hop, int frames, float* out, void* stream);
+int fs2_stft_magphase(const float* spec, int ld, int B, int cutoff, int frames, float* mag, float* phase, void* stream);
+int fs2_istft_recombine(const float* mag, const float* phase, int B, int cutoff, int frames, int ld, float* rec, void* stream);
+int fs2_istft_overlap_add(const float* frames_out, int B, int n_fft, int hop, int frames, const float* window_sum, float tiny, float* y, void* stream);
+
 /* ---- multi-GPU exchange step: gather of the final mel shards on one rank over NVLink peer memory ----------------- */
 /* Replaces what a reference user would write as torch.distributed.gather / all_gather of `after_outs` (the reference has
  * no multi-GPU path; SURVEY.md section 8e defines the step).  The root rank owns one receive buffer and exports it with

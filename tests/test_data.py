@@ -1,6 +1,7 @@
 """Input side: collate parity with the reference's collate_tts (golden fixture), pinned collator,
 bucket sampler.  CPU only."""
 import numpy as np
+import pytest
 import torch
 
 from fastspeech2_b200.data import BucketBatchSampler, PinnedCollator, collate_tts
@@ -72,3 +73,27 @@ def test_vocoder_handoff_layout():
     parts = split_utterances(mels, olens)
     assert [tuple(p.shape) for p in parts] == [(1, 80, 7), (1, 80, 3), (1, 80, 5)]
     assert torch.equal(torch.cat(parts, dim=2), want)
+
+
+@pytest.mark.gpu
+def test_pinned_collator_uploads_survive_run_ahead(golden):
+    """a loader that runs ahead of the GPU must never refill a pinned slot an asynchronous upload is still
+    reading.  Batches of different content are collated and uploaded back to back while the GPU is kept busy."""
+    g = golden("collate")
+    base = items_from(g)
+    for slots in (1, 2):
+        pc = PinnedCollator(max_batch=8, max_T=20, max_L=64, slots=slots)
+        busy = torch.randn(4096, 4096, device="cuda")
+        want, got = [], []
+        for step in range(6):
+            items = [(it[0], it[1] + step, it[2], it[3], it[4], it[5] * (step + 1), it[6]) for it in base]
+            for _ in range(4):
+                busy = busy @ busy * 1e-4                 # queue GPU work so the H2D copies lag behind the host
+            col = pc(items)
+            want.append(tuple(t.clone() if torch.is_tensor(t) else t for t in col))
+            got.append(pc.to_device(col, "cuda"))
+        torch.cuda.synchronize()
+        for w, o in zip(want, got):
+            for a, b in zip(w, o):
+                if torch.is_tensor(a):
+                    assert torch.equal(a, b.cpu())
