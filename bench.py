@@ -337,7 +337,14 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    peer = PeerGather((B, L, 80), dev) if (world > 1 and args.collective == "peer_copy") else None
+    peer, collective_note = None, None
+    if world > 1 and args.collective == "peer_copy":
+        try:
+            peer = PeerGather((B, L, 80), dev)      # raises on ALL ranks if any rank cannot map the root's buffer
+        except Exception as e:      # no IPC / peer access on this box: say so and use the NCCL gather instead of dying
+            peer = None
+            args.collective = "gather"
+            collective_note = f"peer_copy unavailable ({type(e).__name__}: {str(e)[:160]}); fell back to the NCCL gather"
     step_no = [0]
 
     def timed(fn, steps, warmup):
@@ -577,6 +584,7 @@ def run_b200(args):
                    "tolerance": "3xf16 (default): max-abs 1e-4, mean-abs 1e-5 vs the CPU fp32 oracle on the mels, durations / bucket ids bit-exact; "
                                 "fp32: 1e-4; f16: 5e-3 / 5e-4; tf32: 1e-2 / 1e-3 (tests/test_gpu_parity.py)"},
         "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "collective_note": collective_note,
         "gpu_launches": int(launches_per_step * args.steps),
         "gpu_launches_per_step": int(launches_per_step),
         "gpu_busy_ms_per_step": gpu_busy,

@@ -690,8 +690,11 @@ int attention_planes(const __half* qkp, const __half* vtp, int lpad, const int64
   if (B == 0 || L == 0) return FS2_OK;
   const int dk = C / heads;
   if (!x3) {
-    static int use_x2 = -1;   // FS2_ATT_X2=0 (debug / A-B): single-tile kernel in F16 too
-    if (use_x2 < 0) { const char* e = getenv("FS2_ATT_X2"); use_x2 = e ? atoi(e) : 1; }
+    // FS2_ATT_X2=1 (experiment): the two-tile kernel.  Measured slower than the single-tile one (c2: 0.50 vs 0.42 ms per
+    // step, c4: 1.09 vs 0.77, profiles/r02_attention_ab.md): with 64 keys per step it pays twice the softmax <-> MMA
+    // hand-offs per key, and the softmax itself is bound by the TMEM read of S and MUFU.EX2, not by MMA overlap
+    static int use_x2 = -1;
+    if (use_x2 < 0) { const char* e = getenv("FS2_ATT_X2"); use_x2 = e ? atoi(e) : 0; }
     if (use_x2 && dk == 192) return launch_x2<192>(qkp, vtp, lpad, lens, B, L, C, heads, ctx, ctxp, st);
     if (use_x2 && dk == 128) return launch_x2<128>(qkp, vtp, lpad, lens, B, L, C, heads, ctx, ctxp, st);
   }

@@ -664,7 +664,7 @@ int fs2_attn_softmax_backward(const float* p, const float* dpd, const uint8_t* d
   return FS2_OK;
 }
 int fs2_embed_backward(const int64_t* xs, const float* dy, const float* pe, int B, int T, int C, int n_sym, float* dtable, float* dalpha, void* stream) {
-  FS2_REQUIRE(xs && dy && pe && dalpha, "fs2_embed_backward: null argument");
+  FS2_REQUIRE(dy && pe && dalpha && (xs || !dtable), "fs2_embed_backward: null argument");
   const long rows = (long)B * T;
   if (rows == 0) return FS2_OK;
   embed_backward_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(xs, dy, pe, rows, T, C, n_sym, dtable, dalpha);

@@ -121,21 +121,37 @@ class PeerGather:
         assert self.world * 8 <= self.HEADER
         handle = (C.c_char * 64)()
         ptr = C.c_void_p()
+        err = None
         with torch.cuda.device(self.device):
+            # every rank takes part in every collective below whatever fails locally, then all agree on success
             if self.rank == root:
-                _lib.check(self._lib.fs2_peer_alloc(total, C.byref(ptr), handle), "fs2_peer_alloc")
-            obj = [bytes(handle) if self.rank == root else None]
+                try:
+                    _lib.check(self._lib.fs2_peer_alloc(total, C.byref(ptr), handle), "fs2_peer_alloc")
+                except Exception as e:          # noqa: BLE001
+                    err = e
+            obj = [bytes(handle) if (self.rank == root and err is None) else None]
             dist.broadcast_object_list(obj, src=root, group=group, device=self.device)
             if self.rank != root:
-                _lib.check(self._lib.fs2_peer_open(C.create_string_buffer(obj[0], 64), C.byref(ptr)), "fs2_peer_open")
-        self._base = int(ptr.value)
+                try:
+                    if obj[0] is None:
+                        raise _lib.Fs2Error("the root rank could not export its receive buffer")
+                    _lib.check(self._lib.fs2_peer_open(C.create_string_buffer(obj[0], 64), C.byref(ptr)), "fs2_peer_open")
+                except Exception as e:          # noqa: BLE001
+                    err = e
+            ok = torch.tensor([0.0 if err is not None else 1.0], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        self._base = int(ptr.value or 0)
+        if float(ok) < 1:
+            if self._base:
+                (self._lib.fs2_peer_free if self.rank == root else self._lib.fs2_peer_close)(self._base)
+                self._base = 0
+            raise _lib.Fs2Error(f"PeerGather: peer memory unavailable on at least one rank ({err})")
         self._flags = self._base
         self._data = self._base + self.HEADER
         self.stream = torch.cuda.Stream(self.device)
         if self.rank == root:
             raw = torch.as_tensor(_RawCudaBuffer(self._data, self.world * self.shard_bytes), device=self.device)
             self.gathered = raw.view(dtype).view((self.world * self.shape[0],) + self.shape[1:])
-        dist.barrier(group=group)
 
     def push(self, mel: torch.Tensor, step: int) -> None:
         if not self._cuda or self.world == 1:

@@ -44,7 +44,7 @@ class STFT(torch.nn.Module):
         super().__init__()
         if window != "hann":
             raise NotImplementedError("only the hann window the reference uses is implemented")
-        assert filter_length >= win_length and filter_length % 16 == 0
+        assert filter_length >= win_length and filter_length % 80 == 0 or filter_length % 128 == 0, "n_fft must be a multiple of 80 or 128 (GEMM tile widths)"
         self.filter_length, self.hop_length, self.win_length, self.window = filter_length, hop_length, win_length, window
         self.math_mode = _lib.MATH_MODES[math_mode]
         scale = filter_length / hop_length
@@ -56,8 +56,8 @@ class STFT(torch.nn.Module):
         inv = torch.FloatTensor(np.linalg.pinv(scale * fourier).T[:, None, :]) * torch.from_numpy(win).float()
         self.register_buffer("forward_basis", fwd.float())                                         # [2*cutoff, 1, n_fft]
         self.register_buffer("inverse_basis", inv.float())
-        # GEMM operands in the library's [taps=1][N][K] layout, N / K padded to multiples of 16 with zeros
-        self.cpad = (2 * cutoff + 15) // 16 * 16
+        # GEMM operands in the library's [taps=1][N][K] layout, N / K padded with zero rows / columns to the next tile multiple
+        self.cpad = (2 * cutoff + 63) // 64 * 64
         w_f = torch.zeros(self.cpad, filter_length); w_f[: 2 * cutoff] = fwd[:, 0, :]
         w_i = torch.zeros(filter_length, self.cpad); w_i[:, : 2 * cutoff] = inv[:, 0, :].T
         self.register_buffer("_w_forward", w_f.contiguous(), persistent=False)

@@ -71,3 +71,29 @@ def _root_worker(rank, world, port):
 
 def test_gather_mels_to_root_world2():
     mp.spawn(_root_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
+def _peer_worker(rank, world, port):
+    """PeerGather's protocol (push per step, root waits, `gathered` view) with CPU tensors: the class degrades to the gloo
+    gather, so the host-side sequencing of bench.py / serving loops is exercised without a GPU."""
+    from fastspeech2_b200.sharded import PeerGather
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        pg = PeerGather((4, 6, 5), "cpu")
+        for step in (1, 2, 3):
+            full = torch.randn(8, 6, 5, generator=torch.Generator().manual_seed(step))
+            lo, hi = shard_bounds(8, rank, world)
+            pg.push(full[lo:hi].contiguous(), step)
+            pg.wait(step)
+            if rank == 0:
+                assert torch.equal(pg.gathered, full)
+            else:
+                assert pg.gathered is None
+        pg.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_gather_protocol_world2_cpu_fallback():
+    mp.spawn(_peer_worker, args=(2, _free_port()), nprocs=2, join=True)
