@@ -538,6 +538,7 @@ int fs2_create(fs2_handle** out, const fs2_config* cfg, int device) {
 
 void fs2_destroy(fs2_handle* h) {
   if (!h) return;
+  if (t_prof == &h->prof) t_prof = nullptr;   // the single-operator entries must not record into a destroyed handle's profiler
   {
     DeviceGuard guard(h->device);
     if (h->arena) cudaFree(h->arena);

@@ -63,7 +63,38 @@ struct HParams {
   __half* ctxp;          // planes [P][B*L][C] or null
   float scale_log2e;     // log2(e) / sqrt(dk) / kPlaneScale^2  (Q and K are both pre-scaled)
   int debug;             // FS2_ATT_DEBUG (profiling experiments only): 1 skip exp math, 2 skip the S load, 4 skip the P store
+  long long* trace;      // FS2_ATT_TRACE=1 (profiling experiments only): clock64 stamps of CTA (0,0,0), see att_trace_dump
 };
+constexpr int TRACE_SLOTS = 8, TRACE_TILES = 32;     // per tile: 2 softmax halves x 8 stamps, then 8 MMA-warp stamps
+__device__ __forceinline__ void trace_at(const HParams& p, int j, int who, int k) {
+  if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x & 31) == 0 && j < TRACE_TILES)
+    p.trace[(j * 3 + who) * TRACE_SLOTS + k] = clock64();
+}
+// FS2_ATT_TRACE=1: a device buffer for the clock64 stamps of CTA (0,0,0); dumped (with a stream sync) after the launch
+inline long long* att_trace_buffer() {
+  static int on = -1; static long long* buf = nullptr;
+  if (on < 0) { const char* e = getenv("FS2_ATT_TRACE"); on = e ? atoi(e) : 0; }
+  if (on && !buf) { cudaMalloc(&buf, 32 * 3 * 8 * sizeof(long long)); }
+  if (on && buf) cudaMemset(buf, 0, 32 * 3 * 8 * sizeof(long long));
+  return on ? buf : nullptr;
+}
+inline void att_trace_dump(long long* dev, int tiles, cudaStream_t st) {
+  static int dumped = 0;
+  if (dumped++ >= 2) return;
+  long long h[32 * 3 * 8];
+  cudaStreamSynchronize(st);
+  cudaMemcpy(h, dev, sizeof(h), cudaMemcpyDeviceToHost);
+  const long long t0 = h[(0 * 3 + 2) * 8 + 0] ? h[(0 * 3 + 2) * 8 + 0] : h[0];
+  fprintf(stderr, "fs2 attention trace (cycles since the MMA warp's first stamp; CTA 0)\n tile | softmax half0: wait_begin s_ready ld_done max_done exp_done p_arrived | half1: ... | mma: loop_top s_next_issued p_ready pv_issued\n");
+  for (int j = 0; j < tiles && j < 32; ++j) {
+    fprintf(stderr, " %3d |", j);
+    for (int who = 0; who < 3; ++who) {
+      for (int k = 0; k < (who == 2 ? 4 : 6); ++k) fprintf(stderr, " %7lld", h[(j * 3 + who) * 8 + k] ? h[(j * 3 + who) * 8 + k] - t0 : -1);
+      fprintf(stderr, " |");
+    }
+    fprintf(stderr, "\n");
+  }
+}
 inline int att_debug() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("FS2_ATT_DEBUG"); v = e ? atoi(e) : 0; }
@@ -201,9 +232,12 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
         };
         issue_s(0);
         for (int j = 0; j < J; ++j) {
+          trace_at(p, j, 2, 0);
           if (j + 1 < J) issue_s(j + 1);                 // the tensor core computes S_{j+1} while the softmax warps work on tile j
+          trace_at(p, j, 2, 1);
           mbar_wait(&p_full[j & 1], (j >> 1) & 1);
           tcgen05_fence_after();
+          trace_at(p, j, 2, 2);
           const uint32_t p_hi = tmem_base + (uint32_t)((j & 1) * BKV), p_lo = p_hi + BKV / 2;   // packed fp16: 64 columns each
           const uint32_t o = tmem_base + A::O_COL;
           for (int c = 0; c < BKV / CH; ++c) {
@@ -226,6 +260,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
             }
           }
           tcgen05_commit(&pv_done[0]);                   // lets the softmax warps rescale O if tile j+1 raises the reference max
+          trace_at(p, j, 2, 3);
         }
         tcgen05_commit(o_full);
       }
@@ -238,13 +273,16 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
       float m_ref = -INFINITY, l_row = 0.f;     // reference maximum (raw-score domain) and row sum relative to it
       const float c_exp = p.scale_log2e;
       for (int j = 0; j < J; ++j) {
+        if (wq == 0) trace_at(p, j, half, 0);
         mbar_wait(&s_full[j & 1], (j >> 1) & 1);
         tcgen05_fence_after();
+        if (wq == 0) trace_at(p, j, half, 1);
         const int kv0 = j * BKV + half * 64;
         const bool masked = kv0 + 64 > len;                      // only the last tile of an utterance
         __syncwarp();
         const uint32_t tb = lane_addr + (uint32_t)((j & 1) * BKV);
         tmem_ld32_nowait(tb + half * 64, v); tmem_ld32_nowait(tb + half * 64 + 32, v + 32); tmem_ld_wait_pin<64>(v);
+        if (wq == 0) trace_at(p, j, half, 2);
         float tmax = -INFINITY;
         if (masked) {
 #pragma unroll
@@ -257,6 +295,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
         xr[half * BQ + row] = tmax;
         named_bar_sync(1, 256);                                   // also: both halves of every row have read their S columns
         tmax = fmaxf(tmax, xr[(half ^ 1) * BQ + row]);           // both threads of the row now hold the tile's row maximum
+        if (wq == 0) trace_at(p, j, half, 3);
         // lazy reference update: move m_ref only if the tile exceeds it by more than 2^8 in the exp2 domain
         const bool bump = (tmax - m_ref) * c_exp > 8.0f;          // first tile: m_ref = -inf -> always
         if (__any_sync(0xffffffffu, bump)) {
@@ -283,12 +322,14 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
         uint32_t ph[32], pl[32];
         l_row += masked ? softmax_tile<X3, true>(v, c_exp, mb, kv0, len, ph, pl) : softmax_tile<X3, false>(v, c_exp, mb, kv0, len, ph, pl);
         __syncwarp();
+        if (wq == 0) trace_at(p, j, half, 4);
         tmem_st32u(tb + half * 32, ph);                           // P hi: packed columns [0,64) of the tile's buffer
         if (X3) tmem_st32u(tb + BKV / 2 + half * 32, pl);         // P lo: [64,128)
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[j & 1]);
+        if (wq == 0) trace_at(p, j, half, 5);
       }
       named_bar_sync(1, 256);                                     // last exchange buffer is free again
       xchg[half * BQ + row] = l_row;
@@ -622,6 +663,7 @@ int launch_x2(const __half* qkp, const __half* vtp, int lpad, const int64_t* len
   p.lens = lens; p.B = B; p.L = L; p.C = C; p.heads = heads; p.ctx = ctx; p.ctxp = ctxp;
   p.scale_log2e = (1.0f / sqrtf((float)DK)) * 1.4426950408889634f * kPlaneInv * kPlaneInv;
   p.debug = att_debug();
+  p.trace = nullptr;
   dim3 grid((L + 2 * BQ - 1) / (2 * BQ), heads, B);
   attention_f16x2_kernel<DK><<<grid, ATT2_THREADS, A::SMEM, st>>>(mq, mk, mvt, p);
   FS2_LAUNCH_CHECK();
@@ -644,9 +686,11 @@ int launch(const __half* qkp, const __half* vtp, int lpad, const int64_t* lens, 
   p.lens = lens; p.B = B; p.L = L; p.C = C; p.heads = heads; p.ctx = ctx; p.ctxp = ctxp;
   p.scale_log2e = (1.0f / sqrtf((float)DK)) * 1.4426950408889634f * kPlaneInv * kPlaneInv;
   p.debug = 0;
+  p.trace = att_trace_buffer();
   dim3 grid((L + BQ - 1) / BQ, heads, B);
   attention_f16_kernel<DK, X3><<<grid, ATT_THREADS, A::SMEM, st>>>(mqk, mvt, p);
   FS2_LAUNCH_CHECK();
+  if (p.trace) att_trace_dump(p.trace, (L + BKV - 1) / BKV, st);
   return FS2_OK;
 }
 
