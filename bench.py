@@ -72,7 +72,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -115,6 +115,19 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+    def median_between(self, t_begin, t_end):
+        """Median SM clock of the samples inside [t_begin, t_end] (per timed loop), or None."""
+        sm = []
+        for ts, ln in self.lines:
+            if t_begin <= ts <= t_end + 0.03:
+                f = [x.strip() for x in ln.split(",")]
+                try:
+                    sm.append(float(f[1]))
+                except (ValueError, IndexError):
+                    pass
+        sm.sort()
+        return sm[len(sm) // 2] if sm else None
 
 
 def ncu_traffic(kernel: str, precision: str = "tf32", info: bool = False):
@@ -453,13 +466,20 @@ def run_b200(args):
         step(i)
     torch.cuda.synchronize()
     t_begin = time.time()
-    ms_step = timed(step, args.steps, 0)
-    flush()
-    ms_e2e = timed(step_e2e, args.steps, 2)
-    flush()
-    clocks = sampler.stop(t_begin, time.time()) if sampler else None
+    if args.e2e_first:                      # diagnostic: does the e2e - value gap follow the loop order (clock sag under the power cap)?
+        ms_e2e = timed(step_e2e, args.steps, 2); flush()
+        t_mid = time.time()
+        ms_step = timed(step, args.steps, 0); flush()
+    else:
+        ms_step = timed(step, args.steps, 0); flush()
+        t_mid = time.time()
+        ms_e2e = timed(step_e2e, args.steps, 2); flush()
+    t_end = time.time()
+    clocks = sampler.stop(t_begin, t_end) if sampler else None
     if clocks is not None:
-        clocks["window"] = "samples every 100 ms during the device-timed loop and the e2e loop"
+        first, second = sampler.median_between(t_begin, t_mid), sampler.median_between(t_mid, t_end)
+        clocks["sm_mhz_value_loop"], clocks["sm_mhz_e2e_loop"] = (second, first) if args.e2e_first else (first, second)
+        clocks["window"] = "samples every 25 ms during the device-timed loop and the e2e loop (which run back to back; the second one sees the clocks the power cap has settled to)"
 
     # per-kernel-class CUDA-event profile on extra steps of the same workload
     prof = None
@@ -624,6 +644,7 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=32, help="host threads of the CPU reference (fixed; oversubscription is slower)")
     ap.add_argument("--collective", default="peer_copy", choices=["peer_copy", "all_gather", "gather"],
                     help="N>1: gather to rank 0 by copy-engine pushes over NVLink peer memory (default), or NCCL gather / all_gather")
+    ap.add_argument("--e2e-first", type=int, default=0, help="diagnostic: time the e2e loop before the device-resident loop")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (default), 0: eager launches")
     args = ap.parse_args()
     if args.impl == "reference":
