@@ -136,24 +136,34 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)A::SLOTS * A::SLOT);
   uint64_t* full_bar = bars;                   // [SLOTS]
   uint64_t* empty_bar = bars + A::SLOTS;       // [SLOTS]
-  uint64_t* q_bar = bars + 2 * A::SLOTS;       // Q landed
+  uint64_t* q_bar = bars + 2 * A::SLOTS;       // TMA -> MMA: Q of the current work item landed
   uint64_t* s_full = q_bar + 1;                // [2] MMA -> softmax: S tile ready
   uint64_t* pv_done = s_full + 2;              // MMA -> softmax: P.V of the previous tile has finished
   uint64_t* p_full = pv_done + 2;              // [2] softmax -> MMA: P written
-  uint64_t* o_full = p_full + 2;               // all P.V done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* o_full = p_full + 2;               // MMA -> epilogue: all P.V of the work item done
+  uint64_t* o_free = o_full + 1;               // epilogue -> MMA: O has been read, the next work item may overwrite it
+  uint64_t* q_free = o_free + 1;               // MMA -> TMA: every S product of the work item has read Q
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_free + 1);
   float* xchg = reinterpret_cast<float*>(tmem_slot + 4);   // [2 tiles][2 halves][BQ] row-statistic exchange between column halves
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
-  const int len = p.lens ? (int)min((long)p.lens[b], (long)p.L) : p.L;   // keys >= len are masked
-  const int J = (len + BKV - 1) / BKV;                                   // kv tiles that contain valid keys
+  // Persistent CTA: work item w = ((b * heads + h) * nq + qt), taken round-robin.  The TMA producer and the MMA warp run
+  // ahead into the next item (its Q lands while the current item's last softmax / P.V / epilogue are still running), so
+  // the 2-3 us cold-start of a tile (Q + first K over TMA, first S) is paid once per CTA instead of once per tile.
+  const int nq = (p.L + BQ - 1) / BQ;
+  const int total_work = p.B * p.heads * nq;
+  auto decode = [&](int w, int& b, int& h, int& q0, int& len, int& J) {
+    const int qt = w % nq; const int bh = w / nq;
+    h = bh % p.heads; b = bh / p.heads; q0 = qt * BQ;
+    len = p.lens ? (int)min((long)p.lens[b], (long)p.L) : p.L;       // keys >= len are masked
+    J = (len + BKV - 1) / BKV;                                        // kv tiles that contain valid keys
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < A::SLOTS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(q_bar, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&pv_done[i], 1); mbar_init(&p_full[i], 8); }
-    mbar_init(o_full, 1);
+    mbar_init(o_full, 1); mbar_init(o_free, 8); mbar_init(q_free, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, A::TMEM_COLS);
@@ -162,14 +172,18 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (J > 0) {
-    if (warp == 0) {
-      if (lane == 0) {  // ---- TMA producer: Q once, then K / V^T boxes in exactly the order the MMA warp consumes them ----
+  if (warp == 0) {
+    if (lane == 0) {  // ---- TMA producer: per work item Q once, then K / V^T boxes in exactly the order the MMA warp consumes them ----
+      int n = 0, wc = 0;    // ring position and count of non-empty work items, both run across items
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        int b, h, q0, len, J;
+        decode(w, b, h, q0, len, J);
+        if (J == 0) continue;
+        if (wc > 0) mbar_wait(q_free, (wc - 1) & 1);      // the previous item's S products are done with Q
         mbar_expect_tx(q_bar, A::Q_BYTES);
         for (int pl = 0; pl < A::P; ++pl)
           for (int c = 0; c < A::QCH; ++c)
             tma_load_3d(q_smem + (size_t)(pl * A::QCH + c) * A::Q_BOX, &tmap_qk, q_bar, h * DK + c * CH, q0, b + pl * p.B);
-        int n = 0;
         auto push_k = [&](int j) {
           for (int c = 0; c < A::QCH; ++c)
             for (int pl = 0; pl < A::P; ++pl, ++n) {
@@ -190,55 +204,67 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
         };
         push_k(0);
         for (int j = 0; j < J; ++j) { if (j + 1 < J) push_k(j + 1); push_v(j); }
+        ++wc;
       }
-    } else if (warp == 1) {
-      {  // ---- MMA issuer: all 32 lanes run the loop, one lane is elected inside each tcgen05 asm ----
-        mbar_wait(q_bar, 0);
+    }
+  } else if (warp == 1) {
+    {  // ---- MMA issuer: all 32 lanes run the loop, one lane is elected inside each tcgen05 asm ----
+      const uint32_t q_addr = smem_u32(q_smem);
+      int n = 0, wc = 0, g0 = 0;      // ring position, non-empty work items, kv tiles issued so far (all run across items)
+      auto take = [&]() -> uint64_t {   // next ring slot, as a descriptor
+        const int slot = n % A::SLOTS;
+        mbar_wait(&full_bar[slot], (n / A::SLOTS) & 1);
         tcgen05_fence_after();
-        const uint32_t q_addr = smem_u32(q_smem);
-        int n = 0;
-        auto take = [&]() -> uint64_t {   // next ring slot, as a descriptor
-          const int slot = n % A::SLOTS;
-          mbar_wait(&full_bar[slot], (n / A::SLOTS) & 1);
-          tcgen05_fence_after();
-          return make_sw128_kmajor_desc(smem_u32(ring + (size_t)slot * A::SLOT));
-        };
-        auto release = [&]() { tcgen05_commit(&empty_bar[n % A::SLOTS]); ++n; };
-        // S tile g goes to S/P buffer g & 1; S_{g+2} reuses it after P.V_g, which is issued earlier in this thread
-        auto issue_s = [&](int g) {
-          const uint32_t d = tmem_base + (uint32_t)((g & 1) * BKV);
-          for (int c = 0; c < A::QCH; ++c) {
-            const uint64_t q_hi = make_sw128_kmajor_desc(q_addr + c * A::Q_BOX);
-            const uint64_t k_hi = take();
-            if (X3) {
-              const uint64_t q_lo = make_sw128_kmajor_desc(q_addr + (A::QCH + c) * A::Q_BOX);
+        return make_sw128_kmajor_desc(smem_u32(ring + (size_t)slot * A::SLOT));
+      };
+      auto release = [&]() { tcgen05_commit(&empty_bar[n % A::SLOTS]); ++n; };
+      // S tile g goes to S/P buffer g & 1; S_{g+2} reuses it after P.V_g, which is issued earlier in this thread
+      auto issue_s = [&](int g) {
+        const uint32_t d = tmem_base + (uint32_t)((g & 1) * BKV);
+        for (int c = 0; c < A::QCH; ++c) {
+          const uint64_t q_hi = make_sw128_kmajor_desc(q_addr + c * A::Q_BOX);
+          const uint64_t k_hi = take();
+          if (X3) {
+            const uint64_t q_lo = make_sw128_kmajor_desc(q_addr + (A::QCH + c) * A::Q_BOX);
 #pragma unroll
-              for (int k = 0; k < CH / 16; ++k) {
-                umma_f16(d, q_lo + 2 * k, k_hi + 2 * k, A::IDESC_S, (c | k) != 0);
-                umma_f16(d, q_hi + 2 * k, k_hi + 2 * k, A::IDESC_S, 1);
-              }
-              release();
-              const uint64_t k_lo = take();
-#pragma unroll
-              for (int k = 0; k < CH / 16; ++k) umma_f16(d, q_hi + 2 * k, k_lo + 2 * k, A::IDESC_S, 1);
-              release();
-            } else {
-#pragma unroll
-              for (int k = 0; k < CH / 16; ++k) umma_f16(d, q_hi + 2 * k, k_hi + 2 * k, A::IDESC_S, (c | k) != 0);
-              release();
+            for (int k = 0; k < CH / 16; ++k) {
+              umma_f16(d, q_lo + 2 * k, k_hi + 2 * k, A::IDESC_S, (c | k) != 0);
+              umma_f16(d, q_hi + 2 * k, k_hi + 2 * k, A::IDESC_S, 1);
             }
+            release();
+            const uint64_t k_lo = take();
+#pragma unroll
+            for (int k = 0; k < CH / 16; ++k) umma_f16(d, q_hi + 2 * k, k_lo + 2 * k, A::IDESC_S, 1);
+            release();
+          } else {
+#pragma unroll
+            for (int k = 0; k < CH / 16; ++k) umma_f16(d, q_hi + 2 * k, k_hi + 2 * k, A::IDESC_S, (c | k) != 0);
+            release();
           }
-          tcgen05_commit(&s_full[g & 1]);
-        };
-        issue_s(0);
+        }
+        tcgen05_commit(&s_full[g & 1]);
+      };
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        int b, h, q0, len, J;
+        decode(w, b, h, q0, len, J);
+        if (J == 0) continue;
+        mbar_wait(q_bar, wc & 1);
+        tcgen05_fence_after();
+        issue_s(g0);
+        if (J == 1) tcgen05_commit(q_free);
         for (int j = 0; j < J; ++j) {
-          trace_at(p, j, 2, 0);
-          if (j + 1 < J) issue_s(j + 1);                 // the tensor core computes S_{j+1} while the softmax warps work on tile j
-          trace_at(p, j, 2, 1);
-          mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+          const int g = g0 + j;
+          if (wc == 0) trace_at(p, j, 2, 0);
+          if (j + 1 < J) {
+            issue_s(g + 1);                               // the tensor core computes S_{g+1} while the softmax warps work on tile g
+            if (j + 2 == J) tcgen05_commit(q_free);       // that was the item's last S product: Q may be overwritten once it completes
+          }
+          if (wc == 0) trace_at(p, j, 2, 1);
+          mbar_wait(&p_full[g & 1], (g >> 1) & 1);
+          if (j == 0 && wc > 0) mbar_wait(o_free, (wc - 1) & 1);   // the previous item's epilogue has read O
           tcgen05_fence_after();
-          trace_at(p, j, 2, 2);
-          const uint32_t p_hi = tmem_base + (uint32_t)((j & 1) * BKV), p_lo = p_hi + BKV / 2;   // packed fp16: 64 columns each
+          if (wc == 0) trace_at(p, j, 2, 2);
+          const uint32_t p_hi = tmem_base + (uint32_t)((g & 1) * BKV), p_lo = p_hi + BKV / 2;   // packed fp16: 64 columns each
           const uint32_t o = tmem_base + A::O_COL;
           for (int c = 0; c < BKV / CH; ++c) {
             const uint64_t v_hi = take();
@@ -259,30 +285,52 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
               release();
             }
           }
-          tcgen05_commit(&pv_done[0]);                   // lets the softmax warps rescale O if tile j+1 raises the reference max
-          trace_at(p, j, 2, 3);
+          tcgen05_commit(&pv_done[0]);                   // lets the softmax warps rescale O if tile g+1 raises the reference max
+          if (wc == 0) trace_at(p, j, 2, 3);
         }
         tcgen05_commit(o_full);
+        g0 += J; ++wc;
       }
-    } else {
-      // ---- softmax / epilogue: 8 warps; warps w and w+4 share TMEM lane quarter w%4 and split the columns ----
-      const int wq = warp & 3, half = (warp - 2) >> 2;          // half 0: columns [0,64), half 1: [64,128)
-      const int row = wq * 32 + lane;
-      const uint32_t lane_addr = tmem_base + ((uint32_t)(wq * 32) << 16);
-      float v[64];
+    }
+  } else {
+    // ---- softmax / epilogue: 8 warps; warps w and w+4 share TMEM lane quarter w%4 and split the columns ----
+    const int wq = warp & 3, half = (warp - 2) >> 2;          // half 0: columns [0,64), half 1: [64,128)
+    const int row = wq * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(wq * 32) << 16);
+    const float c_exp = p.scale_log2e;
+    const long plane = (long)p.B * p.L * p.C;
+    float v[64];
+    int wc = 0, g0 = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      int b, h, q0, len, J;
+      decode(w, b, h, q0, len, J);
+      const int t = q0 + row;
+      const bool store = t < p.L;
+      const long o_off = ((long)b * p.L + t) * p.C + h * DK + half * (DK / 2);
+      if (J == 0) {
+        // no valid key at all (len == 0): the reference's masked_fill turns the NaN rows into 0
+        if (store) {
+          if (p.ctx) for (int c = 0; c < DK / 2; c += 4) *reinterpret_cast<float4*>(p.ctx + o_off + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.ctxp) for (int c = 0; c < DK / 2; c += 8) {
+            *reinterpret_cast<uint4*>(p.ctxp + o_off + c) = make_uint4(0, 0, 0, 0);
+            if (X3) *reinterpret_cast<uint4*>(p.ctxp + plane + o_off + c) = make_uint4(0, 0, 0, 0);
+          }
+        }
+        continue;
+      }
       float m_ref = -INFINITY, l_row = 0.f;     // reference maximum (raw-score domain) and row sum relative to it
-      const float c_exp = p.scale_log2e;
       for (int j = 0; j < J; ++j) {
-        if (wq == 0) trace_at(p, j, half, 0);
-        mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+        const int g = g0 + j;
+        if (wq == 0 && wc == 0) trace_at(p, j, half, 0);
+        mbar_wait(&s_full[g & 1], (g >> 1) & 1);
         tcgen05_fence_after();
-        if (wq == 0) trace_at(p, j, half, 1);
+        if (wq == 0 && wc == 0) trace_at(p, j, half, 1);
         const int kv0 = j * BKV + half * 64;
         const bool masked = kv0 + 64 > len;                      // only the last tile of an utterance
         __syncwarp();
-        const uint32_t tb = lane_addr + (uint32_t)((j & 1) * BKV);
+        const uint32_t tb = lane_addr + (uint32_t)((g & 1) * BKV);
         tmem_ld32_nowait(tb + half * 64, v); tmem_ld32_nowait(tb + half * 64 + 32, v + 32); tmem_ld_wait_pin<64>(v);
-        if (wq == 0) trace_at(p, j, half, 2);
+        if (wq == 0 && wc == 0) trace_at(p, j, half, 2);
         float tmax = -INFINITY;
         if (masked) {
 #pragma unroll
@@ -291,17 +339,17 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
 #pragma unroll
           for (int i = 0; i < 64; ++i) tmax = fmaxf(tmax, v[i]);
         }
-        float* xr = xchg + (j & 1) * 2 * BQ;                     // double-buffered exchange: one barrier per tile
+        float* xr = xchg + (g & 1) * 2 * BQ;                     // double-buffered exchange: one barrier per tile
         xr[half * BQ + row] = tmax;
         named_bar_sync(1, 256);                                   // also: both halves of every row have read their S columns
         tmax = fmaxf(tmax, xr[(half ^ 1) * BQ + row]);           // both threads of the row now hold the tile's row maximum
-        if (wq == 0) trace_at(p, j, half, 3);
+        if (wq == 0 && wc == 0) trace_at(p, j, half, 3);
         // lazy reference update: move m_ref only if the tile exceeds it by more than 2^8 in the exp2 domain
         const bool bump = (tmax - m_ref) * c_exp > 8.0f;          // first tile: m_ref = -inf -> always
         if (__any_sync(0xffffffffu, bump)) {
           const float alpha = bump ? fast_exp2((m_ref - tmax) * c_exp) : 1.0f;   // exp2(-inf) = 0 on the first tile
-          if (j > 0) {   // O holds tiles 0..j-1: wait until P.V_{j-1} has landed, then scale this thread's half of the row
-            mbar_wait(&pv_done[0], (j - 1) & 1);
+          if (j > 0) {   // O holds tiles 0..j-1: wait until P.V_{g-1} has landed, then scale this thread's half of the row
+            mbar_wait(&pv_done[0], (g - 1) & 1);
             tcgen05_fence_after();
             float o[32];
 #pragma unroll 1
@@ -322,32 +370,34 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
         uint32_t ph[32], pl[32];
         l_row += masked ? softmax_tile<X3, true>(v, c_exp, mb, kv0, len, ph, pl) : softmax_tile<X3, false>(v, c_exp, mb, kv0, len, ph, pl);
         __syncwarp();
-        if (wq == 0) trace_at(p, j, half, 4);
+        if (wq == 0 && wc == 0) trace_at(p, j, half, 4);
         tmem_st32u(tb + half * 32, ph);                           // P hi: packed columns [0,64) of the tile's buffer
         if (X3) tmem_st32u(tb + BKV / 2 + half * 32, pl);         // P lo: [64,128)
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[j & 1]);
-        if (wq == 0) trace_at(p, j, half, 5);
+        if (lane == 0) mbar_arrive(&p_full[g & 1]);
+        if (wq == 0 && wc == 0) trace_at(p, j, half, 5);
       }
       named_bar_sync(1, 256);                                     // last exchange buffer is free again
       xchg[half * BQ + row] = l_row;
       named_bar_sync(1, 256);
       l_row += xchg[(half ^ 1) * BQ + row];
+      named_bar_sync(1, 256);                                     // both halves have read the sums before the next item's first tile reuses xchg
       // epilogue: O / l -> context rows (0 for masked query rows); each half stores DK/2 columns.  O carries V's
       // kPlaneScale: the planes take it as is, the fp32 rows divide it out.
-      mbar_wait(o_full, 0);
+      mbar_wait(o_full, wc & 1);
       tcgen05_fence_after();
-      const int t = q0 + row;
-      const bool store = t < p.L;
       const float inv = (p.lens && t >= len) ? 0.f : 1.0f / l_row;
-      const long o_off = ((long)b * p.L + t) * p.C + h * DK + half * (DK / 2);
-      const long plane = (long)p.B * p.L * p.C;
 #pragma unroll 1
       for (int c0 = 0; c0 < DK / 2; c0 += 32) {
         __syncwarp();
         tmem_ld32(lane_addr + (uint32_t)(A::O_COL + half * (DK / 2) + c0), v);
+        if (c0 + 32 >= DK / 2) {                                  // that was this warp's last read of O: the next item may overwrite it
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(o_free);
+        }
         if (!store) continue;
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] *= inv;
@@ -359,8 +409,8 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
             const __half2 hv = __floats2half2_rn(a0, a1);
             hh[i] = *reinterpret_cast<const uint32_t*>(&hv);
             if (X3) {
-              const float2 g = __half22float2(hv);
-              const __half2 lv = __floats2half2_rn(a0 - g.x, a1 - g.y);
+              const float2 gg = __half22float2(hv);
+              const __half2 lv = __floats2half2_rn(a0 - gg.x, a1 - gg.y);
               ll[i] = *reinterpret_cast<const uint32_t*>(&lv);
             }
           }
@@ -375,18 +425,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
             *reinterpret_cast<float4*>(dst + q * 4) = make_float4(v[q * 4] * kPlaneInv, v[q * 4 + 1] * kPlaneInv, v[q * 4 + 2] * kPlaneInv, v[q * 4 + 3] * kPlaneInv);
         }
       }
-    }
-  } else if (warp >= 2 && warp < 6) {
-    // no valid key at all (len == 0): the reference's masked_fill turns the NaN rows into 0
-    const int t = q0 + (warp & 3) * 32 + lane;
-    if (t < p.L) {
-      const long o_off = ((long)b * p.L + t) * p.C + h * DK;
-      const long plane = (long)p.B * p.L * p.C;
-      if (p.ctx) for (int c = 0; c < DK; c += 4) *reinterpret_cast<float4*>(p.ctx + o_off + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p.ctxp) for (int c = 0; c < DK; c += 8) {
-        *reinterpret_cast<uint4*>(p.ctxp + o_off + c) = make_uint4(0, 0, 0, 0);
-        if (X3) *reinterpret_cast<uint4*>(p.ctxp + plane + o_off + c) = make_uint4(0, 0, 0, 0);
-      }
+      g0 += J; ++wc;
     }
   }
   tcgen05_fence_before();
@@ -687,7 +726,8 @@ int launch(const __half* qkp, const __half* vtp, int lpad, const int64_t* lens, 
   p.scale_log2e = (1.0f / sqrtf((float)DK)) * 1.4426950408889634f * kPlaneInv * kPlaneInv;
   p.debug = 0;
   p.trace = att_trace_buffer();
-  dim3 grid((L + BQ - 1) / BQ, heads, B);
+  const long work = (long)B * heads * ((L + BQ - 1) / BQ);
+  const int grid = (int)(work < sm_count_current() ? work : sm_count_current());     // persistent: one CTA per SM
   attention_f16_kernel<DK, X3><<<grid, ATT_THREADS, A::SMEM, st>>>(mqk, mvt, p);
   FS2_LAUNCH_CHECK();
   if (p.trace) att_trace_dump(p.trace, (L + BKV - 1) / BKV, st);

@@ -376,6 +376,11 @@ class FeedForwardTransformer(nn.Module):
     def _forward(self, xs: torch.Tensor, ilens: torch.Tensor, olens: torch.Tensor = None, ds: torch.Tensor = None,
                  es: torch.Tensor = None, ps: torch.Tensor = None, is_inference: bool = False,
                  _one_hot: bool = True, _defer_check: Optional[list] = None) -> Sequence[torch.Tensor]:
+        # the handle-less ABI stages (LengthRegulator, losses, ...) run on the CURRENT device like any CUDA library call:
+        # select the device the data lives on for the whole call, leave the caller's current device untouched
+        if xs.is_cuda and torch.cuda.current_device() != (xs.device.index or 0):
+            with torch.cuda.device(xs.device):
+                return self._forward(xs, ilens, olens, ds, es, ps, is_inference, _one_hot, _defer_check)
         h = self._ready(xs)
         lib = _lib.load()
         dev, d = xs.device, self.dims
@@ -475,6 +480,9 @@ class FeedForwardTransformer(nn.Module):
         """Loss computation (fastspeech.py:245-337). Returns (loss, report_keys).  In train mode the loss is attached to
         the autograd graph of the train path (fastspeech2_b200/train.py) so `loss.backward()` fills `.grad` of every
         parameter the reference trains; `self.dropout_masks` (a train.MaskSource) may be set to inject masks."""
+        if xs.is_cuda and torch.cuda.current_device() != (xs.device.index or 0):
+            with torch.cuda.device(xs.device):
+                return self.forward(xs, ilens, ys, olens, ds, es, ps)
         if self.training:
             from .train import train_forward
             return train_forward(self, xs, ilens, ys, olens, ds, es, ps, masks=self.dropout_masks)

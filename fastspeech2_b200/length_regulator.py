@@ -63,6 +63,9 @@ class LengthRegulator(torch.nn.Module):
         self.pad_value = pad_value
 
     def forward(self, xs: torch.Tensor, ds: torch.Tensor, ilens: torch.Tensor, alpha: float = 1.0) -> torch.Tensor:
+        if xs.is_cuda and torch.cuda.current_device() != (xs.device.index or 0):
+            with torch.cuda.device(xs.device):      # the kernels run on the current device: select the data's
+                return self.forward(xs, ds, ilens, alpha)
         cum, _, stats, ilens_dev = plan(xs, ds, ilens, alpha)
         lmax, n_neg = stats.tolist()  # the path's single host sync
         if n_neg:

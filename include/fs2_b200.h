@@ -19,7 +19,9 @@
  *   - all work is enqueued on the `stream` argument (a cudaStream_t passed as void*);
  *     no function synchronises the device.  fs2_length_plan writes its two result words to
  *     device memory; the caller reads them back (that is the path's single host sync).
- *   - a handle is bound to one device and is not thread-safe.
+ *   - a handle is bound to one device and is not thread-safe; entry points that take a handle select its device for
+ *     the call and restore the caller's.  Handle-less entry points (LengthRegulator, losses, single operators, train /
+ *     STFT / peer kernels) run on the CURRENT device like any CUDA library call: select the device your buffers live on.
  */
 #ifndef FS2_B200_H_
 #define FS2_B200_H_

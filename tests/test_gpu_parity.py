@@ -333,6 +333,32 @@ def test_attention_vs_torch(prec, C, L, masked):
     close(ctx, want, tol, f"attention C={C} L={L} masked={masked}")
 
 
+@pytest.mark.parametrize("prec", ["3xtf32", "f16"])
+def test_attention_persistent_ctas_many_work_items(prec):
+    """The plane-family attention kernel is persistent (one CTA per SM walks (batch, head, query tile) work items with the
+    TMA / MMA warps running ahead into the next item): more items than SMs, ragged key lengths incl. an utterance with no
+    valid key at all (its rows must come out 0) and a length that ends inside a key tile."""
+    B, H, C, L = 14, 2, 384, 1000                                  # 14 * 2 * 8 = 224 work items > 148 SMs
+    g = torch.Generator().manual_seed(99)
+    qkv = torch.randn(B, L, 3 * C, generator=g)
+    lens = torch.tensor([1000, 0, 999, 130, 128, 1, 517, 1000, 64, 900, 0, 385, 1000, 257])
+    q, k, v = [t.view(B, L, H, C // H).transpose(1, 2).double() for t in qkv.split(C, dim=-1)]
+    s = q @ k.transpose(-1, -2) / (C // H) ** 0.5
+    valid = torch.arange(L)[None] < lens[:, None]
+    m = (valid[:, None, :] & valid[:, :, None])[:, None]
+    p = torch.nan_to_num(torch.softmax(s.masked_fill(~m, -float("inf")), -1)).masked_fill(~m, 0.0)
+    want = (p @ v).transpose(1, 2).reshape(B, L, C).float()
+    lib = _lib.load()
+    ctx = torch.full((B, L, C), float("nan"), device="cuda")
+    qkv_c, lens_c = qkv.cuda(), lens.cuda()
+    _lib.check(lib.fs2_op_attention(_lib.MATH_MODES[prec], _lib.ptr(qkv_c), _lib.ptr(lens_c), B, L, C, H, _lib.ptr(ctx), _lib.stream_ptr(ctx.device)),
+               "fs2_op_attention")
+    assert torch.isfinite(ctx).all()
+    tol = dict(max=5e-5, mean=5e-6) if prec == "3xtf32" else dict(max=1e-2, mean=1e-3)
+    close(ctx, want, tol, f"persistent attention {prec}")
+    assert float(ctx[1].abs().max()) == 0.0 and float(ctx[10].abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("prec", ["tf32", "f16"])
 @pytest.mark.parametrize("rows,K,with_resid", [(1000, 384, True), (51, 1024, True), (4097, 256, False)])
 def test_fused_gemm_layernorm_vs_torch(prec, rows, K, with_resid):
