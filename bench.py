@@ -364,6 +364,9 @@ def run_b200(args):
         for i in range(warmup):
             fn(i)
         barrier()
+        if args.settle_s > 0:      # both timed loops start from the same power state (the 1 kW cap is a moving average: a loop
+            time.sleep(args.settle_s)   # that follows another one back to back starts with the clocks already pulled down)
+            barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
@@ -479,7 +482,7 @@ def run_b200(args):
     if clocks is not None:
         first, second = sampler.median_between(t_begin, t_mid), sampler.median_between(t_mid, t_end)
         clocks["sm_mhz_value_loop"], clocks["sm_mhz_e2e_loop"] = (second, first) if args.e2e_first else (first, second)
-        clocks["window"] = "samples every 25 ms during the device-timed loop and the e2e loop (which run back to back; the second one sees the clocks the power cap has settled to)"
+        clocks["window"] = f"samples every 25 ms over the device-timed loop and the e2e loop; {args.settle_s} s idle before each timed loop so both start from the same power-cap state"
 
     # per-kernel-class CUDA-event profile on extra steps of the same workload
     prof = None
@@ -644,6 +647,7 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=32, help="host threads of the CPU reference (fixed; oversubscription is slower)")
     ap.add_argument("--collective", default="peer_copy", choices=["peer_copy", "all_gather", "gather"],
                     help="N>1: gather to rank 0 by copy-engine pushes over NVLink peer memory (default), or NCCL gather / all_gather")
+    ap.add_argument("--settle-s", type=float, default=0.5, help="idle seconds before every timed loop (same power-cap state for each)")
     ap.add_argument("--e2e-first", type=int, default=0, help="diagnostic: time the e2e loop before the device-resident loop")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (default), 0: eager launches")
     args = ap.parse_args()
