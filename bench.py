@@ -351,9 +351,9 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     peer, collective_note = None, None
-    if world > 1 and args.collective == "peer_copy":
+    if world > 1 and args.collective in ("peer_copy", "peer_store"):
         try:
-            peer = PeerGather((B, L, 80), dev)      # raises on ALL ranks if any rank cannot map the root's buffer
+            peer = PeerGather((B, L, 80), dev, buffers=2)      # raises on ALL ranks if any rank cannot map the root's buffer
         except Exception as e:      # no IPC / peer access on this box: say so and use the NCCL gather instead of dying
             peer = None
             args.collective = "gather"
@@ -389,16 +389,24 @@ def run_b200(args):
         """(device-resident step, end-to-end step, flush) for one model.  Graph mode: two captured graphs with their own
         static inputs / outputs alternate, so the D2H copy of step i (side stream) overlaps step i+1; the length
         validation is deferred (checked at the start of the next call), so replays queue back to back."""
-        graphs = [model.graphed_forward(*[devin[k] for k in keys]) for _ in range(2)] if args.graph else None
+        fused = peer is not None and args.collective == "peer_store" and args.graph
+        # fused exchange: the last Postnet kernel of graph i stores its mels straight into this rank's slot of the root's
+        # receive buffer i (peer-mapped over NVLink on the other ranks)
+        graphs = [model.graphed_forward(*[devin[k] for k in keys], after_out=(peer.slot(i) if fused else None)) for i in range(2)] if args.graph else None
         copied = [torch.cuda.Event(), torch.cuda.Event()]
 
         pushed = [None, None]
+        big_host = ([torch.empty((world * B, L, 80), dtype=torch.float32).pin_memory() for _ in range(2)]
+                    if (fused and rank == 0) else None)
 
         def collective(mel, i):
             if world == 1:
                 return
             # the single exchange step: gather the final mel batch over NVLink
-            if peer is not None:                # copy-engine push into the root's buffer on a side stream (csrc/peer.cu)
+            if fused:                           # the mels are already in the root's buffer: publish the step with one flag store
+                step_no[0] += 1
+                peer.signal(step_no[0])
+            elif peer is not None:              # copy-engine push into the root's buffer on a side stream (csrc/peer.cu)
                 step_no[0] += 1
                 peer.push(mel, step_no[0])
                 pushed[i & 1] = peer.pushed     # this graph's output buffer is busy until the transfer has read it
@@ -439,11 +447,17 @@ def run_b200(args):
                     inp = [up[FIELD[k]] for k in keys]
                     out = model._forward(*inp, is_inference=False)
             collective(out[1], i)
+            src, dst = out[1], mel_host[i & 1]
+            if fused:                           # the batch lives on the root only: the root reads ALL shards back, the others nothing
+                if rank != 0:
+                    return out[1]
+                peer.wait(step_no[0])           # every rank's shard of this step has landed
+                src, dst = peer.gathered_buffer(i & 1), big_host[i & 1]
             done = torch.cuda.Event()
             done.record(cur)
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(done)
-                mel_host[i & 1].copy_(out[1], non_blocking=True)
+                dst.copy_(src, non_blocking=True)
                 copied[i & 1].record(copy_stream)
             return out[1]
 
@@ -565,7 +579,7 @@ def run_b200(args):
     value = frames / (ms_step * 1e-3)
     e2e = frames / (ms_e2e * 1e-3)
     h2d = sum(host[k].numel() * host[k].element_size() for k in keys)
-    d2h = mel_host[0].numel() * 4
+    d2h = mel_host[0].numel() * 4 * (world if (peer is not None and args.collective == "peer_store" and args.graph) else 1)
     mf = mflop_per_frame(T, L)
     roof = None
     gpu_busy = None
@@ -601,6 +615,7 @@ def run_b200(args):
                                  "tf32": "decoder side on kind::tf32, encoder + predictors error-compensated",
                                  "fp32": "fp32 FMA on CUDA cores"}[args.precision],
                    "collective": ({"peer_copy": "gather to rank 0 over NVLink peer memory: one copy-engine transfer of the [B,L,80] shard per rank on a side stream + flag words (csrc/peer.cu), no SM-occupying collective kernel",
+                                   "peer_store": "gather to rank 0 fused into the last Postnet kernel: its epilogue stores the [B,L,80] mels straight into the root's receive buffer over NVLink (peer-mapped output pointer) + one flag store per step; no collective kernel, no extra transfer",
                                    "gather": "one NCCL gather of the [B,L,80] mel shard to rank 0",
                                    "all_gather": "one NCCL all-gather of the [B,L,80] mel shard"}[args.collective] if world > 1 else "none"),
                    "l2": "per-step working set ~0.9 GB of activations >> 126 MB L2; no flush needed",
@@ -645,7 +660,7 @@ def main():
     ap.add_argument("--modes", default="f16,tf32", help="N=1: other precision modes measured beside the headline ('' = none)")
     ap.add_argument("--cpu-sample-batch", type=int, default=64, help="utterances per CPU-reference step (64 = the full c2 batch)")
     ap.add_argument("--cpu-threads", type=int, default=32, help="host threads of the CPU reference (fixed; oversubscription is slower)")
-    ap.add_argument("--collective", default="peer_copy", choices=["peer_copy", "all_gather", "gather"],
+    ap.add_argument("--collective", default="peer_copy", choices=["peer_copy", "peer_store", "all_gather", "gather"],
                     help="N>1: gather to rank 0 by copy-engine pushes over NVLink peer memory (default), or NCCL gather / all_gather")
     ap.add_argument("--settle-s", type=float, default=0.5, help="idle seconds before every timed loop (same power-cap state for each)")
     ap.add_argument("--e2e-first", type=int, default=0, help="diagnostic: time the e2e loop before the device-resident loop")

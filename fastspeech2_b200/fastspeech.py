@@ -375,12 +375,12 @@ class FeedForwardTransformer(nn.Module):
     # -- the path ----------------------------------------------------------------------------
     def _forward(self, xs: torch.Tensor, ilens: torch.Tensor, olens: torch.Tensor = None, ds: torch.Tensor = None,
                  es: torch.Tensor = None, ps: torch.Tensor = None, is_inference: bool = False,
-                 _one_hot: bool = True, _defer_check: Optional[list] = None) -> Sequence[torch.Tensor]:
+                 _one_hot: bool = True, _defer_check: Optional[list] = None, _after_out: Optional[torch.Tensor] = None) -> Sequence[torch.Tensor]:
         # the handle-less ABI stages (LengthRegulator, losses, ...) run on the CURRENT device like any CUDA library call:
         # select the device the data lives on for the whole call, leave the caller's current device untouched
         if xs.is_cuda and torch.cuda.current_device() != (xs.device.index or 0):
             with torch.cuda.device(xs.device):
-                return self._forward(xs, ilens, olens, ds, es, ps, is_inference, _one_hot, _defer_check)
+                return self._forward(xs, ilens, olens, ds, es, ps, is_inference, _one_hot, _defer_check, _after_out)
         h = self._ready(xs)
         lib = _lib.load()
         dev, d = xs.device, self.dims
@@ -433,7 +433,12 @@ class FeedForwardTransformer(nn.Module):
         # stage 3: variance adaptor + decoder + postnet
         ws = self._ws(B, T, L)
         before = torch.empty((B, L, d.odim), **f32)
-        after = torch.empty((B, L, d.odim), **f32)
+        if _after_out is not None:      # caller-provided destination of the final mels, e.g. this rank's slot of the root rank's
+            after = _after_out          # receive buffer mapped over NVLink (sharded.PeerGather): the last Postnet epilogue stores there
+            if tuple(after.shape) != (B, L, d.odim) or after.dtype != torch.float32 or not after.is_contiguous():
+                raise ValueError(f"_after_out must be a contiguous float32 [{B}, {L}, {d.odim}] tensor")
+        else:
+            after = torch.empty((B, L, d.odim), **f32)
         e_out, p_out = torch.empty((B, L), **f32), torch.empty((B, L), **f32)
         want_ids = is_inference and _one_hot
         e_ids = torch.empty((B, L), dtype=torch.int64, device=dev) if want_ids else None
@@ -471,9 +476,10 @@ class FeedForwardTransformer(nn.Module):
         if chk[0] != L or chk[3] != L:
             raise RuntimeError(f"length mismatch: es/ps have Lmax={L}, max(sum(ds))={chk[0]}, max(olens)={chk[3]}")
 
-    def graphed_forward(self, xs, ilens, olens, ds, es, ps) -> "GraphedForward":
-        """Capture the teacher-forced `_forward` for these shapes into one CUDA graph (see GraphedForward)."""
-        return GraphedForward(self, xs, ilens, olens, ds, es, ps)
+    def graphed_forward(self, xs, ilens, olens, ds, es, ps, after_out: Optional[torch.Tensor] = None) -> "GraphedForward":
+        """Capture the teacher-forced `_forward` for these shapes into one CUDA graph (see GraphedForward).  `after_out`:
+        where the final mels are written (default: a fresh tensor), e.g. a peer-mapped slot of `sharded.PeerGather`."""
+        return GraphedForward(self, xs, ilens, olens, ds, es, ps, after_out=after_out)
 
     def forward(self, xs: torch.Tensor, ilens: torch.Tensor, ys: torch.Tensor, olens: torch.Tensor, ds: torch.Tensor,
                 es: torch.Tensor, ps: torch.Tensor) -> Tuple[torch.Tensor, List[Dict[str, float]]]:
@@ -537,13 +543,14 @@ class GraphedForward:
     the model's workspace cannot hand that memory to anyone else.  Weight updates require a new capture (the packed
     weight arena is part of the graph): `__call__` raises if the model was repacked or its parameters changed."""
 
-    def __init__(self, model: FeedForwardTransformer, xs, ilens, olens, ds, es, ps):
+    def __init__(self, model: FeedForwardTransformer, xs, ilens, olens, ds, es, ps, after_out: Optional[torch.Tensor] = None):
         self.model = model
+        self._after_out = after_out
         dev = xs.device
         self.inputs = [t.detach().clone().contiguous() for t in (xs, ilens.to(dev), olens.to(dev), ds, es, ps)]
         with torch.no_grad():
             for _ in range(2):                      # warm-up: packs weights, sizes the workspace, sets kernel attributes
-                model._forward(*self.inputs, is_inference=False)
+                model._forward(*self.inputs, is_inference=False, _after_out=after_out)
             torch.cuda.synchronize(dev)
             self._fingerprint = model._current_fingerprint()
             self._params = list(model._sd_cache)
@@ -552,7 +559,7 @@ class GraphedForward:
             self.graph = torch.cuda.CUDAGraph()
             deferred: list = []
             with torch.cuda.graph(self.graph):
-                self.outputs = model._forward(*self.inputs, is_inference=False, _defer_check=deferred)
+                self.outputs = model._forward(*self.inputs, is_inference=False, _defer_check=deferred, _after_out=after_out)
             self._chk, self._T, self._L = deferred[0]
         self._chk_host = torch.empty(self._chk.shape, dtype=self._chk.dtype).pin_memory()
         self._chk_event = torch.cuda.Event()

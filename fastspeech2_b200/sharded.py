@@ -96,12 +96,18 @@ class PeerGather:
 
     `push` returns immediately (the transfer runs on `pg.stream`); the source tensor must stay untouched until
     `pg.pushed` (an event recorded after the transfer) has completed.  With a non-CUDA tensor (gloo host-logic tests) the
-    class degrades to `gather_mels_to_root`."""
+    class degrades to `gather_mels_to_root`.
+
+    Fused form (no transfer at all): `pg.slot(i)` is this rank's shard of receive buffer `i` as a tensor -- on non-root
+    ranks a view of the ROOT's memory mapped over NVLink.  Passed as the output of the last Postnet kernel
+    (`model.graphed_forward(..., after_out=pg.slot(i))`), that kernel's epilogue stores the mels straight into the root's
+    buffer tile by tile while it computes; `pg.signal(step)` then publishes the step with one flag store.  `buffers` > 1
+    gives that many receive buffers (alternating CUDA graphs write alternating buffers)."""
 
     HEADER = 256          # bytes reserved for the flag words in front of the shards
 
-    def __init__(self, shard_shape, device, dtype=torch.float32, root: int = 0, group: Optional[dist.ProcessGroup] = None):
-        self.group, self.root = group, root
+    def __init__(self, shard_shape, device, dtype=torch.float32, root: int = 0, group: Optional[dist.ProcessGroup] = None, buffers: int = 1):
+        self.group, self.root, self.buffers, self.dtype = group, root, max(1, int(buffers)), dtype
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.shape = tuple(int(v) for v in shard_shape)
         self.device = torch.device(device)
@@ -117,7 +123,7 @@ class PeerGather:
         for v in self.shape:
             n *= v
         self.shard_bytes = n * torch.empty((), dtype=dtype).element_size()
-        total = self.HEADER + self.world * self.shard_bytes
+        total = self.HEADER + self.buffers * self.world * self.shard_bytes
         assert self.world * 8 <= self.HEADER
         handle = (C.c_char * 64)()
         ptr = C.c_void_p()
@@ -150,8 +156,29 @@ class PeerGather:
         self._data = self._base + self.HEADER
         self.stream = torch.cuda.Stream(self.device)
         if self.rank == root:
-            raw = torch.as_tensor(_RawCudaBuffer(self._data, self.world * self.shard_bytes), device=self.device)
-            self.gathered = raw.view(dtype).view((self.world * self.shape[0],) + self.shape[1:])
+            raw = torch.as_tensor(_RawCudaBuffer(self._data, self.buffers * self.world * self.shard_bytes), device=self.device)
+            self._all = raw.view(dtype).view((self.buffers, self.world * self.shape[0]) + self.shape[1:])
+            self.gathered = self._all[0]
+
+    def slot(self, buffer: int = 0) -> torch.Tensor:
+        """This rank's shard of receive buffer `buffer` as a [B, L, odim] tensor (root: local memory; other ranks: the
+        root's memory mapped over NVLink -- stores to it travel as peer writes)."""
+        if not self._cuda or self.world == 1:
+            raise RuntimeError("PeerGather.slot needs the CUDA / multi-rank form")
+        off = self._data + (buffer * self.world + self.rank) * self.shard_bytes
+        raw = torch.as_tensor(_RawCudaBuffer(off, self.shard_bytes), device=self.device)
+        return raw.view(self.dtype).view(self.shape)
+
+    def gathered_buffer(self, buffer: int = 0) -> Optional[torch.Tensor]:
+        return self._all[buffer] if (self._cuda and self.world > 1 and self.rank == self.root) else self.gathered
+
+    def signal(self, step: int) -> None:
+        """Fused form: everything this rank stored into its slot on the current stream is complete -> publish `step`."""
+        if not self._cuda or self.world == 1 or self.rank == self.root:
+            return
+        from . import _lib
+        cur = torch.cuda.current_stream(self.device)
+        _lib.check(self._lib.fs2_flag_signal(self._flags + 8 * self.rank, int(step), cur.cuda_stream), "fs2_flag_signal")
 
     def push(self, mel: torch.Tensor, step: int) -> None:
         if not self._cuda or self.world == 1:
