@@ -410,6 +410,8 @@ def run_b200(args):
                 step_no[0] += 1
                 peer.push(mel, step_no[0])
                 pushed[i & 1] = peer.pushed     # this graph's output buffer is busy until the transfer has read it
+            elif args.collective == "none":     # diagnostic: no exchange at all (what N independent replicas cost under max-over-ranks timing)
+                pass
             elif args.collective == "gather":   # NCCL: rank 0 receives everything, the others only send their shard
                 gather_mels_to_root(mel, dst=0, out=gathered if rank == 0 else None)
             else:                               # NCCL all-gather: every rank receives every shard
@@ -617,7 +619,8 @@ def run_b200(args):
                    "collective": ({"peer_copy": "gather to rank 0 over NVLink peer memory: one copy-engine transfer of the [B,L,80] shard per rank on a side stream + flag words (csrc/peer.cu), no SM-occupying collective kernel",
                                    "peer_store": "gather to rank 0 fused into the last Postnet kernel: its epilogue stores the [B,L,80] mels straight into the root's receive buffer over NVLink (peer-mapped output pointer) + one flag store per step; no collective kernel, no extra transfer",
                                    "gather": "one NCCL gather of the [B,L,80] mel shard to rank 0",
-                                   "all_gather": "one NCCL all-gather of the [B,L,80] mel shard"}[args.collective] if world > 1 else "none"),
+                                   "all_gather": "one NCCL all-gather of the [B,L,80] mel shard",
+                                   "none": "DIAGNOSTIC: no exchange step (independent replicas; not a valid multi-GPU number)"}[args.collective] if world > 1 else "none"),
                    "l2": "per-step working set ~0.9 GB of activations >> 126 MB L2; no flush needed",
                    "tolerance": "3xf16 (default): max-abs 1e-4, mean-abs 1e-5 vs the CPU fp32 oracle on the mels, durations / bucket ids bit-exact; "
                                 "fp32: 1e-4; f16: 5e-3 / 5e-4; tf32: 1e-2 / 1e-3 (tests/test_gpu_parity.py)"},
@@ -660,7 +663,7 @@ def main():
     ap.add_argument("--modes", default="f16,tf32", help="N=1: other precision modes measured beside the headline ('' = none)")
     ap.add_argument("--cpu-sample-batch", type=int, default=64, help="utterances per CPU-reference step (64 = the full c2 batch)")
     ap.add_argument("--cpu-threads", type=int, default=32, help="host threads of the CPU reference (fixed; oversubscription is slower)")
-    ap.add_argument("--collective", default="peer_copy", choices=["peer_copy", "peer_store", "all_gather", "gather"],
+    ap.add_argument("--collective", default="peer_copy", choices=["peer_copy", "peer_store", "all_gather", "gather", "none"],
                     help="N>1: gather to rank 0 by copy-engine pushes over NVLink peer memory (default), or NCCL gather / all_gather")
     ap.add_argument("--settle-s", type=float, default=0.5, help="idle seconds before every timed loop (same power-cap state for each)")
     ap.add_argument("--e2e-first", type=int, default=0, help="diagnostic: time the e2e loop before the device-resident loop")
