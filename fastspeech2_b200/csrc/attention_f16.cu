@@ -437,6 +437,380 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Q resident in TMEM (experiment, FS2_ATT_QT=1).  In the kernel above an S = Q K^T instruction streams BOTH operands from
+// shared memory (4 KB + 4 KB per 64 cycles at M = N = 128): the clock64 trace shows S issue at ~1.6x its tensor time while
+// P.V (A operand = P in TMEM) runs at its tensor time.  Here Q is copied shared -> TMEM once per work item (tcgen05.cp,
+// in issue order with the MMAs) and every S product reads only K from shared memory.  TMEM budget with fp32 S / O:
+//   Q hi (DK/2 columns) [+ Q lo] | S0 | S1 | O (DK columns)  ->  64 keys per step (3xF16: 192 + 2 x 64 + 192 = 512 exactly).
+// Shared memory is one ring of DK x 128-byte slots: Q chunks pass through it like K / V^T tiles.  Persistent CTAs, warp
+// roles and softmax as above (two threads per query row, 32 score columns each).
+constexpr int BKVQ = 64;
+
+template <int DK, bool X3>
+struct QCfg {
+  static constexpr int P = X3 ? 2 : 1;
+  static constexpr int QCH = DK / CH;
+  static constexpr int Q_BOX = BQ * 128;                 // 16 KB: 128 query rows x 64 dk
+  static constexpr int K_CHUNK = BKVQ * 128;             // 8 KB: 64 keys x 64 dk
+  static constexpr int SLOT = DK * 128;                  // K step = QCH chunks; V^T step = DK rows x 64 keys; one Q chunk fits too
+  static constexpr int SLOTS_MAX = (222 * 1024) / SLOT;
+  static constexpr int SLOTS = SLOTS_MAX > 12 ? 12 : SLOTS_MAX;
+  static constexpr size_t SMEM = (size_t)SLOTS * SLOT + 1024 + 512 + 4 * BQ * 4;
+  static constexpr uint32_t IDESC_S = idesc_f16(BQ, BKVQ);
+  static constexpr uint32_t IDESC_O = idesc_f16(BQ, DK);
+  static constexpr int Q_COLS = DK / 2;                  // packed fp16
+  static constexpr int QH_COL = 0, QL_COL = Q_COLS;
+  static constexpr int S_COL0 = P * Q_COLS;              // two S/P buffers of 64 columns
+  static constexpr int O_COL = S_COL0 + 2 * BKVQ;
+  static constexpr int TMEM_COLS = 512;
+  static_assert(O_COL + DK <= 512, "TMEM budget");
+  static_assert(Q_BOX <= SLOT && QCH * K_CHUNK == SLOT && SLOT % 1024 == 0 && SLOTS >= 6, "ring");
+};
+
+template <int DK, bool X3>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_qt_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                    const __grid_constant__ CUtensorMap tmap_vt, HParams p) {
+  using A = QCfg<DK, X3>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)A::SLOTS * A::SLOT);
+  uint64_t* full_bar = bars;                   // [SLOTS]
+  uint64_t* empty_bar = bars + A::SLOTS;       // [SLOTS]
+  uint64_t* s_full = bars + 2 * A::SLOTS;      // [2] MMA -> softmax: S tile ready
+  uint64_t* pv_done = s_full + 2;              // MMA -> softmax: P.V of the previous step has finished
+  uint64_t* p_full = pv_done + 2;              // [2] softmax -> MMA: P written
+  uint64_t* o_full = p_full + 2;               // MMA -> epilogue
+  uint64_t* o_free = o_full + 1;               // epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
+  float* xchg = reinterpret_cast<float*>(tmem_slot + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nq = (p.L + BQ - 1) / BQ;
+  const int total_work = p.B * p.heads * nq;
+  auto decode = [&](int w, int& b, int& h, int& q0, int& len, int& J) {
+    const int qt = w % nq; const int bh = w / nq;
+    h = bh % p.heads; b = bh / p.heads; q0 = qt * BQ;
+    len = p.lens ? (int)min((long)p.lens[b], (long)p.L) : p.L;
+    J = (len + BKVQ - 1) / BKVQ;
+  };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < A::SLOTS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&pv_done[i], 1); mbar_init(&p_full[i], 8); }
+    mbar_init(o_full, 1); mbar_init(o_free, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, A::TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---- TMA producer: per work item the Q chunks, then K_0, [K_{j+1}, V_j] ... in consumption order ----
+      int n = 0;
+      auto slot_for = [&](uint32_t bytes) -> uint8_t* {
+        const int slot = n % A::SLOTS;
+        mbar_wait(&empty_bar[slot], ((n / A::SLOTS) & 1) ^ 1);
+        mbar_expect_tx(&full_bar[slot], bytes);
+        return ring + (size_t)slot * A::SLOT;
+      };
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        int b, h, q0, len, J;
+        decode(w, b, h, q0, len, J);
+        if (J == 0) continue;
+        for (int pl = 0; pl < A::P; ++pl)
+          for (int c = 0; c < A::QCH; ++c, ++n) {
+            uint8_t* dst = slot_for(A::Q_BOX);
+            tma_load_3d(dst, &tmap_q, &full_bar[n % A::SLOTS], h * DK + c * CH, q0, b + pl * p.B);
+          }
+        auto push_k = [&](int j) {
+          for (int pl = 0; pl < A::P; ++pl, ++n) {
+            uint8_t* dst = slot_for(A::SLOT);
+            for (int c = 0; c < A::QCH; ++c)
+              tma_load_3d(dst + (size_t)c * A::K_CHUNK, &tmap_k, &full_bar[n % A::SLOTS], p.C + h * DK + c * CH, j * BKVQ, b + pl * p.B);
+          }
+        };
+        auto push_v = [&](int j) {
+          for (int pl = 0; pl < A::P; ++pl, ++n) {
+            uint8_t* dst = slot_for(A::SLOT);
+            tma_load_3d(dst, &tmap_vt, &full_bar[n % A::SLOTS], j * BKVQ, 0, b * p.heads + h + pl * p.B * p.heads);
+          }
+        };
+        push_k(0);
+        for (int j = 0; j < J; ++j) { if (j + 1 < J) push_k(j + 1); push_v(j); }
+      }
+    }
+  } else if (warp == 1) {
+    {  // ---- MMA issuer ----
+      int n = 0, wc = 0, g0 = 0;
+      auto take = [&]() -> uint32_t {
+        const int slot = n % A::SLOTS;
+        mbar_wait(&full_bar[slot], (n / A::SLOTS) & 1);
+        tcgen05_fence_after();
+        return smem_u32(ring + (size_t)slot * A::SLOT);
+      };
+      auto release = [&]() { tcgen05_commit(&empty_bar[n % A::SLOTS]); ++n; };
+      const uint32_t qh = tmem_base + A::QH_COL, ql = tmem_base + A::QL_COL;
+      auto issue_s = [&](int g) {
+        const uint32_t d = tmem_base + (uint32_t)(A::S_COL0 + (g & 1) * BKVQ);
+        const uint32_t khi = take();
+#pragma unroll
+        for (int c = 0; c < A::QCH; ++c) {
+          const uint64_t kd = make_sw128_kmajor_desc(khi + c * A::K_CHUNK);
+#pragma unroll
+          for (int k = 0; k < CH / 16; ++k) {
+            if (X3) {
+              umma_f16_ts(d, ql + (c * 4 + k) * 8, kd + 2 * k, A::IDESC_S, (c | k) != 0);
+              umma_f16_ts(d, qh + (c * 4 + k) * 8, kd + 2 * k, A::IDESC_S, 1);
+            } else {
+              umma_f16_ts(d, qh + (c * 4 + k) * 8, kd + 2 * k, A::IDESC_S, (c | k) != 0);
+            }
+          }
+        }
+        release();
+        if (X3) {
+          const uint32_t klo = take();
+#pragma unroll
+          for (int c = 0; c < A::QCH; ++c) {
+            const uint64_t kd = make_sw128_kmajor_desc(klo + c * A::K_CHUNK);
+#pragma unroll
+            for (int k = 0; k < CH / 16; ++k) umma_f16_ts(d, qh + (c * 4 + k) * 8, kd + 2 * k, A::IDESC_S, 1);
+          }
+          release();
+        }
+        tcgen05_commit(&s_full[g & 1]);
+      };
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        int b, h, q0, len, J;
+        decode(w, b, h, q0, len, J);
+        if (J == 0) continue;
+        // Q: shared -> TMEM, 4 x (128 rows x 32 bytes) per 64-dk chunk; ordered after the previous item's S products by issue order
+        for (int pl = 0; pl < A::P; ++pl)
+          for (int c = 0; c < A::QCH; ++c) {
+            const uint64_t qd = make_sw128_kmajor_desc(take());
+#pragma unroll
+            for (int k = 0; k < CH / 16; ++k) tmem_cp_128x256b((pl ? ql : qh) + (c * 4 + k) * 8, qd + 2 * k);
+            release();
+          }
+        issue_s(g0);
+        for (int j = 0; j < J; ++j) {
+          const int g = g0 + j;
+          if (wc == 0) trace_at(p, j, 2, 0);
+          if (j + 1 < J) issue_s(g + 1);
+          if (wc == 0) trace_at(p, j, 2, 1);
+          mbar_wait(&p_full[g & 1], (g >> 1) & 1);
+          if (j == 0 && wc > 0) mbar_wait(o_free, (wc - 1) & 1);
+          tcgen05_fence_after();
+          if (wc == 0) trace_at(p, j, 2, 2);
+          const uint32_t p_hi = tmem_base + (uint32_t)(A::S_COL0 + (g & 1) * BKVQ), p_lo = p_hi + BKVQ / 2;
+          const uint32_t o = tmem_base + A::O_COL;
+          const uint64_t vhi = make_sw128_kmajor_desc(take());
+#pragma unroll
+          for (int k = 0; k < BKVQ / 16; ++k) {
+            if (X3) {
+              umma_f16_ts(o, p_lo + k * 8, vhi + 2 * k, A::IDESC_O, (j | k) != 0);
+              umma_f16_ts(o, p_hi + k * 8, vhi + 2 * k, A::IDESC_O, 1);
+            } else {
+              umma_f16_ts(o, p_hi + k * 8, vhi + 2 * k, A::IDESC_O, (j | k) != 0);
+            }
+          }
+          release();
+          if (X3) {
+            const uint64_t vlo = make_sw128_kmajor_desc(take());
+#pragma unroll
+            for (int k = 0; k < BKVQ / 16; ++k) umma_f16_ts(o, p_hi + k * 8, vlo + 2 * k, A::IDESC_O, 1);
+            release();
+          }
+          tcgen05_commit(&pv_done[0]);
+          if (wc == 0) trace_at(p, j, 2, 3);
+        }
+        tcgen05_commit(o_full);
+        g0 += J; ++wc;
+      }
+    }
+  } else {
+    // ---- softmax / epilogue: 8 warps; warps w and w+4 share TMEM lane quarter w%4; each thread owns 32 score columns ----
+    const int wq = warp & 3, half = (warp - 2) >> 2;
+    const int row = wq * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(wq * 32) << 16);
+    const float c_exp = p.scale_log2e;
+    const long plane = (long)p.B * p.L * p.C;
+    float v[32];
+    int wc = 0, g0 = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      int b, h, q0, len, J;
+      decode(w, b, h, q0, len, J);
+      const int t = q0 + row;
+      const bool store = t < p.L;
+      const long o_off = ((long)b * p.L + t) * p.C + h * DK + half * (DK / 2);
+      if (J == 0) {
+        if (store) {
+          if (p.ctx) for (int c = 0; c < DK / 2; c += 4) *reinterpret_cast<float4*>(p.ctx + o_off + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.ctxp) for (int c = 0; c < DK / 2; c += 8) {
+            *reinterpret_cast<uint4*>(p.ctxp + o_off + c) = make_uint4(0, 0, 0, 0);
+            if (X3) *reinterpret_cast<uint4*>(p.ctxp + plane + o_off + c) = make_uint4(0, 0, 0, 0);
+          }
+        }
+        continue;
+      }
+      float m_ref = -INFINITY, l_row = 0.f;
+      for (int j = 0; j < J; ++j) {
+        const int g = g0 + j;
+        if (wq == 0 && wc == 0) trace_at(p, j, half, 0);
+        mbar_wait(&s_full[g & 1], (g >> 1) & 1);
+        tcgen05_fence_after();
+        if (wq == 0 && wc == 0) trace_at(p, j, half, 1);
+        const int kv0 = j * BKVQ + half * 32;
+        const bool masked = kv0 + 32 > len;
+        __syncwarp();
+        const uint32_t tb = lane_addr + (uint32_t)(A::S_COL0 + (g & 1) * BKVQ);
+        tmem_ld32(tb + half * 32, v);
+        if (wq == 0 && wc == 0) trace_at(p, j, half, 2);
+        float t0 = -INFINITY, t1 = -INFINITY;
+        if (masked) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (kv0 + i < len) t0 = fmaxf(t0, v[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { t0 = fmaxf(t0, v[i]); t1 = fmaxf(t1, v[16 + i]); }
+        }
+        float tmax = fmaxf(t0, t1);
+        float* xr = xchg + (g & 1) * 2 * BQ;
+        xr[half * BQ + row] = tmax;
+        named_bar_sync(1, 256);
+        tmax = fmaxf(tmax, xr[(half ^ 1) * BQ + row]);
+        if (wq == 0 && wc == 0) trace_at(p, j, half, 3);
+        const bool bump = (tmax - m_ref) * c_exp > 8.0f;
+        if (__any_sync(0xffffffffu, bump)) {
+          const float alpha = bump ? fast_exp2((m_ref - tmax) * c_exp) : 1.0f;
+          if (j > 0) {
+            mbar_wait(&pv_done[0], (g - 1) & 1);
+            tcgen05_fence_after();
+            float o[32];
+#pragma unroll 1
+            for (int c0 = 0; c0 < DK / 2; c0 += 32) {
+              const uint32_t oa = lane_addr + (uint32_t)(A::O_COL + half * (DK / 2) + c0);
+              __syncwarp();
+              tmem_ld32(oa, o);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] *= alpha;
+              tmem_st32(oa, o);
+            }
+            tmem_st_wait();
+          }
+          l_row *= alpha;
+          if (bump) m_ref = tmax;
+        }
+        const float mb = m_ref * c_exp;
+        uint32_t ph[16], pl[16];
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float e0 = fast_exp2(fmaf(v[2 * i], c_exp, -mb)), e1 = fast_exp2(fmaf(v[2 * i + 1], c_exp, -mb));
+          if (masked) { if (kv0 + 2 * i >= len) e0 = 0.f; if (kv0 + 2 * i + 1 >= len) e1 = 0.f; }
+          const __half2 hh = __floats2half2_rn(e0, e1);
+          ph[i] = *reinterpret_cast<const uint32_t*>(&hh);
+          const float2 gg = __half22float2(hh);
+          if (X3) {
+            const __half2 lo2 = __floats2half2_rn(e0 - gg.x, e1 - gg.y);
+            pl[i] = *reinterpret_cast<const uint32_t*>(&lo2);
+            s0 += e0; s1 += e1;
+          } else { s0 += gg.x; s1 += gg.y; }
+        }
+        l_row += s0 + s1;
+        __syncwarp();
+        if (wq == 0 && wc == 0) trace_at(p, j, half, 4);
+        tmem_st16(tb + half * 16, ph);                          // P hi: packed columns [0,32) of the step's S buffer
+        if (X3) tmem_st16(tb + BKVQ / 2 + half * 16, pl);        // P lo: [32,64)
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[g & 1]);
+        if (wq == 0 && wc == 0) trace_at(p, j, half, 5);
+      }
+      named_bar_sync(1, 256);
+      xchg[half * BQ + row] = l_row;
+      named_bar_sync(1, 256);
+      l_row += xchg[(half ^ 1) * BQ + row];
+      named_bar_sync(1, 256);
+      mbar_wait(o_full, wc & 1);
+      tcgen05_fence_after();
+      const float inv = (p.lens && t >= len) ? 0.f : 1.0f / l_row;
+#pragma unroll 1
+      for (int c0 = 0; c0 < DK / 2; c0 += 32) {
+        __syncwarp();
+        tmem_ld32(lane_addr + (uint32_t)(A::O_COL + half * (DK / 2) + c0), v);
+        if (c0 + 32 >= DK / 2) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(o_free);
+        }
+        if (!store) continue;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= inv;
+        if (p.ctxp != nullptr) {
+          uint32_t hh[16], ll[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float a0 = fminf(fmaxf(v[2 * i], -65504.f), 65504.f), a1 = fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f);
+            const __half2 hv = __floats2half2_rn(a0, a1);
+            hh[i] = *reinterpret_cast<const uint32_t*>(&hv);
+            if (X3) {
+              const float2 gg = __half22float2(hv);
+              const __half2 lv = __floats2half2_rn(a0 - gg.x, a1 - gg.y);
+              ll[i] = *reinterpret_cast<const uint32_t*>(&lv);
+            }
+          }
+          __half* dh = p.ctxp + o_off + c0;
+          st_global_v8_b32(dh, hh); st_global_v8_b32(dh + 16, hh + 8);
+          if (X3) { st_global_v8_b32(dh + plane, ll); st_global_v8_b32(dh + plane + 16, ll + 8); }
+        }
+        if (p.ctx != nullptr) {
+          float* dst = p.ctx + o_off + c0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(dst + q * 4) = make_float4(v[q * 4] * kPlaneInv, v[q * 4 + 1] * kPlaneInv, v[q * 4 + 2] * kPlaneInv, v[q * 4 + 3] * kPlaneInv);
+        }
+      }
+      g0 += J; ++wc;
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, A::TMEM_COLS);
+  }
+}
+
+template <int DK, bool X3>
+int launch_qt(const __half* qkp, const __half* vtp, int lpad, const int64_t* lens, int B, int L, int C, int heads, float* ctx,
+              __half* ctxp, cudaStream_t st) {
+  using A = QCfg<DK, X3>;
+  static unsigned long long configured = 0;
+  int rc;
+  if ((rc = ensure_smem_attr(attention_qt_kernel<DK, X3>, A::SMEM, &configured))) return rc;
+  CUtensorMap mq, mk, mvt;
+  const uint64_t row = (uint64_t)2 * C * 2;
+  if ((rc = make_map(&mq, qkp, (uint64_t)2 * C, L, (uint64_t)B * A::P, row, row * L, BQ, true))) return rc;
+  if ((rc = make_map(&mk, qkp, (uint64_t)2 * C, L, (uint64_t)B * A::P, row, row * L, BKVQ, true))) return rc;
+  if ((rc = make_map(&mvt, vtp, L, DK, (uint64_t)B * heads * A::P, (uint64_t)lpad * 2, (uint64_t)lpad * 2 * DK, DK, true))) return rc;
+  HParams p;
+  p.lens = lens; p.B = B; p.L = L; p.C = C; p.heads = heads; p.ctx = ctx; p.ctxp = ctxp;
+  p.scale_log2e = (1.0f / sqrtf((float)DK)) * 1.4426950408889634f * kPlaneInv * kPlaneInv;
+  p.debug = 0;
+  p.trace = att_trace_buffer();
+  const long work = (long)B * heads * ((L + BQ - 1) / BQ);
+  const int grid = (int)(work < sm_count_current() ? work : sm_count_current());
+  attention_qt_kernel<DK, X3><<<grid, ATT_THREADS, A::SMEM, st>>>(mq, mk, mvt, p);
+  FS2_LAUNCH_CHECK();
+  if (p.trace) att_trace_dump(p.trace, (L + BKVQ - 1) / BKVQ, st);
+  return FS2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // F16, two query tiles in flight per CTA (FS2_MATH_F16's decoder): the single-tile kernel above leaves the tensor pipe idle
 // while a tile's softmax runs (S -> exp2 -> P -> P.V is one dependency chain per tile; profiles/r01_ncu_attn_tf32_v18.md:
 // tensor pipe 33 % active).  Here a CTA owns TWO 128-query tiles A and B of the same (batch, head), each with its own S/P
@@ -773,6 +1147,12 @@ int attention_planes(const __half* qkp, const __half* vtp, int lpad, const int64
   FS2_REQUIRE(!ctxp || ((reinterpret_cast<uintptr_t>(ctxp) & 31) == 0 && (((long)B * L * C) % 16) == 0), "attention_planes: context planes must be 32-byte aligned");
   if (B == 0 || L == 0) return FS2_OK;
   const int dk = C / heads;
+  {
+    static int use_qt = -1;   // FS2_ATT_QT=1 (experiment): Q resident in TMEM, 64 keys per step
+    if (use_qt < 0) { const char* e = getenv("FS2_ATT_QT"); use_qt = e ? atoi(e) : 0; }
+    if (use_qt && dk == 192) return x3 ? launch_qt<192, true>(qkp, vtp, lpad, lens, B, L, C, heads, ctx, ctxp, st) : launch_qt<192, false>(qkp, vtp, lpad, lens, B, L, C, heads, ctx, ctxp, st);
+    if (use_qt && dk == 128) return x3 ? launch_qt<128, true>(qkp, vtp, lpad, lens, B, L, C, heads, ctx, ctxp, st) : launch_qt<128, false>(qkp, vtp, lpad, lens, B, L, C, heads, ctx, ctxp, st);
+  }
   if (!x3) {
     // FS2_ATT_X2=1 (experiment): the two-tile kernel.  Measured slower than the single-tile one (c2: 0.50 vs 0.42 ms per
     // step, c4: 1.09 vs 0.77, profiles/r02_attention_ab.md): with 64 keys per step it pays twice the softmax <-> MMA
