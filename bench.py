@@ -663,8 +663,9 @@ def main():
     ap.add_argument("--modes", default="f16,tf32", help="N=1: other precision modes measured beside the headline ('' = none)")
     ap.add_argument("--cpu-sample-batch", type=int, default=64, help="utterances per CPU-reference step (64 = the full c2 batch)")
     ap.add_argument("--cpu-threads", type=int, default=32, help="host threads of the CPU reference (fixed; oversubscription is slower)")
-    ap.add_argument("--collective", default="peer_copy", choices=["peer_copy", "peer_store", "all_gather", "gather", "none"],
-                    help="N>1: gather to rank 0 by copy-engine pushes over NVLink peer memory (default), or NCCL gather / all_gather")
+    ap.add_argument("--collective", default="peer_store", choices=["peer_store", "peer_copy", "all_gather", "gather", "none"],
+                    help="N>1 exchange step: peer_store = the last Postnet kernel stores the mels straight into rank 0's receive buffer over "
+                         "NVLink (default); peer_copy = one copy-engine push per rank on a side stream; gather / all_gather = NCCL; none = diagnostic")
     ap.add_argument("--settle-s", type=float, default=0.5, help="idle seconds before every timed loop (same power-cap state for each)")
     ap.add_argument("--e2e-first", type=int, default=0, help="diagnostic: time the e2e loop before the device-resident loop")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (default), 0: eager launches")
