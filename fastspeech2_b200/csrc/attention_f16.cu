@@ -146,7 +146,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_free + 1);
   float* xchg = reinterpret_cast<float*>(tmem_slot + 4);   // [2 tiles][2 halves][BQ] row-statistic exchange between column halves
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   // Persistent CTA: work item w = ((b * heads + h) * nq + qt), taken round-robin.  The TMA producer and the MMA warp run
   // ahead into the next item (its Q lands while the current item's last softmax / P.V / epilogue are still running), so
   // the 2-3 us cold-start of a tile (Q + first K over TMA, first S) is paid once per CTA instead of once per tile.
@@ -485,7 +485,7 @@ attention_qt_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
   float* xchg = reinterpret_cast<float*>(tmem_slot + 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int nq = (p.L + BQ - 1) / BQ;
   const int total_work = p.B * p.heads * nq;
   auto decode = [&](int w, int& b, int& h, int& q0, int& len, int& J) {
@@ -859,7 +859,7 @@ attention_f16x2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
   uint64_t* pv_done = p_full + 2;              // [2] MMA -> softmax X: P.V of the previous step has finished (O may be rescaled)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 2 * BQ, h = blockIdx.y, b = blockIdx.z;
   const int len = p.lens ? (int)min((long)p.lens[b], (long)p.L) : p.L;
   const int J = (len + BKV2 - 1) / BKV2;

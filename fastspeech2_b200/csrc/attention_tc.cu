@@ -72,7 +72,7 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
   float* xchg = reinterpret_cast<float*>(tmem_slot + 4);   // [2 tiles][2 halves][BQ] row-statistic exchange between column halves
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
   const int len = p.lens ? (int)min((long)p.lens[b], (long)p.L) : p.L;   // keys >= len are masked
   const int J = (len + BKV - 1) / BKV;                                   // kv tiles that contain valid keys

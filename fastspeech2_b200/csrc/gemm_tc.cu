@@ -130,7 +130,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   uint64_t* acc_empty = acc_full + 4;             // [NACC] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int kchunks = (p.K + C::BKE - 1) / C::BKE;
   const int steps = p.taps * kchunks;
   const int total_tiles = p.m_tiles * p.n_tiles;

@@ -27,13 +27,32 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
+// Bounded wait, written as ONE asm block with its own loop: a C++ loop around try_wait makes the compiler treat everything
+// after it as divergent, so descriptors and loop counters of the (warp-uniform) MMA / TMA issue loops end up in vector
+// registers and every tcgen05.mma operand costs an R2UR.  try_wait suspends for a HW-defined time slice; 1 << 22 slices is
+// seconds -- far beyond any legal wait: a pipeline bug traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  // try_wait suspends for a HW-defined time slice; 1<<22 slices is seconds -- far beyond any legal wait
-  for (uint32_t spin = 0; spin < (1u << 22); ++spin)
-    if (mbar_try_wait(bar, parity)) return;
-  printf("fs2 tcgen05 kernel: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
-  __trap();
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .u32 cnt;\n\t"
+      "mov.u32 cnt, 0;\n"
+      "FS2_WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "@p bra FS2_WAIT_DONE;\n\t"
+      "add.u32 cnt, cnt, 1;\n\t"
+      "setp.lt.u32 q, cnt, 4194304;\n\t"
+      "@q bra FS2_WAIT_LOOP;\n"
+      "FS2_WAIT_DONE:\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  if (!ok) {
+    printf("fs2 tcgen05 kernel: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+    __trap();
+  }
 }
+// warp index as a value the compiler can prove warp-uniform (so branches on it and everything computed under them can use the
+// uniform datapath)
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
