@@ -56,6 +56,39 @@ def main():
             err = float((got - want).abs()[valid].max())
             print(f"sharded[{prec}]: max-abs err vs per-shard oracle {err:.3e}", flush=True)
             ok = ok and err <= tol
+    # fused exchange step: every rank's teacher-forced forward writes its mels straight into the root's receive buffer
+    # (peer-mapped output pointer of the last Postnet kernel), then publishes the step with a flag store; the root's view
+    # must equal what an NCCL all-gather of locally computed mels delivers, bit for bit
+    from fastspeech2_b200.sharded import PeerGather
+    from fastspeech2_b200.synthetic import make_batch
+    m = FeedForwardTransformer(68, 80, load_hp())
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dev).eval()
+    B, T, L = 3, 25, 210
+    bt = make_batch(B, T, L, seed=900 + rank)
+    args = [bt[k].to(dev) for k in ("xs", "ilens", "olens", "ds", "es", "ps")]
+    pg = PeerGather((B, L, 80), dev, buffers=2)
+    with torch.no_grad():
+        local = m._forward(*args, is_inference=False)[1].clone()
+        for step, buf in ((1, 0), (2, 1), (3, 0)):
+            out = m._forward(*args, is_inference=False, _after_out=pg.slot(buf))[1]
+            assert out.data_ptr() == pg.slot(buf).data_ptr()
+            pg.signal(step)
+            pg.wait(step)
+            both = torch.empty((world * B, L, 80), device=dev)
+            dist.all_gather_into_tensor(both, local)
+            torch.cuda.synchronize()
+            if rank == 0:
+                assert torch.equal(pg.gathered_buffer(buf), both), f"fused gather differs at step {step}"
+        g = m.graphed_forward(*args, after_out=pg.slot(0))          # and through a captured graph
+        g(*args)
+        pg.signal(4); pg.wait(4)
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            assert torch.equal(pg.gathered_buffer(0), both)
+            print("fused peer_store gather: bit-identical to all_gather of local results", flush=True)
+    pg.close()
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
