@@ -118,6 +118,13 @@ struct DeviceGuard {
   DeviceGuard _guard((h)->device);                                                       \
   if (!_guard.ok) { set_error("cannot select device %d", (h)->device); return FS2_ERR_CUDA; }
 
+// FS2_LN_CLUSTER=0 (debug / A-B): plane families use the single-CTA fused kernel (f16) or GEMM -> LayerNorm (3xF16)
+bool ln_cluster_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FS2_LN_CLUSTER"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+
 int dense(const TapGemm& g, int math_mode, cudaStream_t st, int cls) {
   const double M = (double)g.B * g.L;
   // algorithmic bytes: operands at the width this launch reads them (hi plane: 2 B; fp32, or hi + lo planes: 4 B),
@@ -126,7 +133,10 @@ int dense(const TapGemm& g, int math_mode, cudaStream_t st, int cls) {
   const double e_out = (g.out ? 4.0 : 0.0) + ((g.outp || g.vtp) ? (g.outp_lo ? 4.0 : 2.0) : 0.0);
   ProfScope prof_scope(cls, 2.0 * M * g.N * g.K * g.taps,
                e_in * (M * g.K + (double)g.taps * g.N * g.K) + M * g.N * (e_out + (g.resid ? 4.0 : 0.0)), st);
-  if (g.ln_gamma) return gemm_ln_tf32(g, st);       // fused residual + LayerNorm epilogue (tf32 on fp32 rows, or f16 on hi planes)
+  if (g.ln_gamma) {                                 // fused residual + LayerNorm epilogue
+    if (g.xp && gemm_ln_planes_supported(g) && ln_cluster_enabled()) return gemm_ln_planes(g, st);   // plane families: 2-CTA cluster kernel
+    return gemm_ln_tf32(g, st);                     // kind::tf32 on fp32 rows (and the single-CTA f16 variant, FS2_LN_CLUSTER=0)
+  }
   if (g.xp) return tap_gemm_planes(g, st);
   return math_mode == FS2_MATH_TF32 ? tap_gemm_tf32(g, st) : tap_gemm_fp32(g, st);
 }
@@ -249,8 +259,8 @@ int run_blocks_planes(const std::vector<Block>& blocks, const BlockBufs& w, cons
     // x = LN(x + linear_out(ctx)) (attention.py:74, encoder.py:60-62); the LayerNorm also writes the conv-FFN's operand planes
     TapGemm go = make_gemm_p(k.out, w.ctxp, B, L, x3, ACT_NONE, x, C, y, C);
     go.ln_gamma = k.ln1.g; go.ln_beta = k.ln1.b; go.ln_eps = k.ln1.eps;
-    if (!x3 && gemm_ln_tf32_supported(go) && fuse_ln_enabled()) {   // fused: result in y, swap roles
-      planes_out(go, w.xp, C, false);
+    if (fuse_ln_enabled() && (ln_cluster_enabled() ? gemm_ln_planes_supported(go) : (!x3 && gemm_ln_tf32_supported(go)))) {   // fused: result in y, swap roles
+      planes_out(go, w.xp, C, x3);
       if ((rc = dense(go, FS2_MATH_F16, st, c_out))) return rc;
       float* t = x; x = y; y = t;
     } else {
@@ -267,8 +277,8 @@ int run_blocks_planes(const std::vector<Block>& blocks, const BlockBufs& w, cons
     if ((rc = dense(g1, FS2_MATH_F16, st, c_w1))) return rc;
     TapGemm g2 = make_gemm_p(k.w2, w.hidp, B, L, x3, ACT_NONE, x, C, y, C);
     g2.ln_gamma = k.ln2.g; g2.ln_beta = k.ln2.b; g2.ln_eps = k.ln2.eps;
-    if (!x3 && gemm_ln_tf32_supported(g2) && fuse_ln_enabled()) {
-      planes_out(g2, w.xp, C, false);              // planes of the block output: A operand of the next q|k|v / mel projection
+    if (fuse_ln_enabled() && (ln_cluster_enabled() ? gemm_ln_planes_supported(g2) : (!x3 && gemm_ln_tf32_supported(g2)))) {
+      planes_out(g2, w.xp, C, x3);                 // planes of the block output: A operand of the next q|k|v / mel projection
       if ((rc = dense(g2, FS2_MATH_F16, st, c_w2))) return rc;
       float* t = x; x = y; y = t;
     } else {
@@ -775,25 +785,39 @@ int fs2_op_tap_gemm(int math_mode, const float* x, int B, int L, int K, const fl
   d.w_hi = t.w_hi; d.w_lo = t.w_lo; d.w_inv = t.sc + 1;
   return dense(make_gemm_p(d, t.xp, B, L, math_mode == MATH_3XTF32, act, resid, N, out, N), math_mode, st, P_DEC_W1);
 }
-int fs2_op_gemm_layernorm(int math_mode, const float* x, int64_t rows, int K, const float* w, const float* bias, const float* resid,
-                          const float* gamma, const float* beta, float eps, float* out, void* stream) {
+int fs2_op_gemm_layernorm(int math_mode, const float* x, int64_t rows, int K, int N, const float* w, const float* bias, const float* resid,
+                          const float* gamma, const float* beta, float eps, float* out, float* out_planes, void* stream) {
   FS2_REQUIRE(x && w && gamma && beta && out, "fs2_op_gemm_layernorm: null argument");
   FS2_REQUIRE(rows < (1LL << 31), "fs2_op_gemm_layernorm: too many rows");
-  FS2_REQUIRE(math_mode == FS2_MATH_TF32 || math_mode == FS2_MATH_F16, "fs2_op_gemm_layernorm: the fused epilogue exists for FS2_MATH_TF32 and FS2_MATH_F16");
+  FS2_REQUIRE(math_mode == FS2_MATH_TF32 || math_mode == FS2_MATH_F16 || math_mode == FS2_MATH_3XTF32,
+              "fs2_op_gemm_layernorm: the fused epilogue exists for FS2_MATH_TF32, FS2_MATH_F16 and FS2_MATH_3XTF32");
+  FS2_REQUIRE(N == 384 || (N == 256 && math_mode != FS2_MATH_TF32), "fs2_op_gemm_layernorm: N must be 384 (or 256 in the plane families)");
   cudaStream_t st = (cudaStream_t)stream;
-  Dense d; d.w = w; d.bias = bias; d.N = 384; d.K = K; d.taps = 1;
+  Dense d; d.w = w; d.bias = bias; d.N = N; d.K = K; d.taps = 1;
   if (math_mode == FS2_MATH_TF32) {
-    TapGemm g = make_gemm(d, x, K, 1, (int)rows, ACT_NONE, resid, 384, out, 384);
+    FS2_REQUIRE(!out_planes, "fs2_op_gemm_layernorm: the kind::tf32 variant has no plane output in this entry");
+    TapGemm g = make_gemm(d, x, K, 1, (int)rows, ACT_NONE, resid, N, out, N);
     g.ln_gamma = gamma; g.ln_beta = beta; g.ln_eps = eps;
     return dense(g, FS2_MATH_TF32, st, P_DEC_OUT);
   }
+  const bool x3 = math_mode == FS2_MATH_3XTF32;
   TempPlanes t;
-  int rc = t.make(x, (long)rows, K, w, (long)384 * K, st);
+  int rc = t.make(x, (long)rows, K, w, (long)N * K, st);
   if (rc) return rc;
   d.w_hi = t.w_hi; d.w_lo = t.w_lo; d.w_inv = t.sc + 1;
-  TapGemm g = make_gemm_p(d, t.xp, 1, (int)rows, false, ACT_NONE, resid, 384, out, 384);
+  TapGemm g = make_gemm_p(d, t.xp, 1, (int)rows, x3, ACT_NONE, resid, N, out, N);
   g.ln_gamma = gamma; g.ln_beta = beta; g.ln_eps = eps;
-  return dense(g, FS2_MATH_F16, st, P_DEC_OUT);
+  // optional: the result's operand planes (what the next contraction would read), returned as fp32 = (hi + lo) / kPlaneScale
+  __half* op = nullptr;
+  if (out_planes) {
+    FS2_CUDA_CHECK(cudaMallocAsync(&op, (size_t)2 * rows * N * sizeof(__half) + 64, st));
+    FS2_CUDA_CHECK(cudaMemsetAsync(op, 0, (size_t)2 * rows * N * sizeof(__half), st));
+    planes_out(g, op, N, x3);
+  }
+  rc = dense(g, FS2_MATH_F16, st, P_DEC_OUT);
+  if (!rc && op) rc = planes_to_rows(op, (long)rows * N, out_planes, st);
+  if (op) cudaFreeAsync(op, st);
+  return rc;
 }
 int fs2_op_attention(int math_mode, const float* qkv, const int64_t* lens, int B, int L, int C, int heads, float* ctx,
                      void* stream) {

@@ -79,10 +79,15 @@ int tap_gemm_fp32(const TapGemm& g, cudaStream_t st);
 int tap_gemm_tf32(const TapGemm& g, cudaStream_t st);   // tcgen05 + TMA, kind::tf32 on fp32 data (gemm_tc.cu)
 bool gemm_ln_tf32_supported(const TapGemm& g);         // row-complete GEMM + residual + LayerNorm (gemm_ln_tc.cu)
 int gemm_ln_tf32(const TapGemm& g, cudaStream_t st);
+// plane families, N in {256, 384}: the same fusion as a 2-CTA cluster (each CTA half a row, double-buffered accumulators,
+// statistics merged through distributed shared memory); kind::f16 on the hi planes or 3xF16 (g.precise)  (gemm_ln_cl.cu)
+bool gemm_ln_planes_supported(const TapGemm& g);
+int gemm_ln_planes(const TapGemm& g, cudaStream_t st);
 int tap_gemm_planes(const TapGemm& g, cudaStream_t st); // same kernel on fp16 operand planes: kind::f16 or 3xF16 (g.precise)
 int split_f16(const float* src, __half* hi, __half* lo, long n, const float* scale /*device scalar or null*/, cudaStream_t st);
 // x [rows][ldx] fp32 -> planes [2][rows][K] scaled by kPlaneScale (the one pre-pass left: LengthRegulator output, test entries)
 int split_rows(const float* x, int ldx, long rows, int K, __half* planes, cudaStream_t st);
+int planes_to_rows(const __half* planes, long n, float* out, cudaStream_t st);   // test helper: (hi + lo) / kPlaneScale
 // power-of-two scale of a weight tensor: inv[0] = 2^-k with max|w| * 2^k in [2^13, 2^14), scale[0] = 2^k (1 for all-zero)
 int weight_scale(const float* w, long n, float* scale, float* inv, cudaStream_t st);
 constexpr int MATH_3XTF32 = FS2_MATH_3XTF32;            // also what the other tensor-core modes use for the encoder + predictors

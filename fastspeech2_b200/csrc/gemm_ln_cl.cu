@@ -20,9 +20,9 @@
 //   * the residual arrives by TMA (128-byte-swizzled 128 x 32 fp32 boxes, a ring refilled by its own producer warp while
 //     the main loop runs) instead of row-strided global loads that sat exposed in the epilogue;
 //   * outputs go straight from registers as sector-complete 256-bit stores (fire and forget).
-// Warp roles (384 threads): 0 = TMA producer for the operand stages, 1 = MMA issuer (+ TMEM allocation), 2 = TMA producer
-// for the residual ring, 3 idle, 4..11 = epilogue (warp & 3 = TMEM lane quarter, (warp - 4) / 4 = column group; the
-// groups take alternate 32-column chunks).
+// Warp roles (352 threads): 0..7 = epilogue (warp & 3 = TMEM lane quarter, warp / 4 = column group; the groups take
+// alternate 32-column chunks), 8 = TMA producer for the operand stages, 9 = MMA issuer (+ TMEM allocation), 10 = TMA
+// producer for the residual ring.
 // Every mbarrier wait is bounded (tc_common.cuh): a protocol bug traps instead of hanging the GPU.
 #include "tc_common.cuh"
 
@@ -33,7 +33,7 @@ using namespace tc;
 constexpr int BM = 128, BKE = 64;                      // fp16 K elements per stage = one 128-byte swizzle row
 constexpr int A_BYTES = BM * 128;                      // 16 KB per A plane per stage
 constexpr int CHUNK_BYTES = BM * 128;                  // residual chunk: 128 rows x 32 fp32
-constexpr int CL_THREADS = 384;
+constexpr int CL_THREADS = 352;
 
 template <int C, bool X3>
 struct CCfg {
@@ -144,7 +144,7 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     mbar_init(x_bar, 16);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, L::TMEM_COLS);
+  if (warp == 9) tmem_alloc(tmem_slot, L::TMEM_COLS);
   for (int i = threadIdx.x; i < L::H; i += blockDim.x) {
     vec[i] = p.bias ? __ldg(p.bias + col0 + i) : 0.f;
     vec[L::H + i] = __ldg(p.gamma + col0 + i);
@@ -156,7 +156,7 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == 8) {
     if (lane == 0) {  // ---- TMA producer: operand stages ----
       int n = 0;
       for (int tile = cluster_id; tile < tiles_total; tile += n_clusters) {
@@ -173,7 +173,7 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     // ---- MMA issuer: whole warp, one lane elected inside each tcgen05 asm ----
     int n = 0, it = 0;
     for (int tile = cluster_id; tile < tiles_total; tile += n_clusters, ++it) {
@@ -202,7 +202,7 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       }
       tcgen05_commit(&acc_full[acc]);
     }
-  } else if (warp == 2) {
+  } else if (warp == 10) {
     if (lane == 0 && p.has_resid) {  // ---- TMA producer: residual ring (chunk c of a tile = columns col0 + 32 c .. + 31) ----
       int q = 0;
       for (int tile = cluster_id; tile < tiles_total; tile += n_clusters) {
@@ -215,9 +215,9 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         }
       }
     }
-  } else if (warp >= 4) {
+  } else {
     // ---- epilogue: thread == row (TMEM lane), group g takes the 32-column chunks g, g + 2, ... of this CTA's half ----
-    const int wq = warp & 3, grp = (warp - 4) >> 2;
+    const int wq = warp & 3, grp = warp >> 2;
     const int row = wq * 32 + lane;
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
     const float oscale = p.a_inv * (p.w_inv ? __ldg(p.w_inv) : 1.0f);
@@ -335,7 +335,7 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   tcgen05_fence_before();
   __syncthreads();
   cluster_sync_all();                          // no CTA leaves while its peer may still write into it
-  if (warp == 1) {
+  if (warp == 9) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, L::TMEM_COLS);
   }

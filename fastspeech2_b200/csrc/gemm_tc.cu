@@ -562,6 +562,22 @@ __global__ void weight_scale_kernel(const float* __restrict__ w, long n, float* 
 }
 }  // namespace
 
+namespace {
+__global__ void planes_to_rows_kernel(const __half* __restrict__ planes, long n, float* __restrict__ out) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    out[i] = (__half2float(planes[i]) + __half2float(planes[n + i])) * kPlaneInv;
+}
+}  // namespace
+
+// test helper: planes [2][n] (hi, lo; scaled by kPlaneScale) -> fp32
+int planes_to_rows(const __half* planes, long n, float* out, cudaStream_t st) {
+  if (n == 0) return FS2_OK;
+  long blocks = (n + 255) / 256;
+  planes_to_rows_kernel<<<(int)(blocks > 1184 ? 1184 : blocks), 256, 0, st>>>(planes, n, out);
+  FS2_LAUNCH_CHECK();
+  return FS2_OK;
+}
+
 int split_f16(const float* src, __half* hi, __half* lo, long n, const float* scale, cudaStream_t st) {
   if (n == 0) return FS2_OK;
   long blocks = (n + 255) / 256;

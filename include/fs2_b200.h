@@ -177,11 +177,15 @@ int fs2_one_hot(const int64_t* ids, int64_t n, int n_bins, float* out, void* str
  * act: 0 none, 1 relu, 2 tanh */
 int fs2_op_tap_gemm(int math_mode, const float* x, int B, int L, int K, const float* w, const float* bias, int N, int taps,
                     int act, const float* resid, float* out, void* stream);
-/* out = LayerNorm_384(x . w^T + bias + resid) * gamma + beta in one tcgen05 kernel (x [rows,K], w [384,K]);
- * the fused form of core/encoder.py:60-62 / :67-69 used for the decoder blocks in FS2_MATH_TF32 (kind::tf32 on the
- * fp32 rows) and FS2_MATH_F16 (kind::f16 on operand planes made on the fly here) */
-int fs2_op_gemm_layernorm(int math_mode, const float* x, int64_t rows, int K, const float* w, const float* bias,
-                          const float* resid, const float* gamma, const float* beta, float eps, float* out, void* stream);
+/* out = LayerNorm_N(x . w^T + bias + resid) * gamma + beta in one tcgen05 kernel (x [rows,K], w [N,K]);
+ * the fused form of core/encoder.py:60-62 / :67-69: FS2_MATH_TF32 (kind::tf32 on the fp32 rows, N = 384),
+ * FS2_MATH_F16 (kind::f16) and FS2_MATH_3XTF32 (error-compensated 3xF16) on operand planes made on the fly here,
+ * N in {256, 384}; the plane families run as a 2-CTA cluster, each CTA normalising half of every row.
+ * out_planes (nullable, plane families): the operand planes the kernel writes for the next contraction, returned
+ * recombined as fp32 [rows,N] = (hi + lo) / scale (hi only in FS2_MATH_F16) */
+int fs2_op_gemm_layernorm(int math_mode, const float* x, int64_t rows, int K, int N, const float* w, const float* bias,
+                          const float* resid, const float* gamma, const float* beta, float eps, float* out,
+                          float* out_planes, void* stream);
 /* qkv [B,L,3C] (q | k | v, heads contiguous inside each) -> ctx [B,L,C]; lens NULL => no mask.  FS2_MATH_FP32: CUDA cores;
  * FS2_MATH_TF32: tcgen05 kind::tf32; FS2_MATH_F16 / FS2_MATH_3XTF32: tcgen05 kind::f16 / error-compensated 3xF16 on planes */
 int fs2_op_attention(int math_mode, const float* qkv, const int64_t* lens, int B, int L, int C, int heads, float* ctx,

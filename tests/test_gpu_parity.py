@@ -359,21 +359,31 @@ def test_attention_persistent_ctas_many_work_items(prec):
     assert float(ctx[1].abs().max()) == 0.0 and float(ctx[10].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("prec", ["tf32", "f16"])
-@pytest.mark.parametrize("rows,K,with_resid", [(1000, 384, True), (51, 1024, True), (4097, 256, False)])
-def test_fused_gemm_layernorm_vs_torch(prec, rows, K, with_resid):
-    """tcgen05 GEMM with residual + LayerNorm fused into the epilogue (decoder out-projection / conv-FFN w_2)."""
-    g = torch.Generator().manual_seed(rows + K)
-    x = torch.randn(rows, K, generator=g); w = torch.randn(384, K, generator=g) / K ** 0.5; bias = torch.randn(384, generator=g)
-    resid = torch.randn(rows, 384, generator=g); gamma = 1 + 0.1 * torch.randn(384, generator=g); beta = torch.randn(384, generator=g)
-    y = x.double() @ w.double().T + bias.double() + (resid.double() if with_resid else 0)
-    want = torch.nn.functional.layer_norm(y, (384,), gamma.double(), beta.double(), 1e-5).float()
-    out = torch.empty(rows, 384, device="cuda")
-    lib = _lib.load()
+@pytest.mark.parametrize("prec,N", [("tf32", 384), ("f16", 384), ("3xtf32", 384), ("f16", 256), ("3xtf32", 256)])
+@pytest.mark.parametrize("rows,K,with_resid", [(1000, 384, True), (51, 1024, True), (4097, 256, False), (40000, 384, True)])
+def test_fused_gemm_layernorm_vs_torch(prec, N, rows, K, with_resid):
+    """tcgen05 GEMM with residual + LayerNorm fused into the epilogue (out-projection / conv-FFN w_2): the kind::tf32 single-CTA
+    kernel and the 2-CTA-cluster plane kernels (kind::f16, 3xF16; rows split between the CTAs, statistics merged through
+    distributed shared memory).  40000 rows = more tiles than cluster slots: every pipeline ring wraps several times."""
+    g = torch.Generator().manual_seed(rows + K + N)
+    x = torch.randn(rows, K, generator=g); w = torch.randn(N, K, generator=g) / K ** 0.5; bias = torch.randn(N, generator=g)
+    resid = torch.randn(rows, N, generator=g) + 2.0          # non-zero row mean: exercises the merge of the partial statistics
+    gamma = 1 + 0.1 * torch.randn(N, generator=g); beta = torch.randn(N, generator=g)
     xc, wc, bc, rc, gc, btc = x.cuda(), w.cuda(), bias.cuda(), resid.cuda(), gamma.cuda(), beta.cuda()
-    _lib.check(lib.fs2_op_gemm_layernorm(_lib.MATH_MODES[prec], _lib.ptr(xc), rows, K, _lib.ptr(wc), _lib.ptr(bc), _lib.ptr(rc) if with_resid else None,
-                                         _lib.ptr(gc), _lib.ptr(btc), 1e-5, _lib.ptr(out), _lib.stream_ptr(out.device)), "fs2_op_gemm_layernorm")
-    close(out, want, dict(max=1e-2, mean=1e-3), f"gemm+ln rows={rows} K={K}")
+    y = xc.double() @ wc.double().T + bc.double() + (rc.double() if with_resid else 0)
+    want = torch.nn.functional.layer_norm(y, (N,), gc.double(), btc.double(), 1e-5).float()
+    out = torch.full((rows, N), float("nan"), device="cuda")
+    planes = torch.full((rows, N), float("nan"), device="cuda") if prec != "tf32" else None
+    lib = _lib.load()
+    _lib.check(lib.fs2_op_gemm_layernorm(_lib.MATH_MODES[prec], _lib.ptr(xc), rows, K, N, _lib.ptr(wc), _lib.ptr(bc), _lib.ptr(rc) if with_resid else None,
+                                         _lib.ptr(gc), _lib.ptr(btc), 1e-5, _lib.ptr(out), _lib.ptr(planes) if planes is not None else None,
+                                         _lib.stream_ptr(out.device)), "fs2_op_gemm_layernorm")
+    tol = dict(max=3e-5, mean=3e-6) if prec == "3xtf32" else dict(max=1e-2, mean=1e-3)
+    close(out, want, tol, f"gemm+ln {prec} N={N} rows={rows} K={K}")
+    if planes is not None:      # the operand planes written for the next contraction carry the same rows (22 / 11 mantissa bits)
+        rel = 2e-6 if prec == "3xtf32" else 1.5e-3
+        assert torch.isfinite(planes).all()
+        assert float(((planes - out).abs() - rel * out.abs()).max()) <= 1e-6, float((planes - out).abs().max())
 
 
 @pytest.mark.parametrize("C", [256, 384])
