@@ -103,12 +103,13 @@ inline int att_debug() {
 
 __device__ __forceinline__ void tmem_st32u(uint32_t taddr, const uint32_t* r) { tmem_st32(taddr, reinterpret_cast<const float*>(r)); }
 
-// exp2 of one thread's 64 scores -> packed fp16 P (hi, and lo when X3); returns the row-sum contribution
-template <bool X3, bool MASKED>
+// exp2 of one thread's 2 NP scores (64, or 32 in a short last tile) -> packed fp16 P (hi, and lo when X3); returns the
+// row-sum contribution
+template <bool X3, bool MASKED, int NP = 32>
 __device__ __forceinline__ float softmax_tile(const float* v, float c_exp, float mb, int kv0, int len, uint32_t* ph, uint32_t* pl) {
   float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
+  for (int i = 0; i < NP; ++i) {
     float e0 = fast_exp2(fmaf(v[2 * i], c_exp, -mb)), e1 = fast_exp2(fmaf(v[2 * i + 1], c_exp, -mb));
     if (MASKED) { if (kv0 + 2 * i >= len) e0 = 0.f; if (kv0 + 2 * i + 1 >= len) e1 = 0.f; }
     const __half2 h = __floats2half2_rn(e0, e1);
@@ -158,6 +159,10 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
     len = p.lens ? (int)min((long)p.lens[b], (long)p.L) : p.L;       // keys >= len are masked
     J = (len + BKV - 1) / BKV;                                        // kv tiles that contain valid keys
   };
+  // keys of kv tile j the tensor core has to look at: all 128, or -- in the last tile of an utterance -- the valid ones
+  // rounded up to the MMA's granularity of 16 (the softmax writes P = 0 for the masked keys inside that granule).  The S
+  // product of a partial tile uses N = n16, its P.V only the first n16 / 16 K-steps and ceil(n16 / 64) V^T boxes.
+  auto keys16 = [&](int j, int len) { const int r = len - j * BKV; return r >= BKV ? BKV : (r + 15) & ~15; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < A::SLOTS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -194,7 +199,8 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
             }
         };
         auto push_v = [&](int j) {
-          for (int c = 0; c < BKV / CH; ++c)
+          const int vch = (keys16(j, len) + CH - 1) / CH;
+          for (int c = 0; c < vch; ++c)
             for (int pl = 0; pl < A::P; ++pl, ++n) {
               const int slot = n % A::SLOTS;
               mbar_wait(&empty_bar[slot], ((n / A::SLOTS) & 1) ^ 1);
@@ -219,8 +225,9 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
       };
       auto release = [&]() { tcgen05_commit(&empty_bar[n % A::SLOTS]); ++n; };
       // S tile g goes to S/P buffer g & 1; S_{g+2} reuses it after P.V_g, which is issued earlier in this thread
-      auto issue_s = [&](int g) {
+      auto issue_s = [&](int g, int n16) {
         const uint32_t d = tmem_base + (uint32_t)((g & 1) * BKV);
+        const uint32_t idesc_s = (A::IDESC_S & ~(0x3Fu << 17)) | ((uint32_t)(n16 >> 3) << 17);   // N = n16
         for (int c = 0; c < A::QCH; ++c) {
           const uint64_t q_hi = make_sw128_kmajor_desc(q_addr + c * A::Q_BOX);
           const uint64_t k_hi = take();
@@ -228,17 +235,17 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
             const uint64_t q_lo = make_sw128_kmajor_desc(q_addr + (A::QCH + c) * A::Q_BOX);
 #pragma unroll
             for (int k = 0; k < CH / 16; ++k) {
-              umma_f16(d, q_lo + 2 * k, k_hi + 2 * k, A::IDESC_S, (c | k) != 0);
-              umma_f16(d, q_hi + 2 * k, k_hi + 2 * k, A::IDESC_S, 1);
+              umma_f16(d, q_lo + 2 * k, k_hi + 2 * k, idesc_s, (c | k) != 0);
+              umma_f16(d, q_hi + 2 * k, k_hi + 2 * k, idesc_s, 1);
             }
             release();
             const uint64_t k_lo = take();
 #pragma unroll
-            for (int k = 0; k < CH / 16; ++k) umma_f16(d, q_hi + 2 * k, k_lo + 2 * k, A::IDESC_S, 1);
+            for (int k = 0; k < CH / 16; ++k) umma_f16(d, q_hi + 2 * k, k_lo + 2 * k, idesc_s, 1);
             release();
           } else {
 #pragma unroll
-            for (int k = 0; k < CH / 16; ++k) umma_f16(d, q_hi + 2 * k, k_hi + 2 * k, A::IDESC_S, (c | k) != 0);
+            for (int k = 0; k < CH / 16; ++k) umma_f16(d, q_hi + 2 * k, k_hi + 2 * k, idesc_s, (c | k) != 0);
             release();
           }
         }
@@ -250,13 +257,13 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
         if (J == 0) continue;
         mbar_wait(q_bar, wc & 1);
         tcgen05_fence_after();
-        issue_s(g0);
+        issue_s(g0, keys16(0, len));
         if (J == 1) tcgen05_commit(q_free);
         for (int j = 0; j < J; ++j) {
           const int g = g0 + j;
           if (wc == 0) trace_at(p, j, 2, 0);
           if (j + 1 < J) {
-            issue_s(g + 1);                               // the tensor core computes S_{g+1} while the softmax warps work on tile g
+            issue_s(g + 1, keys16(j + 1, len));          // the tensor core computes S_{g+1} while the softmax warps work on tile g
             if (j + 2 == J) tcgen05_commit(q_free);       // that was the item's last S product: Q may be overwritten once it completes
           }
           if (wc == 0) trace_at(p, j, 2, 1);
@@ -266,22 +273,28 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
           if (wc == 0) trace_at(p, j, 2, 2);
           const uint32_t p_hi = tmem_base + (uint32_t)((g & 1) * BKV), p_lo = p_hi + BKV / 2;   // packed fp16: 64 columns each
           const uint32_t o = tmem_base + A::O_COL;
-          for (int c = 0; c < BKV / CH; ++c) {
+          const int n16 = keys16(j, len);
+          for (int c = 0; c * CH < n16; ++c) {
             const uint64_t v_hi = take();
+            const int ks = n16 - c * CH >= CH ? CH / 16 : (n16 - c * CH) / 16;    // K-steps of this box that hold valid keys
             if (X3) {
 #pragma unroll
               for (int k = 0; k < CH / 16; ++k) {
-                umma_f16_ts(o, p_lo + (c * 4 + k) * 8, v_hi + 2 * k, A::IDESC_O, (j | c | k) != 0);
-                umma_f16_ts(o, p_hi + (c * 4 + k) * 8, v_hi + 2 * k, A::IDESC_O, 1);
+                if (k < ks) {
+                  umma_f16_ts(o, p_lo + (c * 4 + k) * 8, v_hi + 2 * k, A::IDESC_O, (j | c | k) != 0);
+                  umma_f16_ts(o, p_hi + (c * 4 + k) * 8, v_hi + 2 * k, A::IDESC_O, 1);
+                }
               }
               release();
               const uint64_t v_lo = take();
 #pragma unroll
-              for (int k = 0; k < CH / 16; ++k) umma_f16_ts(o, p_hi + (c * 4 + k) * 8, v_lo + 2 * k, A::IDESC_O, 1);
+              for (int k = 0; k < CH / 16; ++k)
+                if (k < ks) umma_f16_ts(o, p_hi + (c * 4 + k) * 8, v_lo + 2 * k, A::IDESC_O, 1);
               release();
             } else {
 #pragma unroll
-              for (int k = 0; k < CH / 16; ++k) umma_f16_ts(o, p_hi + (c * 4 + k) * 8, v_hi + 2 * k, A::IDESC_O, (j | c | k) != 0);
+              for (int k = 0; k < CH / 16; ++k)
+                if (k < ks) umma_f16_ts(o, p_hi + (c * 4 + k) * 8, v_hi + 2 * k, A::IDESC_O, (j | c | k) != 0);
               release();
             }
           }
@@ -327,14 +340,18 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
         if (wq == 0 && wc == 0) trace_at(p, j, half, 1);
         const int kv0 = j * BKV + half * 64;
         const bool masked = kv0 + 64 > len;                      // only the last tile of an utterance
+        // columns of this half the S product wrote (the MMA warp trims the last tile to the valid keys, rounded to 16):
+        // 64 normally; <= 32: half the work; 0: nothing to load, exponentiate or store for this half
+        const int ncols = min(max(keys16(j, len) - half * 64, 0), 64);
         __syncwarp();
         const uint32_t tb = lane_addr + (uint32_t)((g & 1) * BKV);
-        tmem_ld32_nowait(tb + half * 64, v); tmem_ld32_nowait(tb + half * 64 + 32, v + 32); tmem_ld_wait_pin<64>(v);
+        if (ncols > 32) { tmem_ld32_nowait(tb + half * 64, v); tmem_ld32_nowait(tb + half * 64 + 32, v + 32); tmem_ld_wait_pin<64>(v); }
+        else if (ncols > 0) { tmem_ld32_nowait(tb + half * 64, v); tmem_ld_wait_pin<32>(v); }
         if (wq == 0 && wc == 0) trace_at(p, j, half, 2);
         float tmax = -INFINITY;
         if (masked) {
 #pragma unroll
-          for (int i = 0; i < 64; ++i) if (kv0 + i < len) tmax = fmaxf(tmax, v[i]);
+          for (int i = 0; i < 64; ++i) if (kv0 + i < len) tmax = fmaxf(tmax, v[i]);     // stale registers past ncols are >= len
         } else {
 #pragma unroll
           for (int i = 0; i < 64; ++i) tmax = fmaxf(tmax, v[i]);
@@ -368,11 +385,19 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
         }
         const float mb = m_ref * c_exp;
         uint32_t ph[32], pl[32];
-        l_row += masked ? softmax_tile<X3, true>(v, c_exp, mb, kv0, len, ph, pl) : softmax_tile<X3, false>(v, c_exp, mb, kv0, len, ph, pl);
-        __syncwarp();
-        if (wq == 0 && wc == 0) trace_at(p, j, half, 4);
-        tmem_st32u(tb + half * 32, ph);                           // P hi: packed columns [0,64) of the tile's buffer
-        if (X3) tmem_st32u(tb + BKV / 2 + half * 32, pl);         // P lo: [64,128)
+        if (ncols > 32) {
+          l_row += masked ? softmax_tile<X3, true>(v, c_exp, mb, kv0, len, ph, pl) : softmax_tile<X3, false>(v, c_exp, mb, kv0, len, ph, pl);
+          __syncwarp();
+          if (wq == 0 && wc == 0) trace_at(p, j, half, 4);
+          tmem_st32u(tb + half * 32, ph);                           // P hi: packed columns [0,64) of the tile's buffer
+          if (X3) tmem_st32u(tb + BKV / 2 + half * 32, pl);         // P lo: [64,128)
+        } else if (ncols > 0) {                                     // short last tile: 32 keys of this half at most
+          l_row += softmax_tile<X3, true, 16>(v, c_exp, mb, kv0, len, ph, pl);
+          __syncwarp();
+          if (wq == 0 && wc == 0) trace_at(p, j, half, 4);
+          tmem_st16(tb + half * 32, ph);
+          if (X3) tmem_st16(tb + BKV / 2 + half * 32, pl);
+        }
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();

@@ -43,6 +43,9 @@ def run(mode, n=10):
 
 
 flop = 4.0 * B * L * L * C
+only = [m_ for m_ in os.environ.get("PROBE_MODES", "").split(",") if m_]          # e.g. PROBE_MODES=3xf16 FS2_ATT_TRACE=1: trace that mode
 for name, mode in (("f16", 3), ("3xf16", 2), ("tf32", 1)):
+    if only and name not in only:
+        continue
     ms = run(mode)
     print(f"X2={os.environ.get('FS2_ATT_X2','1')} DEBUG={os.environ.get('FS2_ATT_DEBUG','0')} {name}: {ms*1e3:.1f} us kernel only  ({flop/ms/1e9:.0f} TFLOP/s algorithmic)", flush=True)
