@@ -19,8 +19,9 @@ reference, the reference's own precision).  The 10-bit-mantissa fast modes are m
 
 `value`  : whole-job frames/s with inputs resident in HBM, CUDA-event timed, max over ranks.
 `e2e`    : same through the public API with HOST (pinned) inputs: H2D of xs/ilens/olens/ds/es/ps
-           and D2H of the mel batch inside the timed region, every step (mel copy on a side stream,
-           two captured graphs with their own output buffers alternate so the copy of step i overlaps step i+1).
+           and D2H of the mel batch inside the timed region, every step (both on side streams: two captured graphs
+           with their own static inputs / outputs alternate, so the uploads of step i+1 and the mel copy of step i-1
+           overlap step i; events order every copy against the replay that produces / consumes the buffer).
 `roofline`: dominant kernel class (decoder conv-FFN w_1: k=9 conv 384->1024 as a tap-GEMM),
            algorithmic FLOPs per launch / its CUDA-event duration measured by the library's
            per-kernel-class event profiler on extra steps of this same workload.
@@ -338,7 +339,8 @@ def run_b200(args):
     frames_rank = int(bt["olens"].sum())
     gathered = torch.empty((world * B, L, 80), dtype=torch.float32, device=dev) if world > 1 else None
     mel_host = [torch.empty((B, L, 80), dtype=torch.float32).pin_memory() for _ in range(2)]
-    copy_stream = torch.cuda.Stream(dev)
+    copy_stream = torch.cuda.Stream(dev)      # D2H of the results
+    up_stream = torch.cuda.Stream(dev)        # H2D of the inputs
 
     def build(precision):
         m = FeedForwardTransformer(68, 80, load_hp(), precision=precision)
@@ -394,6 +396,8 @@ def run_b200(args):
         # receive buffer i (peer-mapped over NVLink on the other ranks)
         graphs = [model.graphed_forward(*[devin[k] for k in keys], after_out=(peer.slot(i) if fused else None)) for i in range(2)] if args.graph else None
         copied = [torch.cuda.Event(), torch.cuda.Event()]
+        uploaded = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [None, None]                 # graph i's static inputs may be overwritten once its last replay has finished
 
         pushed = [None, None]
         big_host = ([torch.empty((world * B, L, 80), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -442,8 +446,17 @@ def run_b200(args):
                     dst9 = [None] * 9
                     for dst, k in zip(g.inputs, keys):
                         dst9[FIELD[k]] = dst
-                    collator.upload_into(col, dst9)                     # H2D from the pinned slot straight into the graph's static inputs
+                    # H2D from the pinned slot straight into the graph's static inputs, on the upload stream: step i's
+                    # inputs travel while step i-1 computes (they only wait for this graph's previous replay, step i-2)
+                    with torch.cuda.stream(up_stream):
+                        if consumed[i & 1] is not None:
+                            up_stream.wait_event(consumed[i & 1])
+                        collator.upload_into(col, dst9)
+                        uploaded[i & 1].record(up_stream)
+                    cur.wait_event(uploaded[i & 1])
                     out = g.replay(validate="deferred")
+                    consumed[i & 1] = torch.cuda.Event()
+                    consumed[i & 1].record(cur)
                 else:
                     up = collator.to_device(pinned[i & 1], dev)
                     inp = [up[FIELD[k]] for k in keys]
@@ -468,6 +481,7 @@ def run_b200(args):
                 for g in graphs:
                     g.flush()
             copy_stream.synchronize()
+            up_stream.synchronize()
         return step, step_e2e, flush
 
     model = build(args.precision)
