@@ -135,6 +135,7 @@ int dense(const TapGemm& g, int math_mode, cudaStream_t st, int cls) {
                e_in * (M * g.K + (double)g.taps * g.N * g.K) + M * g.N * (e_out + (g.resid ? 4.0 : 0.0)), st);
   if (g.ln_gamma) {                                 // fused residual + LayerNorm epilogue
     if (g.xp && gemm_ln_planes_supported(g) && ln_cluster_enabled()) return gemm_ln_planes(g, st);   // plane families: 2-CTA cluster kernel
+    FS2_REQUIRE(!g.precise, "fused GEMM + LayerNorm in 3xF16 exists only as the cluster kernel (FS2_LN_CLUSTER=0 set?)");
     return gemm_ln_tf32(g, st);                     // kind::tf32 on fp32 rows (and the single-CTA f16 variant, FS2_LN_CLUSTER=0)
   }
   if (g.xp) return tap_gemm_planes(g, st);

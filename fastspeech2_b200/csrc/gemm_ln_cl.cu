@@ -20,10 +20,21 @@
 //   * the residual arrives by TMA (128-byte-swizzled 128 x 32 fp32 boxes, a ring refilled by its own producer warp while
 //     the main loop runs) instead of row-strided global loads that sat exposed in the epilogue;
 //   * outputs go straight from registers as sector-complete 256-bit stores (fire and forget).
+// Optional operand sharing by TMA multicast (FS2_LN_MG = 2 / 4, FS2_LN_AMC = 1): clusters of 2 MG CTAs = MG row tiles x 2
+// column halves, where the two CTAs of a row tile each fetch 64 of its 128 A rows for both and the MG CTAs of a column
+// half each fetch 1/MG of the weight rows for all of them; a stage is refilled only when every CTA that reads what this
+// CTA writes has consumed it (the MMA warp's tcgen05.commit arrives, multicast, on the empty barriers of its row mate
+// and its column mates).  Correct (tested in every configuration) but measured SLOWER than plain pairs -- the lock step
+// of 4 - 8 CTAs costs more than the halved L2 -> SM traffic saves -- so the default is MG = 1 without multicast.
+// Where the time goes (FS2_LN_DEBUG experiments, tools/ln_time.py, 3xF16 out-projection): removing the output stores
+// -31 %, the residual -15 %, the statistics exchange -13 %, all operand loads -30 % of what is left: the row-per-thread
+// 256-bit stores of three output tensors are the largest single cost.
 // Warp roles (352 threads): 0..7 = epilogue (warp & 3 = TMEM lane quarter, warp / 4 = column group; the groups take
 // alternate 32-column chunks), 8 = TMA producer for the operand stages, 9 = MMA issuer (+ TMEM allocation), 10 = TMA
 // producer for the residual ring.
 // Every mbarrier wait is bounded (tc_common.cuh): a protocol bug traps instead of hanging the GPU.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace fs2 {
@@ -63,6 +74,8 @@ struct CCfg {
 
 struct ClParams {
   int M, K;
+  int a_mc;                                       // A tile fetched half / half by the two CTAs of a row tile (multicast)
+  int debug;                                      // FS2_LN_DEBUG (timing experiments only): 1 no residual, 2 no stores, 4 no statistics exchange
   const float* bias; const float* gamma; const float* beta; float eps;
   int has_resid;
   float* out; int ldo;
@@ -105,17 +118,35 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     __trap();
   }
 }
+__device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
+      : "memory");
+}
+// MMA-completion arrive on the barrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void tcgen05_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
 
-template <int C, bool X3>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1)
-gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                       const __grid_constant__ CUtensorMap tmap_b_lo, const __grid_constant__ CUtensorMap tmap_r, ClParams p) {
+template <int C, bool X3, int MG>
+__global__ void __launch_bounds__(CL_THREADS, 1)
+gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a64,
+                       const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b_lo,
+                       const __grid_constant__ CUtensorMap tmap_r, ClParams p) {
   using L = CCfg<C, X3>;
+  constexpr int CS = 2 * MG;                    // cluster size
+  constexpr int BROWS = L::H / MG;              // weight rows this CTA fetches per stage (for all its column mates)
+  static_assert(BROWS % 8 == 0, "weight slice must keep the 8-row swizzle atom");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* rbuf = tiles + (size_t)L::STAGES * L::STAGE_BYTES;                      // residual ring, 1024-byte aligned chunks
@@ -134,11 +165,20 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   const uint32_t rank = cluster_ctarank();
   const int steps = (p.K + BKE - 1) / BKE;
   const int tiles_total = (p.M + BM - 1) / BM;
-  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-  const int col0 = (int)rank * L::H;           // this CTA's first output column
+  const int cluster_id = blockIdx.x / CS, n_clusters = gridDim.x / CS;
+  const int nh = (int)(rank & 1u), mrow = (int)(rank >> 1);      // column half, row tile inside the cluster
+  const int col0 = nh * L::H;                  // this CTA's first output column
+  // CTAs that read what this CTA fetches: its row mate (A half) and the CTAs of its column half (weight slice)
+  uint32_t mask_b = 0;
+#pragma unroll
+  for (int i = 0; i < MG; ++i) mask_b |= 1u << (2 * i + nh);
+  const uint16_t mask_a = (uint16_t)(3u << (2 * mrow));
+  const bool share = p.a_mc != 0 || MG > 1;
+  const uint16_t mask_e = (uint16_t)((p.a_mc ? mask_a : (1u << rank)) | mask_b);
+  const int n_readers = (p.a_mc ? 1 : 0) + MG;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < L::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < L::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], n_readers); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     for (int i = 0; i < L::RB; ++i) { mbar_init(&r_full[i], 1); mbar_init(&r_empty[i], 4); }
     mbar_init(x_bar, 16);
@@ -159,24 +199,42 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   if (warp == 8) {
     if (lane == 0) {  // ---- TMA producer: operand stages ----
       int n = 0;
-      for (int tile = cluster_id; tile < tiles_total; tile += n_clusters) {
-        const int r0 = tile * BM;
+      for (int rd = cluster_id; rd * MG < tiles_total; rd += n_clusters) {
+        const int r0 = (rd * MG + mrow) * BM;        // a row tile past the end is all zero fill (its mates still need this CTA's share)
         for (int s = 0; s < steps; ++s, ++n) {
           const int slot = n % L::STAGES;
           mbar_wait(&empty_bar[slot], ((n / L::STAGES) & 1) ^ 1);
           uint8_t* st = tiles + (size_t)slot * L::STAGE_BYTES;
-          mbar_expect_tx(&full_bar[slot], L::STAGE_BYTES);
-          tma_load_3d(st, &tmap_a, &full_bar[slot], s * BKE, r0, 0);
-          if (X3) tma_load_3d(st + L::A_LO, &tmap_a, &full_bar[slot], s * BKE, r0, 1);
-          tma_load_3d(st + L::B_HI, &tmap_b, &full_bar[slot], s * BKE, col0, 0);
-          if (X3) tma_load_3d(st + L::B_LO, &tmap_b_lo, &full_bar[slot], s * BKE, col0, 0);
+          if (p.debug & 24) {                           // timing experiments: 8 = no weight loads, 16 = no A loads (stale operands)
+            const uint32_t bytes = ((p.debug & 8) ? 0u : (uint32_t)(L::PL * L::B_BYTES)) + ((p.debug & 16) ? 0u : (uint32_t)(L::PL * A_BYTES));
+            if (bytes == 0) { mbar_arrive(&full_bar[slot]); continue; }
+            mbar_expect_tx(&full_bar[slot], bytes);
+            if (!(p.debug & 16)) { tma_load_3d(st, &tmap_a, &full_bar[slot], s * BKE, r0, 0); if (X3) tma_load_3d(st + L::A_LO, &tmap_a, &full_bar[slot], s * BKE, r0, 1); }
+            if (!(p.debug & 8)) { tma_load_3d(st + L::B_HI, &tmap_b, &full_bar[slot], s * BKE, col0, 0); if (X3) tma_load_3d(st + L::B_LO, &tmap_b_lo, &full_bar[slot], s * BKE, col0, 0); }
+            continue;
+          }
+          mbar_expect_tx(&full_bar[slot], L::STAGE_BYTES);   // everything that lands in this stage, whoever fetches it
+          if (p.a_mc) {                                // rows [64 nh, 64 nh + 64) of the A tile, for both column halves
+            tma_load_3d_mc(st + nh * (64 * 128), &tmap_a64, &full_bar[slot], s * BKE, r0 + nh * 64, 0, mask_a);
+            if (X3) tma_load_3d_mc(st + L::A_LO + nh * (64 * 128), &tmap_a64, &full_bar[slot], s * BKE, r0 + nh * 64, 1, mask_a);
+          } else {
+            tma_load_3d(st, &tmap_a, &full_bar[slot], s * BKE, r0, 0);
+            if (X3) tma_load_3d(st + L::A_LO, &tmap_a, &full_bar[slot], s * BKE, r0, 1);
+          }
+          if (MG > 1) {                                // weight rows [BROWS mrow, +BROWS) of this column half, for every row tile
+            tma_load_3d_mc(st + L::B_HI + mrow * (BROWS * 128), &tmap_b, &full_bar[slot], s * BKE, col0 + mrow * BROWS, 0, (uint16_t)mask_b);
+            if (X3) tma_load_3d_mc(st + L::B_LO + mrow * (BROWS * 128), &tmap_b_lo, &full_bar[slot], s * BKE, col0 + mrow * BROWS, 0, (uint16_t)mask_b);
+          } else {
+            tma_load_3d(st + L::B_HI, &tmap_b, &full_bar[slot], s * BKE, col0, 0);
+            if (X3) tma_load_3d(st + L::B_LO, &tmap_b_lo, &full_bar[slot], s * BKE, col0, 0);
+          }
         }
       }
     }
   } else if (warp == 9) {
     // ---- MMA issuer: whole warp, one lane elected inside each tcgen05 asm ----
     int n = 0, it = 0;
-    for (int tile = cluster_id; tile < tiles_total; tile += n_clusters, ++it) {
+    for (int rd = cluster_id; rd * MG < tiles_total; rd += n_clusters, ++it) {
       const int acc = it & 1;
       mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1);
       tcgen05_fence_after();
@@ -198,15 +256,16 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             umma_f16(d, a_hi + 2 * k, b_hi + 2 * k, L::IDESC, (s | k) != 0);
           }
         }
-        tcgen05_commit(&empty_bar[slot]);
+        if (share) tcgen05_commit_mc(&empty_bar[slot], mask_e);   // every CTA that fetches into this CTA's stage hears it
+        else tcgen05_commit(&empty_bar[slot]);
       }
       tcgen05_commit(&acc_full[acc]);
     }
   } else if (warp == 10) {
     if (lane == 0 && p.has_resid) {  // ---- TMA producer: residual ring (chunk c of a tile = columns col0 + 32 c .. + 31) ----
       int q = 0;
-      for (int tile = cluster_id; tile < tiles_total; tile += n_clusters) {
-        const int r0 = tile * BM;
+      for (int rd = cluster_id; rd * MG < tiles_total; rd += n_clusters) {
+        const int r0 = (rd * MG + mrow) * BM;
         for (int c = 0; c < L::NCH; ++c, ++q) {
           const int slot = q % L::RB;
           mbar_wait(&r_empty[slot], ((q / L::RB) & 1) ^ 1);
@@ -225,13 +284,13 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     const uint32_t swz = (uint32_t)(row & 7);
     const uint32_t x_local = smem_u32(xchg), x_remote = map_to_cta(x_local, rank ^ 1u);
     const uint32_t xbar_remote = map_to_cta(smem_u32(x_bar), rank ^ 1u);
-    const int src = (int)rank * 2 + grp;
+    const int src = nh * 2 + grp;                      // which of the four owners of a row this thread is
     const long plane = (long)p.M * p.ldo_p;
     float y[L::NT];
     int it = 0;
-    for (int tile = cluster_id; tile < tiles_total; tile += n_clusters, ++it) {
+    for (int rd = cluster_id; rd * MG < tiles_total; rd += n_clusters, ++it) {
       const int acc = it & 1;
-      const long m = (long)tile * BM + row;
+      const long m = (long)(rd * MG + mrow) * BM + row;
       const bool row_ok = m < p.M;
       mbar_wait(&acc_full[acc], (it >> 1) & 1);
       tcgen05_fence_after();
@@ -281,14 +340,16 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       for (int i = 0; i < L::NT; ++i) { const float dd = y[i] - mean_t; m2_t = fmaf(dd, dd, m2_t); }
       const uint32_t xoff = (uint32_t)((((it & 1) * 4 + src) * BM + row) * 8);
       xchg[((it & 1) * 4 + src) * BM + row] = make_float2(mean_t, m2_t);
-      st_cluster_f32x2(x_remote + xoff, mean_t, m2_t);
-      __syncwarp();
-      if (lane == 0) {
-        asm volatile("fence.acq_rel.cluster;" ::: "memory");
-        mbar_arrive_cluster(map_to_cta(smem_u32(x_bar), rank));   // own barrier, same release scope
-        mbar_arrive_cluster(xbar_remote);
+      if (!(p.debug & 4)) {
+        st_cluster_f32x2(x_remote + xoff, mean_t, m2_t);
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("fence.acq_rel.cluster;" ::: "memory");
+          mbar_arrive_cluster(map_to_cta(smem_u32(x_bar), rank));   // own barrier, same release scope
+          mbar_arrive_cluster(xbar_remote);
+        }
+        mbar_wait_cluster(x_bar, it & 1);
       }
-      mbar_wait_cluster(x_bar, it & 1);
       float mean = 0.f, m2 = 0.f;
       float2 part[4];
 #pragma unroll
@@ -310,7 +371,7 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
           yy[u * 4 + 0] = fmaf((yy[u * 4 + 0] - mean) * rstd, g4.x, t4.x); yy[u * 4 + 1] = fmaf((yy[u * 4 + 1] - mean) * rstd, g4.y, t4.y);
           yy[u * 4 + 2] = fmaf((yy[u * 4 + 2] - mean) * rstd, g4.z, t4.z); yy[u * 4 + 3] = fmaf((yy[u * 4 + 3] - mean) * rstd, g4.w, t4.w);
         }
-        if (row_ok) {
+        if (row_ok && !(p.debug & 2)) {
           const int col = col0 + c * 32;
           if (p.out != nullptr) {
             float* dst = p.out + m * p.ldo + col;
@@ -341,32 +402,67 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   }
 }
 
-template <int C, bool X3>
-int launch_cl(const TapGemm& g, cudaStream_t st) {
+template <int C, bool X3, int MG>
+int launch_cl(const TapGemm& g, bool a_mc, cudaStream_t st) {
   using L = CCfg<C, X3>;
+  constexpr int CS = 2 * MG;
   const uint64_t M = (uint64_t)g.B * g.L;
   static unsigned long long configured = 0;   // per-device bit mask
   int rc;
-  if ((rc = ensure_smem_attr(gemm_ln_cluster_kernel<C, X3>, L::SMEM, &configured))) return rc;
-  CUtensorMap ma, mb, mb_lo, mr;
+  if ((rc = ensure_smem_attr(gemm_ln_cluster_kernel<C, X3, MG>, L::SMEM, &configured))) return rc;
+  CUtensorMap ma, ma64, mb, mb_lo, mr;
   const uint64_t arow = (uint64_t)g.K * 2;
   if ((rc = make_map(&ma, g.xp, g.K, M, X3 ? 2 : 1, arow, arow * M, BM, true))) return rc;
-  if ((rc = make_map(&mb, g.w_hi, g.K, C, 1, arow, arow * C, L::H, true))) return rc;
-  if ((rc = make_map(&mb_lo, X3 ? g.w_lo : g.w_hi, g.K, C, 1, arow, arow * C, L::H, true))) return rc;
+  if ((rc = make_map(&ma64, g.xp, g.K, M, X3 ? 2 : 1, arow, arow * M, 64, true))) return rc;
+  if ((rc = make_map(&mb, g.w_hi, g.K, C, 1, arow, arow * C, L::H / MG, true))) return rc;
+  if ((rc = make_map(&mb_lo, X3 ? g.w_lo : g.w_hi, g.K, C, 1, arow, arow * C, L::H / MG, true))) return rc;
   if (g.resid) { if ((rc = make_map(&mr, g.resid, C, M, 1, (uint64_t)g.ldr * 4, (uint64_t)g.ldr * 4 * M, BM, false))) return rc; }
   else mr = ma;
   ClParams p;
   p.M = (int)M; p.K = g.K; p.bias = g.bias; p.gamma = g.ln_gamma; p.beta = g.ln_beta; p.eps = g.ln_eps;
-  p.has_resid = g.resid != nullptr;
+  p.a_mc = (a_mc || MG > 1) ? 1 : 0;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FS2_LN_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
+  p.has_resid = g.resid != nullptr && !(p.debug & 1);
   p.out = g.out; p.ldo = g.ldo;
   p.outp = g.outp; p.ldo_p = g.ldo_p; p.outp_lo = (g.outp && g.outp_lo) ? g.outp + (long)M * g.ldo_p : nullptr;
   p.a_inv = g.a_inv; p.w_inv = g.w_inv;
   const int tiles = (int)((M + BM - 1) / BM);
-  const int pairs = sm_count_current() / 2;
-  const int grid = 2 * (tiles < pairs ? tiles : pairs);
-  gemm_ln_cluster_kernel<C, X3><<<grid, CL_THREADS, L::SMEM, st>>>(ma, mb, mb_lo, mr, p);
+  const int rounds = (tiles + MG - 1) / MG;
+  const int slots = sm_count_current() / CS;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(CS * (rounds < slots ? rounds : slots)), 1, 1);
+  cfg.blockDim = dim3(CL_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = L::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  FS2_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_ln_cluster_kernel<C, X3, MG>, ma, ma64, mb, mb_lo, mr, p));
   FS2_LAUNCH_CHECK();
   return FS2_OK;
+}
+
+// FS2_LN_MG: row tiles per cluster (1, 2 or 4 -> clusters of 2, 4 or 8 CTAs); FS2_LN_AMC=1: with MG = 1, the pair shares its A tile.
+// Measured (c2, 3xF16, same box): MG = 1 0.34 / 0.56 ms per step for out-projection / w_2, MG = 2 0.50 / 0.79, MG = 4 0.50 / 0.82; A
+// sharing alone is within noise.  The lock step of 4 - 8 CTAs costs more than the halved operand traffic saves: default MG = 1,
+// no multicast; the variants stay selectable (and tested) for the record.
+int ln_mg() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FS2_LN_MG"); v = e ? atoi(e) : 2; if (v != 1 && v != 2 && v != 4) v = 2; }
+  return v;
+}
+bool ln_amc() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FS2_LN_AMC"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+template <int C, bool X3>
+int launch_any(const TapGemm& g, cudaStream_t st) {
+  const int mg = ln_mg();
+  if (mg == 4) return launch_cl<C, X3, 4>(g, true, st);
+  if (mg == 2) return launch_cl<C, X3, 2>(g, true, st);
+  return launch_cl<C, X3, 1>(g, ln_amc(), st);
 }
 }  // namespace
 
@@ -384,8 +480,8 @@ int gemm_ln_planes(const TapGemm& g, cudaStream_t st) {
   FS2_REQUIRE(!g.outp || (g.ldo_p % 16 == 0 && (reinterpret_cast<uintptr_t>(g.outp) & 31) == 0 && (((long)g.B * g.L * g.ldo_p) % 16) == 0),
               "gemm_ln_planes: output plane rows must be 32-byte aligned");
   if ((uint64_t)g.B * g.L == 0) return FS2_OK;
-  if (g.N == 384) return g.precise ? launch_cl<384, true>(g, st) : launch_cl<384, false>(g, st);
-  return g.precise ? launch_cl<256, true>(g, st) : launch_cl<256, false>(g, st);
+  if (g.N == 384) return g.precise ? launch_any<384, true>(g, st) : launch_any<384, false>(g, st);
+  return g.precise ? launch_any<256, true>(g, st) : launch_any<256, false>(g, st);
 }
 
 }  // namespace fs2
