@@ -26,7 +26,8 @@
 // CTA writes has consumed it (the MMA warp's tcgen05.commit arrives, multicast, on the empty barriers of its row mate
 // and its column mates).  Correct (tested in every configuration) but measured SLOWER than plain pairs -- the lock step
 // of 4 - 8 CTAs costs more than the halved L2 -> SM traffic saves -- so the default is MG = 1 without multicast.
-// Where the time goes (FS2_LN_DEBUG experiments, tools/ln_time.py, 3xF16 out-projection): removing the output stores
+// Where the time goes (experiments with a build that could switch each part off, profiles/r02_ln_time_debug*.log; the
+// switches cost registers -- spills -- in the epilogue and were removed again; 3xF16 out-projection): removing the output stores
 // -31 %, the residual -15 %, the statistics exchange -13 %, all operand loads -30 % of what is left: the row-per-thread
 // 256-bit stores of three output tensors are the largest single cost.
 // Warp roles (352 threads): 0..7 = epilogue (warp & 3 = TMEM lane quarter, warp / 4 = column group; the groups take
@@ -75,7 +76,6 @@ struct CCfg {
 struct ClParams {
   int M, K;
   int a_mc;                                       // A tile fetched half / half by the two CTAs of a row tile (multicast)
-  int debug;                                      // FS2_LN_DEBUG (timing experiments only): 1 no residual, 2 no stores, 4 no statistics exchange
   const float* bias; const float* gamma; const float* beta; float eps;
   int has_resid;
   float* out; int ldo;
@@ -139,7 +139,7 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 }
 
 template <int C, bool X3, int MG>
-__global__ void __launch_bounds__(CL_THREADS, 1)
+__global__ void __maxnreg__(184)
 gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a64,
                        const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b_lo,
                        const __grid_constant__ CUtensorMap tmap_r, ClParams p) {
@@ -205,14 +205,6 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
           const int slot = n % L::STAGES;
           mbar_wait(&empty_bar[slot], ((n / L::STAGES) & 1) ^ 1);
           uint8_t* st = tiles + (size_t)slot * L::STAGE_BYTES;
-          if (p.debug & 24) {                           // timing experiments: 8 = no weight loads, 16 = no A loads (stale operands)
-            const uint32_t bytes = ((p.debug & 8) ? 0u : (uint32_t)(L::PL * L::B_BYTES)) + ((p.debug & 16) ? 0u : (uint32_t)(L::PL * A_BYTES));
-            if (bytes == 0) { mbar_arrive(&full_bar[slot]); continue; }
-            mbar_expect_tx(&full_bar[slot], bytes);
-            if (!(p.debug & 16)) { tma_load_3d(st, &tmap_a, &full_bar[slot], s * BKE, r0, 0); if (X3) tma_load_3d(st + L::A_LO, &tmap_a, &full_bar[slot], s * BKE, r0, 1); }
-            if (!(p.debug & 8)) { tma_load_3d(st + L::B_HI, &tmap_b, &full_bar[slot], s * BKE, col0, 0); if (X3) tma_load_3d(st + L::B_LO, &tmap_b_lo, &full_bar[slot], s * BKE, col0, 0); }
-            continue;
-          }
           mbar_expect_tx(&full_bar[slot], L::STAGE_BYTES);   // everything that lands in this stage, whoever fetches it
           if (p.a_mc) {                                // rows [64 nh, 64 nh + 64) of the A tile, for both column halves
             tma_load_3d_mc(st + nh * (64 * 128), &tmap_a64, &full_bar[slot], s * BKE, r0 + nh * 64, 0, mask_a);
@@ -340,16 +332,14 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       for (int i = 0; i < L::NT; ++i) { const float dd = y[i] - mean_t; m2_t = fmaf(dd, dd, m2_t); }
       const uint32_t xoff = (uint32_t)((((it & 1) * 4 + src) * BM + row) * 8);
       xchg[((it & 1) * 4 + src) * BM + row] = make_float2(mean_t, m2_t);
-      if (!(p.debug & 4)) {
-        st_cluster_f32x2(x_remote + xoff, mean_t, m2_t);
-        __syncwarp();
-        if (lane == 0) {
-          asm volatile("fence.acq_rel.cluster;" ::: "memory");
-          mbar_arrive_cluster(map_to_cta(smem_u32(x_bar), rank));   // own barrier, same release scope
-          mbar_arrive_cluster(xbar_remote);
-        }
-        mbar_wait_cluster(x_bar, it & 1);
+      st_cluster_f32x2(x_remote + xoff, mean_t, m2_t);
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("fence.acq_rel.cluster;" ::: "memory");
+        mbar_arrive_cluster(map_to_cta(smem_u32(x_bar), rank));   // own barrier, same release scope
+        mbar_arrive_cluster(xbar_remote);
       }
+      mbar_wait_cluster(x_bar, it & 1);
       float mean = 0.f, m2 = 0.f;
       float2 part[4];
 #pragma unroll
@@ -371,7 +361,7 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
           yy[u * 4 + 0] = fmaf((yy[u * 4 + 0] - mean) * rstd, g4.x, t4.x); yy[u * 4 + 1] = fmaf((yy[u * 4 + 1] - mean) * rstd, g4.y, t4.y);
           yy[u * 4 + 2] = fmaf((yy[u * 4 + 2] - mean) * rstd, g4.z, t4.z); yy[u * 4 + 3] = fmaf((yy[u * 4 + 3] - mean) * rstd, g4.w, t4.w);
         }
-        if (row_ok && !(p.debug & 2)) {
+        if (row_ok) {
           const int col = col0 + c * 32;
           if (p.out != nullptr) {
             float* dst = p.out + m * p.ldo + col;
@@ -421,8 +411,7 @@ int launch_cl(const TapGemm& g, bool a_mc, cudaStream_t st) {
   ClParams p;
   p.M = (int)M; p.K = g.K; p.bias = g.bias; p.gamma = g.ln_gamma; p.beta = g.ln_beta; p.eps = g.ln_eps;
   p.a_mc = (a_mc || MG > 1) ? 1 : 0;
-  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FS2_LN_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
-  p.has_resid = g.resid != nullptr && !(p.debug & 1);
+  p.has_resid = g.resid != nullptr;
   p.out = g.out; p.ldo = g.ldo;
   p.outp = g.outp; p.ldo_p = g.ldo_p; p.outp_lo = (g.outp && g.outp_lo) ? g.outp + (long)M * g.ldo_p : nullptr;
   p.a_inv = g.a_inv; p.w_inv = g.w_inv;
