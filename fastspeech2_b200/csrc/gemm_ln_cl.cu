@@ -25,7 +25,8 @@
 // half each fetch 1/MG of the weight rows for all of them; a stage is refilled only when every CTA that reads what this
 // CTA writes has consumed it (the MMA warp's tcgen05.commit arrives, multicast, on the empty barriers of its row mate
 // and its column mates).  Correct (tested in every configuration) but measured SLOWER than plain pairs -- the lock step
-// of 4 - 8 CTAs costs more than the halved L2 -> SM traffic saves -- so the default is MG = 1 without multicast.
+// of 4 - 8 CTAs costs more than the halved L2 -> SM traffic saves -- so the default is MG = 1 (pairs; the pair shares its A
+// tile by multicast, FS2_LN_AMC = 1, which measured 5 - 10 % faster than separate fetches).
 // Where the time goes (experiments with a build that could switch each part off, profiles/r02_ln_time_debug*.log; the
 // switches cost registers -- spills -- in the epilogue and were removed again; 3xF16 out-projection): removing the output stores
 // -31 %, the residual -15 %, the statistics exchange -13 %, all operand loads -30 % of what is left: the row-per-thread
@@ -139,7 +140,7 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 }
 
 template <int C, bool X3, int MG>
-__global__ void __maxnreg__(184)
+__global__ void __launch_bounds__(CL_THREADS, 1)
 gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a64,
                        const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b_lo,
                        const __grid_constant__ CUtensorMap tmap_r, ClParams p) {
@@ -433,12 +434,12 @@ int launch_cl(const TapGemm& g, bool a_mc, cudaStream_t st) {
 }
 
 // FS2_LN_MG: row tiles per cluster (1, 2 or 4 -> clusters of 2, 4 or 8 CTAs); FS2_LN_AMC=1: with MG = 1, the pair shares its A tile.
-// Measured (c2, 3xF16, same box): MG = 1 0.34 / 0.56 ms per step for out-projection / w_2, MG = 2 0.50 / 0.79, MG = 4 0.50 / 0.82; A
-// sharing alone is within noise.  The lock step of 4 - 8 CTAs costs more than the halved operand traffic saves: default MG = 1,
-// no multicast; the variants stay selectable (and tested) for the record.
+// Measured (c2, 3xF16, same box, gpurun_out/bench_t_*.json): MG = 1 0.34 / 0.56 ms per step for out-projection / w_2 (0.38 / 0.60
+// without A sharing), MG = 2 0.50 / 0.79, MG = 4 0.50 / 0.82.  The lock step of 4 - 8 CTAs costs more than the halved operand
+// traffic saves: default MG = 1 with the pair sharing its A tile; the variants stay selectable (and tested) for the record.
 int ln_mg() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("FS2_LN_MG"); v = e ? atoi(e) : 2; if (v != 1 && v != 2 && v != 4) v = 2; }
+  if (v < 0) { const char* e = getenv("FS2_LN_MG"); v = e ? atoi(e) : 1; if (v != 1 && v != 2 && v != 4) v = 1; }
   return v;
 }
 bool ln_amc() {

@@ -236,3 +236,76 @@ def synthesize_sharded(model, xs: torch.Tensor, ilens: torch.Tensor, group: Opti
     if world == 1:
         return after, olens
     return gather_mels(after, olens, group)
+
+
+class GradientSync:
+    """Data-parallel training step of SURVEY.md section 8f-1 (the reference itself has no data parallelism; its loop is
+    `loss.backward(); clip_grad_norm_; optimizer.step()`, train_fastspeech.py:117-124): every rank runs
+    `loss, report = model(...); loss.backward()` on its own utterance shard, then
+
+        sync = GradientSync(model)          # once: flat fp32 bucket, every parameter's .grad becomes a view of it
+        ...
+        loss.backward()
+        sync.all_reduce()                   # ONE collective over the whole bucket (NCCL ring / NVLS over NVLink), mean over ranks
+        clip_grad_norm_(...); optimizer.step(); sync.zero_grad()
+
+    The whole model is 35 M parameters = 141 MB of fp32 gradients: one bucket, one launch -- with NVSwitch the cost is
+    launch latency plus bytes, so splitting into DDP-style 25 MB buckets buys nothing once backward has finished, and
+    the backward of this model is ~100 short launches with nothing long to hide a collective behind.  Semantics are
+    those of torch DDP: the mean over ranks of per-shard masked-mean losses (equal to the single-process gradient when
+    shards hold the same number of valid frames / phonemes, as the bucketed sampler arranges).
+    `broadcast_parameters()` makes every rank start from the root's weights (and BatchNorm running statistics).
+    Backend-agnostic (gloo on CPU for the host-logic test)."""
+
+    def __init__(self, model: torch.nn.Module, group: Optional[dist.ProcessGroup] = None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        if not self.params:
+            raise ValueError("GradientSync: the model has no trainable parameters")
+        dev, dt = self.params[0].device, self.params[0].dtype
+        if any(p.device != dev or p.dtype != dt for p in self.params):
+            raise ValueError("GradientSync: parameters must share one device and dtype")
+        self.model = model
+        sizes = [p.numel() for p in self.params]
+        # 128-byte aligned segments so every view is a legal vector-access target for the backward kernels
+        self.offsets, off = [], 0
+        for n in sizes:
+            self.offsets.append(off)
+            off += (n + 31) // 32 * 32
+        self.flat = torch.zeros(off, dtype=dt, device=dev)
+        for p, o, n in zip(self.params, self.offsets, sizes):
+            view = self.flat[o:o + n].view_as(p)
+            if p.grad is not None:
+                view.copy_(p.grad)
+            p.grad = view
+
+    def _check_views(self) -> None:
+        for p, o in zip(self.params, self.offsets):
+            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + o * self.flat.element_size():
+                raise RuntimeError("GradientSync: a parameter's .grad no longer aliases the bucket "
+                                   "(use sync.zero_grad(), not optimizer.zero_grad(set_to_none=True))")
+
+    def all_reduce(self) -> None:
+        """Mean of the gradient bucket over the ranks, in place; enqueued on the current stream (NCCL) / blocking (gloo)."""
+        self._check_views()
+        if self.world == 1:
+            return
+        if self.flat.is_cuda:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+        else:                                   # gloo has no AVG
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat.div_(self.world)
+
+    def zero_grad(self) -> None:
+        self.flat.zero_()
+
+    def broadcast_parameters(self, src: int = 0) -> None:
+        if self.world == 1:
+            return
+        with torch.no_grad():
+            for t in list(self.model.parameters()) + [b for b in self.model.buffers() if b.dtype.is_floating_point or b.dtype == torch.int64]:
+                dist.broadcast(t.data, src=src, group=self.group)
+        inv = getattr(self.model, "invalidate", None)
+        if callable(inv):
+            inv()                               # packed weight arena follows the new values
