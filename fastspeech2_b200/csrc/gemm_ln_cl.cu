@@ -43,18 +43,24 @@ namespace fs2 {
 namespace {
 using namespace tc;
 
-constexpr int BM = 128, BKE = 64;                      // fp16 K elements per stage = one 128-byte swizzle row
-constexpr int A_BYTES = BM * 128;                      // 16 KB per A plane per stage
+constexpr int BM = 128;
 constexpr int CHUNK_BYTES = BM * 128;                  // residual chunk: 128 rows x 32 fp32
 constexpr int CL_THREADS = 352;
 
-template <int C, bool X3>
+// KH ("half-depth K"): a stage holds 32 instead of 64 fp16 of K per row (64-byte swizzle rows).  Same bytes in flight, twice
+// the stages: the 3xF16 C = 384 stage is 80 KB at K = 64, so only two fit and the ring cannot cover the L2 latency (each slot is
+// re-requested only after 1152 cycles of MMA work on it have retired: per-stage time (R + M) / 2 with refill time R ~ 3000
+// cycles); four 40 KB stages bring that to max(M, (R' + M) / 4).
+template <int C, bool X3, bool KH = false>
 struct CCfg {
+  static constexpr int BKE = KH ? 32 : 64;              // fp16 K elements per stage = one swizzle row
+  static constexpr int ROWB = BKE * 2;                  // bytes per operand row in a stage (128- or 64-byte swizzle)
+  static constexpr int A_BYTES = BM * ROWB;             // 16 (8) KB per A plane per stage
   static constexpr int H = C / 2;                       // columns per CTA
   static constexpr int NT = H / 2;                      // values per epilogue thread
   static constexpr int NJ = NT / 32;                    // 32-column chunks per thread
   static constexpr int NCH = H / 32;                    // residual chunks per tile and CTA
-  static constexpr int B_BYTES = H * 128;
+  static constexpr int B_BYTES = H * ROWB;
   static constexpr int PL = X3 ? 2 : 1;
   static constexpr int STAGE_BYTES = PL * (A_BYTES + B_BYTES);
   static constexpr int A_LO = A_BYTES, B_HI = PL * A_BYTES, B_LO = B_HI + B_BYTES;
@@ -63,7 +69,7 @@ struct CCfg {
   static constexpr int FIXED = VEC_BYTES + XCHG_BYTES + 512 /*barriers*/ + 1024 /*alignment slack*/;
   static constexpr int BUDGET = 227 * 1024 - FIXED;
   // a full tile of residual chunks when at least 2 (3xF16) / 3 (f16) operand stages still fit, else half a tile
-  static constexpr int MIN_STAGES = X3 ? 2 : 3;
+  static constexpr int MIN_STAGES = KH ? 4 : (X3 ? 2 : 3);
   static constexpr int RB = (BUDGET - NCH * CHUNK_BYTES) / STAGE_BYTES >= MIN_STAGES ? NCH : NCH / 2;
   static constexpr int STAGES_RAW = (BUDGET - RB * CHUNK_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
@@ -77,6 +83,7 @@ struct CCfg {
 struct ClParams {
   int M, K;
   int a_mc;                                       // A tile fetched half / half by the two CTAs of a row tile (multicast)
+  int prefetch;                                   // FS2_GEMM_PREFETCH (default 0: measured slower, see the producer loop): L2 prefetch of the next row tile's A planes and residual rows
   const float* bias; const float* gamma; const float* beta; float eps;
   int has_resid;
   float* out; int ldo;
@@ -139,13 +146,14 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   return v;
 }
 
-template <int C, bool X3, int MG>
+template <int C, bool X3, int MG, bool KH>
 __global__ void __launch_bounds__(CL_THREADS, 1)
 gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a64,
                        const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b_lo,
                        const __grid_constant__ CUtensorMap tmap_r, ClParams p) {
-  using L = CCfg<C, X3>;
+  using L = CCfg<C, X3, KH>;
   constexpr int CS = 2 * MG;                    // cluster size
+  constexpr int BKE = L::BKE, ROWB = L::ROWB;
   constexpr int BROWS = L::H / MG;              // weight rows this CTA fetches per stage (for all its column mates)
   static_assert(BROWS % 8 == 0, "weight slice must keep the 8-row swizzle atom");
   extern __shared__ uint8_t smem_raw[];
@@ -164,7 +172,7 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const int steps = (p.K + BKE - 1) / BKE;
+  const int steps = (p.K + L::BKE - 1) / L::BKE;
   const int tiles_total = (p.M + BM - 1) / BM;
   const int cluster_id = blockIdx.x / CS, n_clusters = gridDim.x / CS;
   const int nh = (int)(rank & 1u), mrow = (int)(rank >> 1);      // column half, row tile inside the cluster
@@ -202,21 +210,26 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       int n = 0;
       for (int rd = cluster_id; rd * MG < tiles_total; rd += n_clusters) {
         const int r0 = (rd * MG + mrow) * BM;        // a row tile past the end is all zero fill (its mates still need this CTA's share)
+        // L2 prefetch of the next row tile's A planes (one K chunk per step, by the column-half-0 CTA of each row tile): the A
+        // planes are first-touch DRAM reads, and the 2 - 4 stage ring cannot cover DRAM latency
+        const int r0n = ((rd + n_clusters) * MG + mrow) * BM;
+        const bool pf = p.prefetch && nh == 0 && r0n < p.M;
         for (int s = 0; s < steps; ++s, ++n) {
+          if (pf) { tma_prefetch_3d(&tmap_a, s * BKE, r0n, 0); if (X3) tma_prefetch_3d(&tmap_a, s * BKE, r0n, 1); }
           const int slot = n % L::STAGES;
           mbar_wait(&empty_bar[slot], ((n / L::STAGES) & 1) ^ 1);
           uint8_t* st = tiles + (size_t)slot * L::STAGE_BYTES;
           mbar_expect_tx(&full_bar[slot], L::STAGE_BYTES);   // everything that lands in this stage, whoever fetches it
           if (p.a_mc) {                                // rows [64 nh, 64 nh + 64) of the A tile, for both column halves
-            tma_load_3d_mc(st + nh * (64 * 128), &tmap_a64, &full_bar[slot], s * BKE, r0 + nh * 64, 0, mask_a);
-            if (X3) tma_load_3d_mc(st + L::A_LO + nh * (64 * 128), &tmap_a64, &full_bar[slot], s * BKE, r0 + nh * 64, 1, mask_a);
+            tma_load_3d_mc(st + nh * (64 * ROWB), &tmap_a64, &full_bar[slot], s * BKE, r0 + nh * 64, 0, mask_a);
+            if (X3) tma_load_3d_mc(st + L::A_LO + nh * (64 * ROWB), &tmap_a64, &full_bar[slot], s * BKE, r0 + nh * 64, 1, mask_a);
           } else {
             tma_load_3d(st, &tmap_a, &full_bar[slot], s * BKE, r0, 0);
             if (X3) tma_load_3d(st + L::A_LO, &tmap_a, &full_bar[slot], s * BKE, r0, 1);
           }
           if (MG > 1) {                                // weight rows [BROWS mrow, +BROWS) of this column half, for every row tile
-            tma_load_3d_mc(st + L::B_HI + mrow * (BROWS * 128), &tmap_b, &full_bar[slot], s * BKE, col0 + mrow * BROWS, 0, (uint16_t)mask_b);
-            if (X3) tma_load_3d_mc(st + L::B_LO + mrow * (BROWS * 128), &tmap_b_lo, &full_bar[slot], s * BKE, col0 + mrow * BROWS, 0, (uint16_t)mask_b);
+            tma_load_3d_mc(st + L::B_HI + mrow * (BROWS * ROWB), &tmap_b, &full_bar[slot], s * BKE, col0 + mrow * BROWS, 0, (uint16_t)mask_b);
+            if (X3) tma_load_3d_mc(st + L::B_LO + mrow * (BROWS * ROWB), &tmap_b_lo, &full_bar[slot], s * BKE, col0 + mrow * BROWS, 0, (uint16_t)mask_b);
           } else {
             tma_load_3d(st + L::B_HI, &tmap_b, &full_bar[slot], s * BKE, col0, 0);
             if (X3) tma_load_3d(st + L::B_LO, &tmap_b_lo, &full_bar[slot], s * BKE, col0, 0);
@@ -226,6 +239,7 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     }
   } else if (warp == 9) {
     // ---- MMA issuer: whole warp, one lane elected inside each tcgen05 asm ----
+    auto mkdesc = [](uint32_t a) { return KH ? make_sw64_kmajor_desc(a) : make_sw128_kmajor_desc(a); };
     int n = 0, it = 0;
     for (int rd = cluster_id; rd * MG < tiles_total; rd += n_clusters, ++it) {
       const int acc = it & 1;
@@ -237,11 +251,11 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         mbar_wait(&full_bar[slot], (n / L::STAGES) & 1);
         tcgen05_fence_after();
         const uint32_t base = smem_u32(tiles + (size_t)slot * L::STAGE_BYTES);
-        const uint64_t a_hi = make_sw128_kmajor_desc(base), b_hi = make_sw128_kmajor_desc(base + L::B_HI);
+        const uint64_t a_hi = mkdesc(base), b_hi = mkdesc(base + L::B_HI);
 #pragma unroll
         for (int k = 0; k < BKE / 16; ++k) {
           if (X3) {
-            const uint64_t a_lo = make_sw128_kmajor_desc(base + L::A_LO), b_lo = make_sw128_kmajor_desc(base + L::B_LO);
+            const uint64_t a_lo = mkdesc(base + L::A_LO), b_lo = mkdesc(base + L::B_LO);
             umma_f16(d, a_lo + 2 * k, b_hi + 2 * k, L::IDESC, (s | k) != 0);   // small terms first
             umma_f16(d, a_hi + 2 * k, b_lo + 2 * k, L::IDESC, 1);
             umma_f16(d, a_hi + 2 * k, b_hi + 2 * k, L::IDESC, 1);
@@ -259,7 +273,10 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       int q = 0;
       for (int rd = cluster_id; rd * MG < tiles_total; rd += n_clusters) {
         const int r0 = (rd * MG + mrow) * BM;
+        const int r0n = ((rd + n_clusters) * MG + mrow) * BM;
+        const bool pf = p.prefetch && r0n < p.M;     // the residual rows are first-touch DRAM reads too
         for (int c = 0; c < L::NCH; ++c, ++q) {
+          if (pf) tma_prefetch_3d(&tmap_r, col0 + c * 32, r0n, 0);
           const int slot = q % L::RB;
           mbar_wait(&r_empty[slot], ((q / L::RB) & 1) ^ 1);
           mbar_expect_tx(&r_full[slot], CHUNK_BYTES);
@@ -393,26 +410,27 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   }
 }
 
-template <int C, bool X3, int MG>
+template <int C, bool X3, int MG, bool KH = false>
 int launch_cl(const TapGemm& g, bool a_mc, cudaStream_t st) {
-  using L = CCfg<C, X3>;
+  using L = CCfg<C, X3, KH>;
   constexpr int CS = 2 * MG;
   const uint64_t M = (uint64_t)g.B * g.L;
   static unsigned long long configured = 0;   // per-device bit mask
   int rc;
-  if ((rc = ensure_smem_attr(gemm_ln_cluster_kernel<C, X3, MG>, L::SMEM, &configured))) return rc;
+  if ((rc = ensure_smem_attr(gemm_ln_cluster_kernel<C, X3, MG, KH>, L::SMEM, &configured))) return rc;
   CUtensorMap ma, ma64, mb, mb_lo, mr;
   const uint64_t arow = (uint64_t)g.K * 2;
-  if ((rc = make_map(&ma, g.xp, g.K, M, X3 ? 2 : 1, arow, arow * M, BM, true))) return rc;
-  if ((rc = make_map(&ma64, g.xp, g.K, M, X3 ? 2 : 1, arow, arow * M, 64, true))) return rc;
-  if ((rc = make_map(&mb, g.w_hi, g.K, C, 1, arow, arow * C, L::H / MG, true))) return rc;
-  if ((rc = make_map(&mb_lo, X3 ? g.w_lo : g.w_hi, g.K, C, 1, arow, arow * C, L::H / MG, true))) return rc;
+  if ((rc = make_map(&ma, g.xp, g.K, M, X3 ? 2 : 1, arow, arow * M, BM, true, KH))) return rc;
+  if ((rc = make_map(&ma64, g.xp, g.K, M, X3 ? 2 : 1, arow, arow * M, 64, true, KH))) return rc;
+  if ((rc = make_map(&mb, g.w_hi, g.K, C, 1, arow, arow * C, L::H / MG, true, KH))) return rc;
+  if ((rc = make_map(&mb_lo, X3 ? g.w_lo : g.w_hi, g.K, C, 1, arow, arow * C, L::H / MG, true, KH))) return rc;
   if (g.resid) { if ((rc = make_map(&mr, g.resid, C, M, 1, (uint64_t)g.ldr * 4, (uint64_t)g.ldr * 4 * M, BM, false))) return rc; }
   else mr = ma;
   ClParams p;
   p.M = (int)M; p.K = g.K; p.bias = g.bias; p.gamma = g.ln_gamma; p.beta = g.ln_beta; p.eps = g.ln_eps;
   p.a_mc = (a_mc || MG > 1) ? 1 : 0;
   p.has_resid = g.resid != nullptr;
+  { static int pfe = -1; if (pfe < 0) { const char* e = getenv("FS2_GEMM_PREFETCH"); pfe = e ? atoi(e) : 0; } p.prefetch = pfe; }
   p.out = g.out; p.ldo = g.ldo;
   p.outp = g.outp; p.ldo_p = g.ldo_p; p.outp_lo = (g.outp && g.outp_lo) ? g.outp + (long)M * g.ldo_p : nullptr;
   p.a_inv = g.a_inv; p.w_inv = g.w_inv;
@@ -428,7 +446,7 @@ int launch_cl(const TapGemm& g, bool a_mc, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  FS2_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_ln_cluster_kernel<C, X3, MG>, ma, ma64, mb, mb_lo, mr, p));
+  FS2_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_ln_cluster_kernel<C, X3, MG, KH>, ma, ma64, mb, mb_lo, mr, p));
   FS2_LAUNCH_CHECK();
   return FS2_OK;
 }
@@ -447,11 +465,23 @@ bool ln_amc() {
   if (v < 0) { const char* e = getenv("FS2_LN_AMC"); v = e ? atoi(e) : 1; }
   return v != 0;
 }
+// FS2_LN_KH: half-depth K stages (CCfg) for the 3xF16 C = 384 pairs, where only two full-depth stages fit: 1 = long-K launches
+// (K >= 512: w_2) only (default: w_2 0.58 -> 0.53 ms per c2 step, the K = 384 out-projection is epilogue-bound and unchanged),
+// 2 = every launch, 0 = off.
+int ln_kh() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FS2_LN_KH"); v = e ? atoi(e) : 1; }
+  return v;
+}
 template <int C, bool X3>
 int launch_any(const TapGemm& g, cudaStream_t st) {
   const int mg = ln_mg();
   if (mg == 4) return launch_cl<C, X3, 4>(g, true, st);
   if (mg == 2) return launch_cl<C, X3, 2>(g, true, st);
+  if constexpr (X3 && C == 384) {
+    const int kh = ln_kh();
+    if (kh == 2 || (kh == 1 && g.K >= 512)) return launch_cl<C, X3, 1, true>(g, ln_amc(), st);
+  }
   return launch_cl<C, X3, 1>(g, ln_amc(), st);
 }
 }  // namespace

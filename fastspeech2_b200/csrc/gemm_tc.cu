@@ -85,6 +85,7 @@ struct TcParams {
   // vt[(b*heads + h)*dk + d][t] with row pitch vt_lpad, for the attention kernel's K-major P.V operand
   float* vt_out; __half* vtp; __half* vtp_lo; int vt_col0, vt_dk, vt_heads, vt_lpad, vt_L;
   int debug;   // FS2_GEMM_DEBUG: bit0 skip tcgen05.ld, bit1 skip stores (profiling experiments only)
+  int prefetch;  // FS2_GEMM_PREFETCH (default 0: measured slower, see the producer loop): L2 prefetch of the next tile's activation rows
 };
 
 constexpr int pow2_at_least(int x) { return x <= 32 ? 32 : x <= 64 ? 64 : x <= 128 ? 128 : x <= 256 ? 256 : 512; }
@@ -168,7 +169,23 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int n0, b, t0, packed;
         tile_coords(tile, n0, b, t0, packed);
+        // Experiment (FS2_GEMM_PREFETCH=1, off by default): L2 prefetch of the NEXT tile's activation rows, one K chunk per
+        // pipeline step, by the one CTA whose next tile is the first column tile of its row tile.  Hypothesis: first-touch
+        // activations arrive with DRAM latency that the 3 - 8 stage ring cannot cover (ncu of the K = 384 q|k|v projection: TMA,
+        // MMA and epilogue warps each wait ~30 %, nothing saturated).  Measured on c2 / 3xF16: q|k|v 0.485 -> 0.51 ms, w_2
+        // (cluster kernel, same idea) 0.53 -> 0.64 ms: the extra TMA traffic costs more than the latency it hides.
+        const int nxt = tile + (int)gridDim.x;
+        int pn0 = 0, pb = 0, pt0 = 0, ppacked = 0;
+        bool pf = p.prefetch && nxt < total_tiles && (nxt % p.n_tiles) == 0;
+        if (pf) { tile_coords(nxt, pn0, pb, pt0, ppacked); pf = ppacked < 0; }
         for (int s = 0; s < steps; ++s, ++n) {
+          if (pf && s < 2 * kchunks && (s < kchunks || p.taps > 1)) {
+            // rows [t0 - pad, +128) in the first pass; a k > 1 convolution also reads up to row t0 + 127 + pad: second pass
+            const int pass = s < kchunks ? 0 : 1, kc = s - pass * kchunks;
+            const int r = pt0 + (pass ? p.pad : -p.pad);
+            tma_prefetch_3d(&tmap_a, kc * C::BKE, r, pb);
+            if (C::SPLIT16) tma_prefetch_3d(&tmap_a, kc * C::BKE, r, pb + p.B);
+          }
           const int slot = n % C::STAGES, round = n / C::STAGES;
           mbar_wait(&empty_bar[slot], (round & 1) ^ 1);
           const int j = s / kchunks, k0 = (s - j * kchunks) * C::BKE;
@@ -406,6 +423,7 @@ int launch(const TapGemm& g, cudaStream_t st) {
   p.outp = HALF ? g.outp : nullptr; p.ldo_p = g.ldo_p;
   p.outp_lo = (HALF && g.outp && g.outp_lo) ? g.outp + rows * g.ldo_p : nullptr;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FS2_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
+  { static int pfe = -1; if (pfe < 0) { const char* e = getenv("FS2_GEMM_PREFETCH"); pfe = e ? atoi(e) : 0; } p.prefetch = pfe; }
   p.vt_out = HALF ? nullptr : g.vt_out; p.vtp = HALF ? g.vtp : nullptr;
   p.vtp_lo = (HALF && g.vtp && g.outp_lo) ? g.vtp + (long)g.B * g.vt_heads * g.vt_dk * g.vt_lpad : nullptr;
   p.vt_col0 = g.vt_col0; p.vt_dk = g.vt_dk; p.vt_heads = g.vt_heads; p.vt_lpad = g.vt_lpad; p.vt_L = g.L;

@@ -59,6 +59,12 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// L2 prefetch of one box (no shared-memory destination, no barrier): issued a tile ahead so that first-touch operand tiles do not
+// arrive with DRAM latency (a 3-stage ring holds 192 KB in flight per SM, far less than latency x bandwidth needs)
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // 256-bit global store (STG.E.256): one full 32-byte sector per thread, so row-per-thread epilogues write
@@ -122,6 +128,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 // 8-row groups | version=1 [46,48) | base_offset [49,52) = 0 (tiles are 1024-B aligned) | layout [61,64) = 2.
 __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// same with 64-byte swizzle rows (32 fp16 of K per row): 512 B between 8-row groups, layout type 4 (SWIZZLE_64B)
+__device__ __forceinline__ uint64_t make_sw64_kmajor_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
 }
 
 
@@ -262,16 +272,17 @@ inline EncodeTiledFn encode_fn() {
 }
 // fp32 (or fp16) tensor {d0 (contiguous), d1, d2}, byte strides s1, s2; box {one 128-byte swizzle row = 32 floats or
 // 64 halfs, box1, 1}, zero OOB fill
+// half64 = true (fp16 only): box rows of 32 halfs = one 64-byte swizzle row (half-depth pipeline stages, gemm_ln_cl.cu)
 inline int make_map(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2, uint32_t box1,
-                    bool half = false) {
+                    bool half = false, bool half64 = false) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled unavailable (driver too old?)"); return FS2_ERR_CUDA; }
   cuuint64_t dims[3] = {d0, d1, d2};
   cuuint64_t strides[2] = {s1, s2};
-  cuuint32_t box[3] = {half ? 64u : 32u, box1, 1};
+  cuuint32_t box[3] = {half ? (half64 ? 32u : 64u) : 32u, box1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(m, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, (half && half64) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (dims %llu,%llu,%llu strides %llu,%llu box1 %u)", (int)r,

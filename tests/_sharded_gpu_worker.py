@@ -89,6 +89,40 @@ def main():
             assert torch.equal(pg.gathered_buffer(0), both)
             print("fused peer_store gather: bit-identical to all_gather of local results", flush=True)
     pg.close()
+    # data-parallel training step: every rank back-propagates its own batch, ONE all-reduce of the flat gradient
+    # bucket over NCCL; afterwards every rank holds the mean of the per-rank gradients and the replicas stay identical
+    from fastspeech2_b200.sharded import GradientSync
+    torch.manual_seed(1000 + rank)
+    mt = FeedForwardTransformer(68, 80, load_hp(), precision="fp32")
+    mt.load_state_dict(synthetic_state_dict(7 + rank), strict=True)      # replicas start different on purpose
+    mt = mt.to(dev).train()
+    sync = GradientSync(mt)
+    sync.broadcast_parameters(src=0)
+    keys = ("xs", "ilens", "ys", "olens", "ds", "es", "ps")
+    bt = make_batch(2, 20, 150, seed=40 + rank)
+    targs = [bt[k].to(dev) for k in keys]
+    opt = torch.optim.Adam(mt.parameters(), lr=1e-3)
+    for it in range(2):
+        sync.zero_grad()
+        loss, _ = mt(*targs)
+        loss.backward()
+        mine = sync.flat.clone()
+        both = torch.empty((world,) + mine.shape, device=dev)
+        dist.all_gather_into_tensor(both.view(-1), mine)
+        sync.all_reduce()
+        torch.cuda.synchronize()
+        want = both.mean(0)
+        err = float((sync.flat - want).abs().max()) / (float(want.abs().max()) + 1e-20)
+        assert err <= 1e-6, f"gradient all-reduce: relative error {err:.3e}"
+        assert float(mine.abs().max()) > 0 and not torch.equal(both[0], both[1])
+        torch.nn.utils.clip_grad_norm_(mt.parameters(), 1.0)
+        opt.step()
+    flat_w = torch.cat([p_.detach().reshape(-1) for p_ in mt.parameters()])
+    ws = torch.empty((world,) + flat_w.shape, device=dev)
+    dist.all_gather_into_tensor(ws.view(-1), flat_w)
+    assert torch.equal(ws[0], ws[1]), "replicas diverged after synchronised steps"
+    if rank == 0:
+        print("data-parallel train step: gradient bucket all-reduce == mean of per-rank gradients, replicas identical", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:

@@ -97,3 +97,58 @@ def _peer_worker(rank, world, port):
 
 def test_peer_gather_protocol_world2_cpu_fallback():
     mp.spawn(_peer_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
+def _grad_worker(rank, world, port):
+    """GradientSync (data-parallel training) on a stand-in module: after the one bucket all-reduce every rank
+    holds the mean of the per-rank gradients, equal to the gradient of the whole batch when shards are equally sized; the
+    optimizer then keeps the replicas bit-identical."""
+    from fastspeech2_b200.sharded import GradientSync
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(100 + rank)                       # replicas start DIFFERENT: broadcast must fix that
+        net = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Tanh(), torch.nn.BatchNorm1d(5), torch.nn.Linear(5, 3))
+        sync = GradientSync(net)
+        sync.broadcast_parameters(src=0)
+        ref = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Tanh(), torch.nn.BatchNorm1d(5), torch.nn.Linear(5, 3))
+        torch.manual_seed(100)
+        ref0 = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Tanh(), torch.nn.BatchNorm1d(5), torch.nn.Linear(5, 3))
+        for a, b in zip(net.parameters(), ref0.parameters()):
+            assert torch.equal(a, b)
+        net.eval(); ref0.eval()                             # BatchNorm on running statistics: shard losses add up exactly
+        g = torch.Generator().manual_seed(5)
+        x, y = torch.randn(8, 7, generator=g), torch.randn(8, 3, generator=g)
+        lo, hi = shard_bounds(8, rank, world)
+        opt = torch.optim.SGD(net.parameters(), lr=0.1)
+        for _ in range(2):
+            sync.zero_grad()
+            torch.nn.functional.mse_loss(net(x[lo:hi]), y[lo:hi]).backward()
+            sync.all_reduce()
+            for p in ref0.parameters():
+                p.grad = None
+            torch.nn.functional.mse_loss(ref0(x), y).backward()
+            for a, b in zip(net.parameters(), ref0.parameters()):
+                assert torch.allclose(a.grad, b.grad, rtol=1e-5, atol=1e-7), (a.grad, b.grad)
+            opt.step()
+            with torch.no_grad():
+                for p in ref0.parameters():
+                    p -= 0.1 * p.grad
+        flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+        both = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(both, flat)
+        assert torch.equal(both[0], both[1])                # replicas stayed in lock step
+        # a .grad that was re-created (set_to_none) no longer aliases the bucket: loud error, not a silent no-op
+        opt.zero_grad(set_to_none=True)
+        try:
+            sync.all_reduce()
+            raise AssertionError("expected GradientSync to notice the detached .grad")
+        except RuntimeError:
+            pass
+        del ref
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_sync_world2():
+    mp.spawn(_grad_worker, args=(2, _free_port()), nprocs=2, join=True)
