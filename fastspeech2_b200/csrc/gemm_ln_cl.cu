@@ -126,10 +126,13 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     __trap();
   }
 }
-__device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint16_t cta_mask) {
+// warp-convergent form (one lane elected inside the asm, tc_common.cuh)
+__device__ __forceinline__ void tma_load_3d_mc_elect(uint32_t dst_addr, const CUtensorMap* map, uint32_t bar_addr, int c0, int c1, int c2, uint16_t cta_mask) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;\n\t}"
+      ::"r"(dst_addr), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
       : "memory");
 }
 // MMA-completion arrive on the barrier at this offset in every CTA of `cta_mask`
@@ -206,34 +209,36 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 8) {
-    if (lane == 0) {  // ---- TMA producer: operand stages ----
-      int n = 0;
-      for (int rd = cluster_id; rd * MG < tiles_total; rd += n_clusters) {
-        const int r0 = (rd * MG + mrow) * BM;        // a row tile past the end is all zero fill (its mates still need this CTA's share)
-        // L2 prefetch of the next row tile's A planes (one K chunk per step, by the column-half-0 CTA of each row tile): the A
-        // planes are first-touch DRAM reads, and the 2 - 4 stage ring cannot cover DRAM latency
-        const int r0n = ((rd + n_clusters) * MG + mrow) * BM;
-        const bool pf = p.prefetch && nh == 0 && r0n < p.M;
-        for (int s = 0; s < steps; ++s, ++n) {
-          if (pf) { tma_prefetch_3d(&tmap_a, s * BKE, r0n, 0); if (X3) tma_prefetch_3d(&tmap_a, s * BKE, r0n, 1); }
-          const int slot = n % L::STAGES;
-          mbar_wait(&empty_bar[slot], ((n / L::STAGES) & 1) ^ 1);
-          uint8_t* st = tiles + (size_t)slot * L::STAGE_BYTES;
-          mbar_expect_tx(&full_bar[slot], L::STAGE_BYTES);   // everything that lands in this stage, whoever fetches it
-          if (p.a_mc) {                                // rows [64 nh, 64 nh + 64) of the A tile, for both column halves
-            tma_load_3d_mc(st + nh * (64 * ROWB), &tmap_a64, &full_bar[slot], s * BKE, r0 + nh * 64, 0, mask_a);
-            if (X3) tma_load_3d_mc(st + L::A_LO + nh * (64 * ROWB), &tmap_a64, &full_bar[slot], s * BKE, r0 + nh * 64, 1, mask_a);
-          } else {
-            tma_load_3d(st, &tmap_a, &full_bar[slot], s * BKE, r0, 0);
-            if (X3) tma_load_3d(st + L::A_LO, &tmap_a, &full_bar[slot], s * BKE, r0, 1);
-          }
-          if (MG > 1) {                                // weight rows [BROWS mrow, +BROWS) of this column half, for every row tile
-            tma_load_3d_mc(st + L::B_HI + mrow * (BROWS * ROWB), &tmap_b, &full_bar[slot], s * BKE, col0 + mrow * BROWS, 0, (uint16_t)mask_b);
-            if (X3) tma_load_3d_mc(st + L::B_LO + mrow * (BROWS * ROWB), &tmap_b_lo, &full_bar[slot], s * BKE, col0 + mrow * BROWS, 0, (uint16_t)mask_b);
-          } else {
-            tma_load_3d(st + L::B_HI, &tmap_b, &full_bar[slot], s * BKE, col0, 0);
-            if (X3) tma_load_3d(st + L::B_LO, &tmap_b_lo, &full_bar[slot], s * BKE, col0, 0);
-          }
+    // ---- TMA producer: operand stages.  Whole warp, one lane elected inside each asm; coordinates and addresses of a stage are
+    // computed before the wait for its slot (gemm_tc.cu: what sits between "slot free" and "loads issued" is refill latency)
+    const uint32_t tiles_addr = smem_u32(tiles), full_addr = smem_u32(full_bar);
+    int n = 0;
+    for (int rd = cluster_id; rd * MG < tiles_total; rd += n_clusters) {
+      const int r0 = (rd * MG + mrow) * BM;        // a row tile past the end is all zero fill (its mates still need this CTA's share)
+      // L2 prefetch of the next row tile's A planes (FS2_GEMM_PREFETCH=1; measured slower, off by default -- gemm_tc.cu)
+      const int r0n = ((rd + n_clusters) * MG + mrow) * BM;
+      const bool pf = p.prefetch && nh == 0 && r0n < p.M;
+      for (int s = 0; s < steps; ++s, ++n) {
+        if (pf && lane == 0) { tma_prefetch_3d(&tmap_a, s * BKE, r0n, 0); if (X3) tma_prefetch_3d(&tmap_a, s * BKE, r0n, 1); }
+        const int slot = n % L::STAGES;
+        const uint32_t st = tiles_addr + (uint32_t)slot * L::STAGE_BYTES, fb = full_addr + (uint32_t)slot * 8u;
+        const int k0 = s * BKE;
+        pin_before(st, fb, k0, r0);
+        mbar_wait(&empty_bar[slot], ((n / L::STAGES) & 1) ^ 1);
+        mbar_expect_tx_elect(fb, L::STAGE_BYTES);   // everything that lands in this stage, whoever fetches it
+        if (p.a_mc) {                                // rows [64 nh, 64 nh + 64) of the A tile, for both column halves
+          tma_load_3d_mc_elect(st + nh * (64 * ROWB), &tmap_a64, fb, k0, r0 + nh * 64, 0, mask_a);
+          if (X3) tma_load_3d_mc_elect(st + L::A_LO + nh * (64 * ROWB), &tmap_a64, fb, k0, r0 + nh * 64, 1, mask_a);
+        } else {
+          tma_load_3d_elect(st, &tmap_a, fb, k0, r0, 0);
+          if (X3) tma_load_3d_elect(st + L::A_LO, &tmap_a, fb, k0, r0, 1);
+        }
+        if (MG > 1) {                                // weight rows [BROWS mrow, +BROWS) of this column half, for every row tile
+          tma_load_3d_mc_elect(st + L::B_HI + mrow * (BROWS * ROWB), &tmap_b, fb, k0, col0 + mrow * BROWS, 0, (uint16_t)mask_b);
+          if (X3) tma_load_3d_mc_elect(st + L::B_LO + mrow * (BROWS * ROWB), &tmap_b_lo, fb, k0, col0 + mrow * BROWS, 0, (uint16_t)mask_b);
+        } else {
+          tma_load_3d_elect(st + L::B_HI, &tmap_b, fb, k0, col0, 0);
+          if (X3) tma_load_3d_elect(st + L::B_LO, &tmap_b_lo, fb, k0, col0, 0);
         }
       }
     }

@@ -164,49 +164,55 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   };
 
   if (warp == 0) {
-    if (lane == 0) {  // ---- TMA producer ----
-      int n = 0;      // ring position, runs across tiles
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int n0, b, t0, packed;
-        tile_coords(tile, n0, b, t0, packed);
-        // Experiment (FS2_GEMM_PREFETCH=1, off by default): L2 prefetch of the NEXT tile's activation rows, one K chunk per
-        // pipeline step, by the one CTA whose next tile is the first column tile of its row tile.  Hypothesis: first-touch
-        // activations arrive with DRAM latency that the 3 - 8 stage ring cannot cover (ncu of the K = 384 q|k|v projection: TMA,
-        // MMA and epilogue warps each wait ~30 %, nothing saturated).  Measured on c2 / 3xF16: q|k|v 0.485 -> 0.51 ms, w_2
-        // (cluster kernel, same idea) 0.53 -> 0.64 ms: the extra TMA traffic costs more than the latency it hides.
-        const int nxt = tile + (int)gridDim.x;
-        int pn0 = 0, pb = 0, pt0 = 0, ppacked = 0;
-        bool pf = p.prefetch && nxt < total_tiles && (nxt % p.n_tiles) == 0;
-        if (pf) { tile_coords(nxt, pn0, pb, pt0, ppacked); pf = ppacked < 0; }
-        for (int s = 0; s < steps; ++s, ++n) {
-          if (pf && s < 2 * kchunks && (s < kchunks || p.taps > 1)) {
-            // rows [t0 - pad, +128) in the first pass; a k > 1 convolution also reads up to row t0 + 127 + pad: second pass
-            const int pass = s < kchunks ? 0 : 1, kc = s - pass * kchunks;
-            const int r = pt0 + (pass ? p.pad : -p.pad);
-            tma_prefetch_3d(&tmap_a, kc * C::BKE, r, pb);
-            if (C::SPLIT16) tma_prefetch_3d(&tmap_a, kc * C::BKE, r, pb + p.B);
-          }
-          const int slot = n % C::STAGES, round = n / C::STAGES;
-          mbar_wait(&empty_bar[slot], (round & 1) ^ 1);
-          const int j = s / kchunks, k0 = (s - j * kchunks) * C::BKE;
-          uint8_t* st = tiles + (size_t)slot * C::STAGE_BYTES;
-          mbar_expect_tx(&full_bar[slot], C::TX_BYTES);
-          if (packed < 0) {
-            tma_load_3d(st, &tmap_a, &full_bar[slot], k0, t0 + j - p.pad, b);
-            if (C::SPLIT16) tma_load_3d(st + C::A_LO, &tmap_a, &full_bar[slot], k0, t0 + j - p.pad, b + p.B);
-          } else {
-            // eight 16-row boxes: granule g belongs to utterance b + g / gn (zero-filled past the batch or past L)
-            for (int g = 0; g < 8; ++g) {
-              const int u = g / p.gn, gi = g - u * p.gn;
-              const bool real = u < p.upt && b + u < p.B;
-              const int oob = C::SPLIT16 ? 2 * p.B : p.B;  // out of bounds in dim 2 -> the box is all zeros
-              tma_load_3d(st + g * (16 * 128), &tmap_a16, &full_bar[slot], k0, t0 + gi * 16 + j - p.pad, real ? b + u : oob);
-              if (C::SPLIT16) tma_load_3d(st + C::A_LO + g * (16 * 128), &tmap_a16, &full_bar[slot], k0, t0 + gi * 16 + j - p.pad, real ? b + u + p.B : oob);
-            }
-          }
-          tma_load_3d(st + C::B_HI, &tmap_b, &full_bar[slot], k0, n0, j);
-          if (PRECISE) tma_load_3d(st + C::B_LO, &tmap_b_lo, &full_bar[slot], k0, n0, j);
+    // ---- TMA producer: the whole warp runs the loop, one lane is elected inside each asm.  Everything a stage's loads need
+    // (coordinates, shared-memory and barrier addresses) is computed BEFORE the wait for its slot, and the tap / K-chunk indices
+    // are carried as counters: what used to sit between "slot free" and "loads issued" (an integer division, address arithmetic,
+    // an ELECT / vote loop per UTMALDG: ~100 of the loop's 140 instructions) is part of the refill latency of a 3-stage ring.
+    const uint32_t tiles_addr = smem_u32(tiles), full_addr = smem_u32(full_bar);
+    int n = 0;      // ring position, runs across tiles
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int n0, b, t0, packed;
+      tile_coords(tile, n0, b, t0, packed);
+      // Experiment (FS2_GEMM_PREFETCH=1, off by default): L2 prefetch of the NEXT tile's activation rows, one K chunk per
+      // pipeline step, by the one CTA whose next tile is the first column tile of its row tile.  Hypothesis: first-touch
+      // activations arrive with DRAM latency that the 3 - 8 stage ring cannot cover (ncu of the K = 384 q|k|v projection: TMA,
+      // MMA and epilogue warps each wait ~30 %, nothing saturated).  Measured on c2 / 3xF16: q|k|v 0.485 -> 0.51 ms, w_2
+      // (cluster kernel, same idea) 0.53 -> 0.64 ms: the extra TMA traffic costs more than the latency it hides.
+      const int nxt = tile + (int)gridDim.x;
+      int pn0 = 0, pb = 0, pt0 = 0, ppacked = 0;
+      bool pf = p.prefetch && nxt < total_tiles && (nxt % p.n_tiles) == 0;
+      if (pf) { tile_coords(nxt, pn0, pb, pt0, ppacked); pf = ppacked < 0; }
+      int j = 0, kc = 0;                        // tap, K chunk of step s
+      for (int s = 0; s < steps; ++s, ++n) {
+        if (pf && s < 2 * kchunks && (s < kchunks || p.taps > 1) && lane == 0) {
+          // rows [t0 - pad, +128) in the first pass; a k > 1 convolution also reads up to row t0 + 127 + pad: second pass
+          const int pass = s < kchunks ? 0 : 1, pkc = s - pass * kchunks;
+          const int r = pt0 + (pass ? p.pad : -p.pad);
+          tma_prefetch_3d(&tmap_a, pkc * C::BKE, r, pb);
+          if (C::SPLIT16) tma_prefetch_3d(&tmap_a, pkc * C::BKE, r, pb + p.B);
         }
+        const int slot = n % C::STAGES, round = n / C::STAGES;
+        const int k0 = kc * C::BKE, row = t0 + j - p.pad;
+        const uint32_t st = tiles_addr + (uint32_t)slot * C::STAGE_BYTES, fb = full_addr + (uint32_t)slot * 8u;
+        pin_before(st, fb, k0, row);
+        mbar_wait(&empty_bar[slot], (round & 1) ^ 1);
+        mbar_expect_tx_elect(fb, C::TX_BYTES);
+        if (packed < 0) {
+          tma_load_3d_elect(st, &tmap_a, fb, k0, row, b);
+          if (C::SPLIT16) tma_load_3d_elect(st + C::A_LO, &tmap_a, fb, k0, row, b + p.B);
+        } else {
+          // eight 16-row boxes: granule g belongs to utterance b + g / gn (zero-filled past the batch or past L)
+          for (int g = 0; g < 8; ++g) {
+            const int u = g / p.gn, gi = g - u * p.gn;
+            const bool real = u < p.upt && b + u < p.B;
+            const int oob = C::SPLIT16 ? 2 * p.B : p.B;  // out of bounds in dim 2 -> the box is all zeros
+            tma_load_3d_elect(st + g * (16 * 128), &tmap_a16, fb, k0, row + gi * 16, real ? b + u : oob);
+            if (C::SPLIT16) tma_load_3d_elect(st + C::A_LO + g * (16 * 128), &tmap_a16, fb, k0, row + gi * 16, real ? b + u + p.B : oob);
+          }
+        }
+        tma_load_3d_elect(st + C::B_HI, &tmap_b, fb, k0, n0, j);
+        if (PRECISE) tma_load_3d_elect(st + C::B_LO, &tmap_b_lo, fb, k0, n0, j);
+        if (++kc == kchunks) { kc = 0; ++j; }
       }
     }
   } else if (warp == 1) {

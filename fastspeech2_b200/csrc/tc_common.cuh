@@ -59,6 +59,26 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// Warp-convergent producer forms: the whole warp runs the producer loop, one lane is elected inside each asm (same reason as the
+// MMA warp below: issuing TMA from an `if (lane == 0)` region makes ptxas wrap every UTMALDG in an ELECT / vote loop and keep its
+// operands in vector registers).  Addresses are passed as shared-space integers so they can be computed before the slot wait.
+__device__ __forceinline__ void mbar_expect_tx_elect(uint32_t bar_addr, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
+      ::"r"(bar_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_elect(uint32_t dst_addr, const CUtensorMap* map, uint32_t bar_addr, int c0, int c1, int c2) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}"
+      ::"r"(dst_addr), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// values computed before a wait stay computed before it (volatile asms are not reordered against each other)
+__device__ __forceinline__ void pin_before(uint32_t a, uint32_t b, int c, int d) { asm volatile("" ::"r"(a), "r"(b), "r"(c), "r"(d)); }
 // L2 prefetch of one box (no shared-memory destination, no barrier): issued a tile ahead so that first-touch operand tiles do not
 // arrive with DRAM latency (a 3-stage ring holds 192 KB in flight per SM, far less than latency x bandwidth needs)
 __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
