@@ -178,24 +178,30 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {  // ---- TMA producer: per work item Q once, then K / V^T boxes in exactly the order the MMA warp consumes them ----
+    {  // ---- TMA producer: per work item Q once, then K / V^T boxes in exactly the order the MMA warp consumes them.  The whole
+       // warp runs the loop, one lane is elected inside each asm, and a box's coordinates and addresses are computed before
+       // the wait for its slot (gemm_tc.cu: what sits between "slot free" and "load issued" is refill latency) ----
+      const uint32_t ring_addr = smem_u32(ring), full_addr = smem_u32(full_bar), q_addr0 = smem_u32(q_smem), qbar_addr = smem_u32(q_bar);
       int n = 0, wc = 0;    // ring position and count of non-empty work items, both run across items
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         int b, h, q0, len, J;
         decode(w, b, h, q0, len, J);
         if (J == 0) continue;
         if (wc > 0) mbar_wait(q_free, (wc - 1) & 1);      // the previous item's S products are done with Q
-        mbar_expect_tx(q_bar, A::Q_BYTES);
+        mbar_expect_tx_elect(qbar_addr, A::Q_BYTES);
         for (int pl = 0; pl < A::P; ++pl)
           for (int c = 0; c < A::QCH; ++c)
-            tma_load_3d(q_smem + (size_t)(pl * A::QCH + c) * A::Q_BOX, &tmap_qk, q_bar, h * DK + c * CH, q0, b + pl * p.B);
+            tma_load_3d_elect(q_addr0 + (uint32_t)((pl * A::QCH + c) * A::Q_BOX), &tmap_qk, qbar_addr, h * DK + c * CH, q0, b + pl * p.B);
         auto push_k = [&](int j) {
           for (int c = 0; c < A::QCH; ++c)
             for (int pl = 0; pl < A::P; ++pl, ++n) {
               const int slot = n % A::SLOTS;
+              const uint32_t dst = ring_addr + (uint32_t)slot * A::SLOT, fb = full_addr + (uint32_t)slot * 8u;
+              const int c0 = p.C + h * DK + c * CH, c2 = b + pl * p.B;
+              pin_before(dst, fb, c0, c2);
               mbar_wait(&empty_bar[slot], ((n / A::SLOTS) & 1) ^ 1);
-              mbar_expect_tx(&full_bar[slot], A::K_BOX);
-              tma_load_3d(ring + (size_t)slot * A::SLOT, &tmap_qk, &full_bar[slot], p.C + h * DK + c * CH, j * BKV, b + pl * p.B);
+              mbar_expect_tx_elect(fb, A::K_BOX);
+              tma_load_3d_elect(dst, &tmap_qk, fb, c0, j * BKV, c2);
             }
         };
         auto push_v = [&](int j) {
@@ -203,9 +209,12 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
           for (int c = 0; c < vch; ++c)
             for (int pl = 0; pl < A::P; ++pl, ++n) {
               const int slot = n % A::SLOTS;
+              const uint32_t dst = ring_addr + (uint32_t)slot * A::SLOT, fb = full_addr + (uint32_t)slot * 8u;
+              const int c0 = j * BKV + c * CH, c2 = b * p.heads + h + pl * p.B * p.heads;
+              pin_before(dst, fb, c0, c2);
               mbar_wait(&empty_bar[slot], ((n / A::SLOTS) & 1) ^ 1);
-              mbar_expect_tx(&full_bar[slot], A::V_BOX);
-              tma_load_3d(ring + (size_t)slot * A::SLOT, &tmap_vt, &full_bar[slot], j * BKV + c * CH, 0, b * p.heads + h + pl * p.B * p.heads);
+              mbar_expect_tx_elect(fb, A::V_BOX);
+              tma_load_3d_elect(dst, &tmap_vt, fb, c0, 0, c2);
             }
         };
         push_k(0);

@@ -253,14 +253,15 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       const uint32_t d = tmem_base + (uint32_t)(acc * L::H);
       for (int s = 0; s < steps; ++s, ++n) {
         const int slot = n % L::STAGES;
+        const uint32_t base = smem_u32(tiles + (size_t)slot * L::STAGE_BYTES);   // descriptors before the wait (gemm_tc.cu)
+        const uint64_t a_hi = mkdesc(base), b_hi = mkdesc(base + L::B_HI);
+        const uint64_t a_lo = mkdesc(base + L::A_LO), b_lo = mkdesc(base + L::B_LO);
+        pin_before64(a_hi, b_hi, a_lo, b_lo);
         mbar_wait(&full_bar[slot], (n / L::STAGES) & 1);
         tcgen05_fence_after();
-        const uint32_t base = smem_u32(tiles + (size_t)slot * L::STAGE_BYTES);
-        const uint64_t a_hi = mkdesc(base), b_hi = mkdesc(base + L::B_HI);
 #pragma unroll
         for (int k = 0; k < BKE / 16; ++k) {
           if (X3) {
-            const uint64_t a_lo = mkdesc(base + L::A_LO), b_lo = mkdesc(base + L::B_LO);
             umma_f16(d, a_lo + 2 * k, b_hi + 2 * k, L::IDESC, (s | k) != 0);   // small terms first
             umma_f16(d, a_hi + 2 * k, b_lo + 2 * k, L::IDESC, 1);
             umma_f16(d, a_hi + 2 * k, b_hi + 2 * k, L::IDESC, 1);
@@ -274,18 +275,21 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       tcgen05_commit(&acc_full[acc]);
     }
   } else if (warp == 10) {
-    if (lane == 0 && p.has_resid) {  // ---- TMA producer: residual ring (chunk c of a tile = columns col0 + 32 c .. + 31) ----
+    if (p.has_resid) {  // ---- TMA producer: residual ring (chunk c of a tile = columns col0 + 32 c .. + 31); whole warp, elected issue ----
+      const uint32_t rbuf_addr = smem_u32(rbuf), rfull_addr = smem_u32(r_full);
       int q = 0;
       for (int rd = cluster_id; rd * MG < tiles_total; rd += n_clusters) {
         const int r0 = (rd * MG + mrow) * BM;
         const int r0n = ((rd + n_clusters) * MG + mrow) * BM;
-        const bool pf = p.prefetch && r0n < p.M;     // the residual rows are first-touch DRAM reads too
+        const bool pf = p.prefetch && r0n < p.M;     // FS2_GEMM_PREFETCH experiment (off)
         for (int c = 0; c < L::NCH; ++c, ++q) {
-          if (pf) tma_prefetch_3d(&tmap_r, col0 + c * 32, r0n, 0);
+          if (pf && lane == 0) tma_prefetch_3d(&tmap_r, col0 + c * 32, r0n, 0);
           const int slot = q % L::RB;
+          const uint32_t dst = rbuf_addr + (uint32_t)slot * CHUNK_BYTES, fb = rfull_addr + (uint32_t)slot * 8u;
+          pin_before(dst, fb, col0 + c * 32, r0);
           mbar_wait(&r_empty[slot], ((q / L::RB) & 1) ^ 1);
-          mbar_expect_tx(&r_full[slot], CHUNK_BYTES);
-          tma_load_3d(rbuf + (size_t)slot * CHUNK_BYTES, &tmap_r, &r_full[slot], col0 + c * 32, r0, 0);
+          mbar_expect_tx_elect(fb, CHUNK_BYTES);
+          tma_load_3d_elect(dst, &tmap_r, fb, col0 + c * 32, r0, 0);
         }
       }
     }

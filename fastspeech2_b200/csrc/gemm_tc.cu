@@ -225,18 +225,21 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         const uint32_t d = tmem_base + (uint32_t)(acc * C::ACC_STRIDE);
         for (int s = 0; s < steps; ++s, ++n) {
           const int slot = n % C::STAGES, round = n / C::STAGES;
-          mbar_wait(&full_bar[slot], round & 1);
-          tcgen05_fence_after();
+          // descriptors of the stage before the wait for its data (they are part of the data-landed -> first-MMA latency otherwise)
           const uint32_t base = smem_u32(tiles + (size_t)slot * C::STAGE_BYTES);
           const uint64_t a_hi = make_sw128_kmajor_desc(base), b_hi = make_sw128_kmajor_desc(base + C::B_HI);
+          const uint64_t a_lo_w = make_sw128_kmajor_desc(base + C::A_LO), b_lo_w = make_sw128_kmajor_desc(base + C::B_LO);
+          pin_before64(a_hi, b_hi, a_lo_w, b_lo_w);
+          mbar_wait(&full_bar[slot], round & 1);
+          tcgen05_fence_after();
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {  // +32 bytes along K inside the swizzle row = +2 in descriptor units
             if (C::WIDE) {
-              const uint64_t a_lo = make_sw128_kmajor_desc(base + C::A_LO);
+              const uint64_t a_lo = a_lo_w;
               umma_f16(d, a_hi + 2 * k, b_hi + 2 * k, C::IDESC_WIDE, (s | k) != 0);   // [0,BN) += a_hi b_hi, [BN,2BN) += a_hi b_lo
               umma_f16(d + BN, a_lo + 2 * k, b_hi + 2 * k, C::IDESC, 1);              // [BN,2BN) += a_lo b_hi
             } else if (PRECISE) {
-              const uint64_t a_lo = make_sw128_kmajor_desc(base + C::A_LO), b_lo = make_sw128_kmajor_desc(base + C::B_LO);
+              const uint64_t a_lo = a_lo_w, b_lo = b_lo_w;
               umma_f16(d, a_lo + 2 * k, b_hi + 2 * k, C::IDESC, (s | k) != 0);  // small terms first
               umma_f16(d, a_hi + 2 * k, b_lo + 2 * k, C::IDESC, 1);
               umma_f16(d, a_hi + 2 * k, b_hi + 2 * k, C::IDESC, 1);

@@ -79,6 +79,7 @@ __device__ __forceinline__ void tma_load_3d_elect(uint32_t dst_addr, const CUten
 }
 // values computed before a wait stay computed before it (volatile asms are not reordered against each other)
 __device__ __forceinline__ void pin_before(uint32_t a, uint32_t b, int c, int d) { asm volatile("" ::"r"(a), "r"(b), "r"(c), "r"(d)); }
+__device__ __forceinline__ void pin_before64(uint64_t a, uint64_t b, uint64_t c, uint64_t d) { asm volatile("" ::"l"(a), "l"(b), "l"(c), "l"(d)); }
 // L2 prefetch of one box (no shared-memory destination, no barrier): issued a tile ahead so that first-touch operand tiles do not
 // arrive with DRAM latency (a 3-stage ring holds 192 KB in flight per SM, far less than latency x bandwidth needs)
 __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
