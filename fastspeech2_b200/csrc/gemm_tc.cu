@@ -84,7 +84,7 @@ struct TcParams {
   // optional: columns >= vt_col0 are the V third of a q|k|v projection and are stored transposed,
   // vt[(b*heads + h)*dk + d][t] with row pitch vt_lpad, for the attention kernel's K-major P.V operand
   float* vt_out; __half* vtp; __half* vtp_lo; int vt_col0, vt_dk, vt_heads, vt_lpad, vt_L;
-  int debug;   // FS2_GEMM_DEBUG: bit0 skip tcgen05.ld, bit1 skip stores (profiling experiments only)
+  int debug;   // FS2_GEMM_DEBUG: bit0 skip tcgen05.ld, bit1 skip stores, bit2 V third untransposed (profiling experiments only)
   int prefetch;  // FS2_GEMM_PREFETCH (default 0: measured slower, see the producer loop): L2 prefetch of the next tile's activation rows
 };
 
@@ -320,7 +320,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           v[q * 4] = fmaf(v[q * 4], oscale, b4.x); v[q * 4 + 1] = fmaf(v[q * 4 + 1], oscale, b4.y);
           v[q * 4 + 2] = fmaf(v[q * 4 + 2], oscale, b4.z); v[q * 4 + 3] = fmaf(v[q * 4 + 3], oscale, b4.w);
         }
-        if (to_vt) {
+        if (to_vt && !(p.debug & 4)) {
           // transposed store: for a fixed column the 32 lanes hold 32 consecutive time steps -> contiguous 128-byte
           // (fp32) / 64-byte (fp16 plane) runs
           const long ub = m / p.vt_L; const int ut = (int)(m - ub * p.vt_L);
@@ -364,12 +364,16 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 #pragma unroll
             for (int i = 0; i < 16; ++i) h[i] = hi_pair(v[2 * i], v[2 * i + 1]);
           }
-          const long off = m * p.ldo_p + n0 + c0;
-          if (full || c0 + 16 <= BN) st_global_v8_b32(p.outp + off, h);
-          if (full) st_global_v8_b32(p.outp + off + 16, h + 8);
-          if (p.outp_lo != nullptr) {
-            if (full || c0 + 16 <= BN) st_global_v8_b32(p.outp_lo + off, l);
-            if (full) st_global_v8_b32(p.outp_lo + off + 16, l + 8);
+          long off = m * p.ldo_p + n0 + c0;
+          __half* ob = p.outp; __half* ob_lo = p.outp_lo;
+          if (to_vt) {   // FS2_GEMM_DEBUG bit 2 (timing experiment only): the V third stored UNtransposed into the V^T buffer (wrong layout)
+            ob = p.vtp; ob_lo = p.vtp_lo; off = m * (long)(p.vt_dk * p.vt_heads) + n0 - p.vt_col0 + c0;
+          }
+          if (full || c0 + 16 <= BN) st_global_v8_b32(ob + off, h);
+          if (full) st_global_v8_b32(ob + off + 16, h + 8);
+          if (ob_lo != nullptr) {
+            if (full || c0 + 16 <= BN) st_global_v8_b32(ob_lo + off, l);
+            if (full) st_global_v8_b32(ob_lo + off + 16, l + 8);
           }
         }
         if (out != nullptr) {
