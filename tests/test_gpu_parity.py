@@ -397,11 +397,12 @@ def test_attention_partial_last_key_tile(prec, C):
 
 
 @pytest.mark.parametrize("prec,N", [("tf32", 384), ("f16", 384), ("3xtf32", 384), ("f16", 256), ("3xtf32", 256)])
-@pytest.mark.parametrize("rows,K,with_resid", [(1000, 384, True), (51, 1024, True), (4097, 256, False), (40000, 384, True)])
+@pytest.mark.parametrize("rows,K,with_resid", [(1000, 384, True), (51, 1024, True), (4097, 256, False), (40000, 384, True), (20000, 1024, True)])
 def test_fused_gemm_layernorm_vs_torch(prec, N, rows, K, with_resid):
     """tcgen05 GEMM with residual + LayerNorm fused into the epilogue (out-projection / conv-FFN w_2): the kind::tf32 single-CTA
     kernel and the 2-CTA-cluster plane kernels (kind::f16, 3xF16; rows split between the CTAs, statistics merged through
-    distributed shared memory).  40000 rows = more tiles than cluster slots: every pipeline ring wraps several times."""
+    distributed shared memory).  40000 rows = more tiles than cluster slots: every pipeline ring wraps several times; K = 1024
+    with 20000 rows does the same for the half-depth-K stages (64-byte swizzle) the 3xF16 C = 384 kernel uses for long K."""
     g = torch.Generator().manual_seed(rows + K + N)
     x = torch.randn(rows, K, generator=g); w = torch.randn(N, K, generator=g) / K ** 0.5; bias = torch.randn(N, generator=g)
     resid = torch.randn(rows, N, generator=g) + 2.0          # non-zero row mean: exercises the merge of the partial statistics
