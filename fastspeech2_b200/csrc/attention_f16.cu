@@ -164,6 +164,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
   // product of a partial tile uses N = n16, its P.V only the first n16 / 16 K-steps and ceil(n16 / 64) V^T boxes.
   auto keys16 = [&](int j, int len) { const int r = len - j * BKV; return r >= BKV ? BKV : (r + 15) & ~15; };
 
+  pdl_trigger();
   if (threadIdx.x == 0) {
     for (int s = 0; s < A::SLOTS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(q_bar, 1);
@@ -172,6 +173,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, A::TMEM_COLS);
+  pdl_wait();                                  // no global memory is touched above: it overlaps the previous kernel's tail
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -1136,7 +1138,7 @@ int launch(const __half* qkp, const __half* vtp, int lpad, const int64_t* lens, 
   p.trace = att_trace_buffer();
   const long work = (long)B * heads * ((L + BQ - 1) / BQ);
   const int grid = (int)(work < sm_count_current() ? work : sm_count_current());     // persistent: one CTA per SM
-  attention_f16_kernel<DK, X3><<<grid, ATT_THREADS, A::SMEM, st>>>(mqk, mvt, p);
+  FS2_CUDA_CHECK(launch_pdl(attention_f16_kernel<DK, X3>, dim3(grid), dim3(ATT_THREADS), A::SMEM, st, mqk, mvt, p));
   FS2_LAUNCH_CHECK();
   if (p.trace) att_trace_dump(p.trace, (L + BKV - 1) / BKV, st);
   return FS2_OK;

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -151,6 +152,34 @@ int pack_conv_weight(const float* src, int N, int K, int taps, const float* scal
 int pack_transpose(const float* src, int rows, int cols, float* dst, cudaStream_t st);  // [rows][cols] -> [cols][rows]
 int fold_batchnorm(const float* gamma, const float* beta, const float* mean, const float* var, float eps, int N,
                    float* scale, float* shift, cudaStream_t st);
+
+// ---- programmatic dependent launch (experiment, FS2_PDL=1; off by default) ---------------------
+// Every kernel of the step calls pdl_trigger() first (the next kernel of the stream may be scheduled as soon as this grid's
+// CTAs are all resident) and pdl_wait() before its first global-memory access (= the previous grid has completed and its
+// writes are visible), so that mbarrier init, TMEM allocation, tensor-map fetch and the launch latency itself overlap the tail
+// of the previous kernel.  Correct (tools/pdl_check.py: 30 graph replays per mode bit-identical to the eager step; the whole
+// GPU suite passes with it) but measured SLOWER inside the CUDA graph: 6.41 / 6.46 ms per c2 step against 6.30 / 6.22 without
+// (same box, alternating runs, gpurun_out/bench_g2_pdl*.json) -- early-resident CTAs of the next kernel compete with the
+// running one for the SM they spin on.  Without the launch attribute the device-side calls are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FS2_PDL"); v = e ? atoi(e) : 0; }
+  return v != 0;
+}
+// kernel<<<grid, block, smem, st>>>(args...) with the programmatic-stream-serialization attribute; ONLY for kernels that call
+// pdl_wait() before touching global memory
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ---- small device helpers -----------------------------------------------------------------
 // two floats -> packed fp16 pair (a in the low half), round-to-nearest, saturating at +-65504 (F2FP.SATFINITE: one instruction

@@ -189,6 +189,7 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   const uint16_t mask_e = (uint16_t)((p.a_mc ? mask_a : (1u << rank)) | mask_b);
   const int n_readers = (p.a_mc ? 1 : 0) + MG;
 
+  pdl_trigger();
   if (threadIdx.x == 0) {
     for (int s = 0; s < L::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], n_readers); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
@@ -197,6 +198,7 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 9) tmem_alloc(tmem_slot, L::TMEM_COLS);
+  pdl_wait();                                  // barrier init and TMEM allocation overlapped the previous kernel's tail
   for (int i = threadIdx.x; i < L::H; i += blockDim.x) {
     vec[i] = p.bias ? __ldg(p.bias + col0 + i) : 0.f;
     vec[L::H + i] = __ldg(p.gamma + col0 + i);
@@ -451,10 +453,12 @@ int launch_cl(const TapGemm& g, bool a_mc, cudaStream_t st) {
   cfg.blockDim = dim3(CL_THREADS, 1, 1);
   cfg.dynamicSmemBytes = L::SMEM;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
   FS2_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_ln_cluster_kernel<C, X3, MG, KH>, ma, ma64, mb, mb_lo, mr, p));
   FS2_LAUNCH_CHECK();
   return FS2_OK;

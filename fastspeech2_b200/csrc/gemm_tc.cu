@@ -136,6 +136,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   const int steps = p.taps * kchunks;
   const int total_tiles = p.m_tiles * p.n_tiles;
 
+  pdl_trigger();
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int i = 0; i < C::NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4 * C::GROUPS); }
@@ -146,6 +147,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                              // everything above overlapped the previous kernel's tail
   float* bias_s = reinterpret_cast<float*>(staging);      // whole bias vector, read back as broadcast LDS in the epilogue
   {
     const int N = p.n_tiles * BN;
@@ -406,6 +408,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 // x [rows][ldx] fp32 -> S[0] = hi plane, S[1] = lo plane, each [rows][K] fp16, scaled by kPlaneScale.
 // One float4 per thread and step, 8-byte stores.
 __global__ void split_rows_f16_kernel(const float* __restrict__ x, int ldx, long rows, int K, __half* __restrict__ S) {
+  pdl_trigger(); pdl_wait();
   const int kq = K >> 2;
   const long quads = rows * kq;
   __half* __restrict__ lo_plane = S + rows * K;
@@ -471,7 +474,7 @@ int launch(const TapGemm& g, cudaStream_t st) {
   if ((rc = make_map(&mb_lo, PRECISE ? (const void*)g.w_lo : w_hi, g.K, g.N, g.taps, (uint64_t)g.K * esz, (uint64_t)g.K * esz * g.N, BN, HALF))) return rc;
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < sm_count_current() ? total : sm_count_current();
-  tap_gemm_tf32_kernel<BN, PRECISE, HALF><<<grid, C::THREADS, C::SMEM, st>>>(ma, mb, mb_lo, ma16, p);
+  FS2_CUDA_CHECK(launch_pdl(tap_gemm_tf32_kernel<BN, PRECISE, HALF>, dim3(grid), dim3(C::THREADS), C::SMEM, st, ma, mb, mb_lo, ma16, p));
   FS2_LAUNCH_CHECK();
   return FS2_OK;
 }
@@ -551,7 +554,7 @@ int split_rows(const float* x, int ldx, long rows, int K, __half* planes, cudaSt
   FS2_REQUIRE(K % 4 == 0 && ldx % 4 == 0, "split_rows: K and the row stride must be multiples of 4");
   const long quads = rows * (K / 4);
   long blocks = (quads + 255) / 256;
-  split_rows_f16_kernel<<<(int)(blocks > 148 * 16 ? 148 * 16 : blocks), 256, 0, st>>>(x, ldx, rows, K, planes);
+  FS2_CUDA_CHECK(launch_pdl(split_rows_f16_kernel, dim3((unsigned)(blocks > 148 * 16 ? 148 * 16 : blocks)), dim3(256), 0, st, x, ldx, rows, K, planes));
   FS2_LAUNCH_CHECK();
   return FS2_OK;
 }

@@ -102,6 +102,7 @@ template <int VEC_PER_ROW_MAX>
 __global__ void __launch_bounds__(256)
 length_gather_kernel(const float* __restrict__ hs, const int32_t* __restrict__ cum, const int64_t* __restrict__ ilens,
                      int T, int C, float* __restrict__ out, int Lcap) {
+  pdl_trigger(); pdl_wait();
   extern __shared__ int32_t scum[];  // [T]
   __shared__ int src_row[FRAMES_PER_CTA];
   const int b = blockIdx.y;
@@ -162,13 +163,17 @@ int length_gather(const float* hs, const int32_t* cum, const int64_t* ilens, int
   if (B == 0 || Lcap == 0) return FS2_OK;
   size_t smem = (size_t)T * sizeof(int32_t);
   FS2_REQUIRE(smem <= 200 * 1024, "length_gather: Tmax=%d too large for the shared cum row", T);
-  static bool attr_set = false;
-  if (smem > 48 * 1024 && !attr_set) {
-    FS2_CUDA_CHECK(cudaFuncSetAttribute(length_gather_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+  static unsigned long long attr_set = 0;   // per-device bit mask: the attribute is a per-device setting
+  if (smem > 48 * 1024) {
+    int dev = 0;
+    FS2_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev >= 64 || !((attr_set >> dev) & 1ull)) {
+      FS2_CUDA_CHECK(cudaFuncSetAttribute(length_gather_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      if (dev < 64) attr_set |= 1ull << dev;
+    }
   }
   dim3 grid((Lcap + FRAMES_PER_CTA - 1) / FRAMES_PER_CTA, B);
-  length_gather_kernel<0><<<grid, 256, smem, st>>>(hs, cum, ilens, T, C, out, Lcap);
+  FS2_CUDA_CHECK(launch_pdl(length_gather_kernel<0>, grid, dim3(256), smem, st, hs, cum, ilens, T, C, out, Lcap));
   FS2_LAUNCH_CHECK();
   return FS2_OK;
 }

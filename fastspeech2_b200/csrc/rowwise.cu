@@ -14,6 +14,7 @@ template <int NV>  // float4 per lane
 __global__ void embed_posenc_kernel(const int64_t* __restrict__ xs, const float* __restrict__ table, int n_sym,
                                     const float* __restrict__ pe, const float* __restrict__ alpha, long rows, int T,
                                     float* __restrict__ out, __half* __restrict__ planes) {
+  pdl_trigger(); pdl_wait();
   const int C = NV * 128;
   long row = (long)blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -45,6 +46,7 @@ __global__ void embed_posenc_kernel(const int64_t* __restrict__ xs, const float*
 // duration_predictor.py:75-84, variance_predictor.py:50-51,75-78.
 template <int NV>
 __global__ void row_norm_kernel(RowNorm r) {
+  pdl_trigger(); pdl_wait();
   long row = (long)blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5);
   if (row >= r.rows) return;
   const int C = NV * 128;
@@ -145,6 +147,7 @@ __global__ void variance_embed_add_kernel(const float* __restrict__ hm, const fl
                                           const float* __restrict__ p_bias, int64_t rows, float* __restrict__ out,
                                           __half* __restrict__ planes, int planes_lo,
                                           int64_t* __restrict__ e_ids, int64_t* __restrict__ p_ids) {
+  pdl_trigger(); pdl_wait();
   const int C = NV * 128;
   int64_t row = (int64_t)blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -281,8 +284,8 @@ int embed_posenc(const int64_t* xs, const float* table, int n_sym, const float* 
   long rows = (long)B * T;
   if (rows == 0) return FS2_OK;
   int grid = (int)((rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
-  if (C == 256) embed_posenc_kernel<2><<<grid, 256, 0, st>>>(xs, table, n_sym, pe, alpha, rows, T, out, planes);
-  else if (C == 384) embed_posenc_kernel<3><<<grid, 256, 0, st>>>(xs, table, n_sym, pe, alpha, rows, T, out, planes);
+  if (C == 256) { FS2_CUDA_CHECK(launch_pdl(embed_posenc_kernel<2>, dim3(grid), dim3(256), 0, st, xs, table, n_sym, pe, alpha, rows, T, out, planes)); }
+  else if (C == 384) { FS2_CUDA_CHECK(launch_pdl(embed_posenc_kernel<3>, dim3(grid), dim3(256), 0, st, xs, table, n_sym, pe, alpha, rows, T, out, planes)); }
   else { set_error("embed_posenc: C=%d unsupported (256 or 384)", C); return FS2_ERR_INVALID; }
   FS2_LAUNCH_CHECK();
   return FS2_OK;
@@ -293,8 +296,8 @@ int row_norm(const RowNorm& r, cudaStream_t st) {
   FS2_REQUIRE(r.ldx % 4 == 0 && (!r.out || r.ldo % 4 == 0) && (!r.resid || r.ldr % 4 == 0), "row_norm: strides must be 16-byte multiples");
   FS2_REQUIRE(!r.split_out || (reinterpret_cast<uintptr_t>(r.split_out) & 7) == 0, "row_norm: operand planes must be 8-byte aligned");
   int grid = (int)((r.rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
-  if (r.C == 256) row_norm_kernel<2><<<grid, 256, 0, st>>>(r);
-  else if (r.C == 384) row_norm_kernel<3><<<grid, 256, 0, st>>>(r);
+  if (r.C == 256) { FS2_CUDA_CHECK(launch_pdl(row_norm_kernel<2>, dim3(grid), dim3(256), 0, st, r)); }
+  else if (r.C == 384) { FS2_CUDA_CHECK(launch_pdl(row_norm_kernel<3>, dim3(grid), dim3(256), 0, st, r)); }
   else { set_error("row_norm: C=%d unsupported (256 or 384)", r.C); return FS2_ERR_INVALID; }
   FS2_LAUNCH_CHECK();
   return FS2_OK;
@@ -321,12 +324,13 @@ int variance_embed_add(const float* hm, const float* e_val, const float* p_val, 
                        cudaStream_t st) {
   if (rows == 0) return FS2_OK;
   int grid = (int)((rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
-  if (C == 256)
-    variance_embed_add_kernel<2><<<grid, 256, 0, st>>>(hm, e_val, p_val, e_bins, p_bins, n_edges, e_tab, e_bias, p_tab,
-                                                       p_bias, rows, out, planes, planes_lo, e_ids, p_ids);
-  else if (C == 384)
-    variance_embed_add_kernel<3><<<grid, 256, 0, st>>>(hm, e_val, p_val, e_bins, p_bins, n_edges, e_tab, e_bias, p_tab,
-                                                       p_bias, rows, out, planes, planes_lo, e_ids, p_ids);
+  if (C == 256) {
+    FS2_CUDA_CHECK(launch_pdl(variance_embed_add_kernel<2>, dim3(grid), dim3(256), 0, st, hm, e_val, p_val, e_bins, p_bins, n_edges, e_tab, e_bias, p_tab,
+                              p_bias, rows, out, planes, planes_lo, e_ids, p_ids));
+  } else if (C == 384) {
+    FS2_CUDA_CHECK(launch_pdl(variance_embed_add_kernel<3>, dim3(grid), dim3(256), 0, st, hm, e_val, p_val, e_bins, p_bins, n_edges, e_tab, e_bias, p_tab,
+                              p_bias, rows, out, planes, planes_lo, e_ids, p_ids));
+  }
   else { set_error("variance_embed_add: C=%d unsupported", C); return FS2_ERR_INVALID; }
   FS2_LAUNCH_CHECK();
   return FS2_OK;

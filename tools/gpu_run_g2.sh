@@ -1,0 +1,12 @@
+mkdir -p gpurun_out
+echo "FS2_PDL default (1)"
+timeout 600 python tools/pdl_check.py 2>&1 | tail -8
+timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+for pdl in 0 1 0 1; do
+  FS2_PDL=$pdl python bench.py --gpus 1 --steps 20 --warmup 5 --modes "f16" 2>/dev/null | grep '^{"metric"' > gpurun_out/bench_g2_pdl$pdl.json
+  python - <<PY
+import json
+d=json.loads(open("gpurun_out/bench_g2_pdl$pdl.json").read().strip().splitlines()[-1])
+print("PDL=$pdl", round(d["ms_per_step"],3), "e2e", round(d["e2e"]["ms_per_step"],3), "busy", round(d["gpu_busy_ms_per_step"],3), {k:round(v["ms_per_step"],3) for k,v in d.get("modes",{}).items()})
+PY
+done
