@@ -164,7 +164,6 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
   // product of a partial tile uses N = n16, its P.V only the first n16 / 16 K-steps and ceil(n16 / 64) V^T boxes.
   auto keys16 = [&](int j, int len) { const int r = len - j * BKV; return r >= BKV ? BKV : (r + 15) & ~15; };
 
-  pdl_trigger();
   if (threadIdx.x == 0) {
     for (int s = 0; s < A::SLOTS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(q_bar, 1);
@@ -466,6 +465,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
   }
   tcgen05_fence_before();
   __syncthreads();
+  pdl_trigger();                               // FS2_PDL: the next kernel may start launching
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, A::TMEM_COLS);

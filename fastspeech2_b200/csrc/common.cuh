@@ -154,13 +154,13 @@ int fold_batchnorm(const float* gamma, const float* beta, const float* mean, con
                    float* scale, float* shift, cudaStream_t st);
 
 // ---- programmatic dependent launch (experiment, FS2_PDL=1; off by default) ---------------------
-// Every kernel of the step calls pdl_trigger() first (the next kernel of the stream may be scheduled as soon as this grid's
-// CTAs are all resident) and pdl_wait() before its first global-memory access (= the previous grid has completed and its
-// writes are visible), so that mbarrier init, TMEM allocation, tensor-map fetch and the launch latency itself overlap the tail
-// of the previous kernel.  Correct (tools/pdl_check.py: 30 graph replays per mode bit-identical to the eager step; the whole
-// GPU suite passes with it) but measured SLOWER inside the CUDA graph: 6.41 / 6.46 ms per c2 step against 6.30 / 6.22 without
-// (same box, alternating runs, gpurun_out/bench_g2_pdl*.json) -- early-resident CTAs of the next kernel compete with the
-// running one for the SM they spin on.  Without the launch attribute the device-side calls are no-ops.
+// Every kernel of the step calls pdl_wait() before its first global-memory access (= the previous grid has completed and its
+// writes are visible) and pdl_trigger() once its work is done (the persistent tcgen05 kernels) or first thing (the short
+// row-wise kernels), so that the launch latency, mbarrier init, TMEM allocation and tensor-map fetch of kernel k+1 overlap the
+// tail of kernel k.  Correct (tools/pdl_check.py: 30 graph replays per mode bit-identical to the eager step; the whole GPU
+// suite passes with it) but no gain inside the CUDA graph: with the trigger at kernel start 6.41 / 6.46 ms per c2 step against
+// 6.30 / 6.22 without (alternating runs on one box, profiles/r02_bench_r2j_pdl*.json); with the trigger at the end 6.68 / 6.59
+// against 6.83 / 6.55 (gpurun_out/bench_h2_pdl*.json) -- inside the noise.  Without the launch attribute the calls are no-ops.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 inline bool pdl_enabled() {

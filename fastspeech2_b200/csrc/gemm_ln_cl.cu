@@ -189,7 +189,6 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   const uint16_t mask_e = (uint16_t)((p.a_mc ? mask_a : (1u << rank)) | mask_b);
   const int n_readers = (p.a_mc ? 1 : 0) + MG;
 
-  pdl_trigger();
   if (threadIdx.x == 0) {
     for (int s = 0; s < L::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], n_readers); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
@@ -415,6 +414,7 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   tcgen05_fence_before();
   __syncthreads();
   cluster_sync_all();                          // no CTA leaves while its peer may still write into it
+  pdl_trigger();
   if (warp == 9) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, L::TMEM_COLS);

@@ -136,7 +136,6 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   const int steps = p.taps * kchunks;
   const int total_tiles = p.m_tiles * p.n_tiles;
 
-  pdl_trigger();
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int i = 0; i < C::NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4 * C::GROUPS); }
@@ -398,6 +397,7 @@ tap_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   }
   tcgen05_fence_before();
   __syncthreads();
+  pdl_trigger();                               // this CTA's work is done: the next kernel may start launching (FS2_PDL)
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
