@@ -2,7 +2,7 @@
 
   * trained-checkpoint statistics -- per-layer weights of magnitude 1e-3 .. 1e-2, LayerNorm gamma << 1, large BatchNorm
     running variances: durations and bucket ids bit-exact against the CPU oracle in every tensor-core mode;
-  * BASELINE config 4 at its full batch (B=32, L=2000);
+  * BASELINE config 4 at its full batch (B=32, L=2000), config 2 at full size with the batch-independence property;
   * a CUDA-graph replay after an eager call that re-allocated the model's workspace (ADVICE r01);
   * two devices driven from one process (per-device kernel attributes);
   * the sharded path on two GPUs against the per-shard oracle (SURVEY 8e caveat).
@@ -114,6 +114,37 @@ def test_config4_full_batch(weights):
         close(got[1].cpu()[valid], want[1][valid], TOL[prec], f"c4 after ({prec})")
         close(got[2], want[2], TOL["fp32"], f"c4 d_outs ({prec})")
         del m
+        torch.cuda.empty_cache()
+
+
+def test_config2_full_batch_oracle_and_batch_independence(weights):
+    """BASELINE config 2 -- the benchmarked shape, B=64, T=100, every utterance 800 frames -- at full size: (i) against the CPU
+    oracle, (ii) a size-independent property: with no padding in the batch an utterance's result does not depend on its batch
+    mates (every GEMM row, attention head, convolution window and LayerNorm row reads only its own utterance, and the K-loop
+    order of a row does not depend on which tile it sits in), so utterance b of the 64-batch must equal, BIT FOR BIT, the same
+    utterance synthesised alone -- in the fp32-class mode and in the f16 mode, and also through the captured CUDA graph."""
+    bt = make_batch(64, 100, 800, seed=1234)
+    torch.set_num_threads(min(32, os.cpu_count() or 1))
+    with torch.no_grad():
+        want = O.forward_path(weights, bt["xs"], bt["ilens"], bt["olens"], bt["ds"].clone(), bt["es"], bt["ps"], False)
+    for prec in ("3xtf32", "f16"):
+        m = FeedForwardTransformer(68, 80, load_hp(), precision=prec)
+        m.load_state_dict(weights, strict=True)
+        m = m.cuda().eval()
+        args = [bt[k].cuda() for k in KEYS]
+        with torch.no_grad():
+            got = [t.clone() for t in m._forward(*args, is_inference=False)]
+            close(got[1].cpu(), want[1], TOL[prec], f"c2 after ({prec})")
+            close(got[0].cpu(), want[0], TOL[prec], f"c2 before ({prec})")
+            close(got[2], want[2], TOL["fp32"], f"c2 d_outs ({prec})")
+            for b in (0, 17, 63):
+                one = m._forward(*[a[b:b + 1].contiguous() for a in args], is_inference=False)
+                for name, x, y in zip(("before", "after", "d_outs", "e_outs", "p_outs"), one, got):
+                    assert torch.equal(x[0], y[b]), f"{prec}: {name} of utterance {b} depends on its batch mates"
+            g = m.graphed_forward(*args)
+            rep = g(*args)
+            assert all(torch.equal(a, b_) for a, b_ in zip(rep, got)), f"{prec}: graph replay differs from the eager step at full size"
+        del m, g
         torch.cuda.empty_cache()
 
 
