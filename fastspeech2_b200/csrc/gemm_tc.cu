@@ -27,7 +27,8 @@
 //
 // One persistent CTA per SM walks the 128 x BN output tiles (n fastest, so concurrently running
 // CTAs share weight tiles in L2).  Three pipelines:
-//   smem ring   : warp 0 (TMA producer, one lane)  <-> warp 1 (MMA issuer, one lane), full/empty mbarriers
+//   smem ring   : warp 0 (TMA producer)  <-> warp 1 (MMA issuer), full/empty mbarriers; both run warp-convergent loops with one
+//                 lane elected inside each asm, and compute a stage's operands before waiting for it
 //   TMEM        : 2 (BN > 128) or 4 accumulator buffers; warp 1 fills buffer i % NACC while the epilogue drains older ones
 //   output      : two epilogue groups (warps 2-5 and 6-9; thread == output row == TMEM lane) take alternate
 //                 32-column chunks: tcgen05.ld -> bias / ReLU / tanh / residual in registers -> four
