@@ -33,3 +33,23 @@ def test_c_host_program_runs_bit_exact(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "C_ABI_OK" in r.stdout, r.stdout + r.stderr
     assert "sm_100a" in r.stdout
+
+
+@pytest.mark.skipif(shutil.which("cuobjdump") is None and not os.path.exists(os.path.join(CUDA, "bin", "cuobjdump")), reason="cuobjdump not available")
+def test_library_is_sm100a_tcgen05_code():
+    """What the shared library contains, read off its SASS (no GPU needed): sm_100a code only, 5th-generation tensor-core
+    instructions (UTCHMMA = tcgen05.mma) fed by TMA (UTMALDG) with TMEM loads in the epilogues (LDTM), and not a single legacy
+    warp-level HMMA -- i.e. the hot path is not a recompiled mma.sync / wmma kernel and not a library GEMM."""
+    exe = shutil.which("cuobjdump") or os.path.join(CUDA, "bin", "cuobjdump")
+    lib = os.path.join(LIBDIR, "libfs2b200.so")
+    assert os.path.exists(lib), "build the library first (python -m fastspeech2_b200.build)"
+    r = subprocess.run([exe, "-sass", lib], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    sass = r.stdout
+    archs = {ln.split("=")[1].strip() for ln in sass.splitlines() if ln.startswith("arch =")}
+    assert archs == {"sm_100a"}, archs
+    count = {m: sass.count(m) for m in ("UTCHMMA", "UTMALDG", "LDTM", "UTCBAR", "HMMA.")}
+    assert count["UTCHMMA"] > 100 and count["UTMALDG"] > 100 and count["LDTM"] > 10 and count["UTCBAR"] > 10, count
+    assert count["HMMA."] == 0, count
+    for kernel in ("tap_gemm_tf32_kernel", "gemm_ln_cluster_kernel", "attention_f16_kernel", "length_gather_kernel", "row_norm_kernel"):
+        assert kernel in sass, f"{kernel} missing from the library"
