@@ -83,6 +83,7 @@ struct CCfg {
 struct ClParams {
   int M, K;
   int a_mc;                                       // A tile fetched half / half by the two CTAs of a row tile (multicast)
+  int xasync;                                     // FS2_LN_XASYNC: statistics exchange by st.async + complete_tx instead of store + fence + remote arrive
   int prefetch;                                   // FS2_GEMM_PREFETCH (default 0: measured slower, see the producer loop): L2 prefetch of the next row tile's A planes and residual rows
   const float* bias; const float* gamma; const float* beta; float eps;
   int has_resid;
@@ -102,6 +103,11 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t ran
 }
 __device__ __forceinline__ void st_cluster_f32x2(uint32_t addr, float a, float b) {
   asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+// asynchronous store into a peer CTA's shared memory; its 8 bytes are credited to the peer's mbarrier when they have landed
+__device__ __forceinline__ void st_async_f32x2(uint32_t remote_addr, float a, float b, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+               ::"r"(remote_addr), "f"(a), "f"(b), "r"(remote_bar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
@@ -171,7 +177,8 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   uint64_t* r_full = acc_empty + 2;          // [RB <= 6]
   uint64_t* r_empty = r_full + 6;            // [RB]
   uint64_t* x_bar = r_empty + 6;             // statistics exchange, 16 warp arrivals (8 local + 8 from the peer) per tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_bar + 1);
+  uint64_t* xa_bar = x_bar + 1;              // [2] st.async form of the exchange (FS2_LN_XASYNC): 8 local warps + expect_tx, by tile parity
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xa_bar + 2);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -194,6 +201,7 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     for (int i = 0; i < L::RB; ++i) { mbar_init(&r_full[i], 1); mbar_init(&r_empty[i], 4); }
     mbar_init(x_bar, 16);
+    mbar_init(&xa_bar[0], 9); mbar_init(&xa_bar[1], 9);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 9) tmem_alloc(tmem_slot, L::TMEM_COLS);
@@ -360,14 +368,27 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       for (int i = 0; i < L::NT; ++i) { const float dd = y[i] - mean_t; m2_t = fmaf(dd, dd, m2_t); }
       const uint32_t xoff = (uint32_t)((((it & 1) * 4 + src) * BM + row) * 8);
       xchg[((it & 1) * 4 + src) * BM + row] = make_float2(mean_t, m2_t);
-      st_cluster_f32x2(x_remote + xoff, mean_t, m2_t);
-      __syncwarp();
-      if (lane == 0) {
-        asm volatile("fence.acq_rel.cluster;" ::: "memory");
-        mbar_arrive_cluster(map_to_cta(smem_u32(x_bar), rank));   // own barrier, same release scope
-        mbar_arrive_cluster(xbar_remote);
+      if (p.xasync) {
+        // The peer's copy travels as an asynchronous remote store that completes on the PEER's barrier (complete_tx, like a TMA
+        // load), so no cluster-scope fence is needed.  The fence of the other form (ERRBAR + CCTL.IVALL in SASS) waits for every
+        // earlier memory operation of the thread -- including the previous tile's 24 output stores -- and was 10 - 14 % of this
+        // kernel's stall samples.  Barriers alternate by tile parity: a CTA can be at most one tile ahead of its peer.
+        const int par = it & 1;
+        st_async_f32x2(x_remote + xoff, mean_t, m2_t, map_to_cta(smem_u32(&xa_bar[par]), rank ^ 1u));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xa_bar[par]);                 // this warp's local partials (release at CTA scope)
+        if (threadIdx.x == 0) mbar_expect_tx(&xa_bar[par], 8u * 32u * 8u);   // the peer's 256 threads x 8 bytes
+        mbar_wait_cluster(&xa_bar[par], (it >> 1) & 1);
+      } else {
+        st_cluster_f32x2(x_remote + xoff, mean_t, m2_t);
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("fence.acq_rel.cluster;" ::: "memory");
+          mbar_arrive_cluster(map_to_cta(smem_u32(x_bar), rank));   // own barrier, same release scope
+          mbar_arrive_cluster(xbar_remote);
+        }
+        mbar_wait_cluster(x_bar, it & 1);
       }
-      mbar_wait_cluster(x_bar, it & 1);
       float mean = 0.f, m2 = 0.f;
       float2 part[4];
 #pragma unroll
@@ -441,6 +462,7 @@ int launch_cl(const TapGemm& g, bool a_mc, cudaStream_t st) {
   p.M = (int)M; p.K = g.K; p.bias = g.bias; p.gamma = g.ln_gamma; p.beta = g.ln_beta; p.eps = g.ln_eps;
   p.a_mc = (a_mc || MG > 1) ? 1 : 0;
   p.has_resid = g.resid != nullptr;
+  { static int xa = -1; if (xa < 0) { const char* e = getenv("FS2_LN_XASYNC"); xa = e ? atoi(e) : 0; } p.xasync = xa; }
   { static int pfe = -1; if (pfe < 0) { const char* e = getenv("FS2_GEMM_PREFETCH"); pfe = e ? atoi(e) : 0; } p.prefetch = pfe; }
   p.out = g.out; p.ldo = g.ldo;
   p.outp = g.outp; p.ldo_p = g.ldo_p; p.outp_lo = (g.outp && g.outp_lo) ? g.outp + (long)M * g.ldo_p : nullptr;
